@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the speech front-end hot path (fbank + LFR + CMVN), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over one batch of synthetic audio: BASELINE.json configs[1], 256 utterances of
+1-30 s (16 kHz), length-packed, Paraformer-zh front-end (hamming, 80 mel, LFR 7/6, CMVN, dither 0).
+  value  audio-seconds per second with the batch resident in HBM (CUDA events, max over ranks)
+  e2e    the same through the reference-shaped API starting from pinned HOST PCM: H2D of the waveforms, the fused
+         kernels, D2H of the feature lengths (the features themselves stay in HBM for the acoustic model, which is
+         where the reference puts them too: funasr moves the CPU front-end's output to cuda:0)
+  roofline      algorithmic bytes of one launch / CUDA-event time of the fused tile kernel / measured HBM peak
+  cpu_baseline  the reference's CPU front-end (funasr WavFrontend over torchaudio kaldi.fbank) on this box's cores
+`--impl reference` times only that CPU implementation, on the same config/metric.
+N > 1: launched by torchrun, one rank per GPU, every rank owns its own 256-utterance shard (weak scaling, no
+data-path collective); rank 0 prints the single JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CONF = dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6)
+BATCH = 256
+WORKLOAD = "paraformer-zh front-end, 256 synthetic utterances 1-30 s @16 kHz, length-packed (BASELINE.json configs[1])"
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def synthetic_cmvn(dim=560, seed=7):
+    from toolbox_for_asr_and_tts_b200 import synth
+    u = (synth.uniform_pcm(seed, 1000, dim, amp=1.0) + 1.0) * 0.5
+    v = (synth.uniform_pcm(seed, 1001, dim, amp=1.0) + 1.0) * 0.5
+    return np.stack([-(8.0 + 4.0 * u), 0.2 + 0.3 * v]).astype(np.float32)
+
+
+def batch_layout(rank: int):
+    from toolbox_for_asr_and_tts_b200 import synth
+    lens = synth.utterance_lengths(rank, BATCH)           # seed = rank: every rank owns a different shard
+    offs, total = synth.packed_offsets(lens, align=4)
+    return lens, offs, int(total)
+
+
+def algorithmic_bytes(lens) -> int:
+    """float32 in + float32 valid rows out; padding, constants and lengths excluded."""
+    t = 1 + (lens - 400) // 160
+    rows = -(-t // 6)
+    return int((4 * lens + 4 * 560 * rows).sum())
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.dev) / 1000.0)
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+
+
+def cpu_reference_step(fe, waves, lens):
+    feats, flens = fe(waves, lens)
+    return feats
+
+
+def make_cpu_sample(lens, wave_host_flat, offs, n_utts):
+    waves = [wave_host_flat[int(o):int(o) + int(n)] for o, n in zip(offs[:n_utts], lens[:n_utts])]
+    return waves, [int(n) for n in lens[:n_utts]]
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, bounded sample."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import ref_thirdparty as ref
+    from toolbox_for_asr_and_tts_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    lens, offs, total = batch_layout(0)
+    n_utts = 32
+    waves = [synth.uniform_pcm(0, u, int(lens[u])) for u in range(n_utts)]
+    wl = [int(n) for n in lens[:n_utts]]
+    fe = ref.make_reference_frontend(synthetic_cmvn(), prefer_vllm=True, **CONF)
+    audio_s = sum(wl) / 16000.0
+    for _ in range(args.warmup):
+        fe(waves, wl)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fe(waves, wl)
+    dt = time.perf_counter() - t0
+    value = audio_s * args.steps / dt
+    sample = f"first {n_utts} of the 256 utterances ({audio_s:.0f} s of audio) per step, {fe.impl}, torch threads={torch.get_num_threads()}"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frontend": CONF, "dither": 0.0},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from toolbox_for_asr_and_tts_b200 import WavFrontend, _native
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    ops = _native.ops()
+
+    lens, offs, total = batch_layout(rank)
+    audio_s = float(lens.sum()) / 16000.0
+    alg_bytes = algorithmic_bytes(lens)
+    wave = torch.zeros(total + 8, dtype=torch.float32, device=dev)
+    ops.synth_uniform(wave, torch.from_numpy(offs), torch.from_numpy(lens), rank * 1000 + 1234, 0.3)
+    torch.cuda.synchronize()
+    fe = WavFrontend(cmvn=torch.from_numpy(synthetic_cmvn()), dither=0.0, **CONF)
+    lens_t, offs_t = torch.from_numpy(lens), torch.from_numpy(offs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+
+    # ---------------- device-resident throughput (`value`) + roofline of the fused kernel
+    for _ in range(args.warmup):
+        feats, flens = fe.forward_packed(wave, offs_t, lens_t)
+    barrier()
+    fe.profile(True)
+    launches0 = fe.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        feats, flens = fe.forward_packed(wave, offs_t, lens_t)
+    ev1.record()
+    barrier()
+    sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = fe.launch_count() - launches0
+    kern_ms, kern_n = fe.profile_collect()
+    fe.profile(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t[0])
+    value = audio_s * world * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end to end from pinned host PCM (`e2e`)
+    host = torch.empty(total + 8, dtype=torch.float32).pin_memory()
+    host.copy_(wave.cpu())
+    stage = torch.empty_like(wave)
+    lens_host = torch.empty(BATCH, dtype=torch.int64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(2):
+        stage.copy_(host, non_blocking=True)
+        f2, l2 = fe.forward_packed(stage, offs_t, lens_t)
+        lens_host.copy_(l2, non_blocking=True)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(e2e_steps):
+        stage.copy_(host, non_blocking=True)
+        f2, l2 = fe.forward_packed(stage, offs_t, lens_t)
+        lens_host.copy_(l2, non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the caller needs the lengths before it can go on
+    ev1.record()
+    barrier()
+    sampler.stop()
+    e2e_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[0])
+    e2e_value = audio_s * world * e2e_steps / (e2e_ms * 1e-3)
+    assert torch.equal(l2.cpu(), flens.cpu())
+
+    if rank != 0:
+        return
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (kern_ms / max(kern_n, 1) * 1e-3) / 1e9 if kern_n else None
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic_bytes_per_launch.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "kernel": "fbank_lfr_cmvn_tile_kernel", "kernel_ms_per_launch": kern_ms / max(kern_n, 1),
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernel_share_of_step": (kern_ms / ms_total) if ms_total else None}
+
+    # ---------------- the reference's CPU front-end on this box's cores, bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import ref_thirdparty as ref
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            n_utts = 64
+            waves, wl = make_cpu_sample(lens, host.numpy(), offs, n_utts)
+            cfe = ref.make_reference_frontend(synthetic_cmvn(), prefer_vllm=True, **CONF)
+            cfe(waves[:4], wl[:4])
+            best = None
+            t_start = time.perf_counter()
+            reps = 0
+            while reps < 5 and time.perf_counter() - t_start < 25.0:
+                t0 = time.perf_counter()
+                cfe(waves, wl)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+                reps += 1
+            cpu = {"value": sum(wl) / 16000.0 / best, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"first {n_utts} of the 256 utterances ({sum(wl) / 16000.0:.0f} s of audio), best of {reps}, "
+                             f"{cfe.impl} WavFrontend loop, torch threads={torch.get_num_threads()}"}
+        except Exception as e:  # torchaudio missing: the numpy restatement is the port
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"unavailable: {e!r}"[:200]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frontend": CONF, "dither": 0.0, "batch_per_gpu": BATCH,
+                       "audio_seconds_per_gpu_step": audio_s, "l2": "inputs_larger_than_l2 (264 MB in + 287 MB out per step vs 126 MB L2)",
+                       "input_layout": "length-packed float32, 16-byte aligned offsets", "output": "[256, 500, 560] float32, zero-padded"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
+                    "d2h_bytes_per_step": int(lens_host.numel() * 8), "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps,
+                    "note": "features stay in HBM for the acoustic model; only feature lengths return to the host"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+/*
+ * b200fe.h - C ABI of the B200-native speech front-end (libb200fe.so).
+ *
+ * This is the drop-in boundary for ONE path of terrense/toolbox-for-ASR-and-TTS: the speech front-end that
+ * `funasr.AutoModel(...).generate(input=np.float32[N])` runs on the CPU before the acoustic model
+ * (reference call sites R:voice-service/app/services/voice_interface.py:422-429,457,1370-1374,1585-1590,
+ * 2049-2053; R:voice-service/full_voice_demo.py:327,425,501).  The arithmetic lives in third-party code:
+ *   VF = vllm/transformers_utils/processors/funasr.py   (verbatim upstream funasr WavFrontend)
+ *   TA = torchaudio/compliance/kaldi.py
+ * Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every `*_dev` / device pointer is CUDA device memory owned by the caller;
+ *   - every call is asynchronous on the `cudaStream_t` passed as `void* stream` (NULL = default stream),
+ *     except b200fe_plan / b200fe_create / b200fe_destroy which are host-side;
+ *   - return value: 0 = OK, negative = error (B200FE_E_*); b200fe_last_error(handle) gives the text;
+ *   - no exceptions cross the ABI; there is NO CPU fallback: without a CUDA device create() fails;
+ *   - one handle may be used from several host threads only with distinct streams AND distinct workspaces.
+ */
+#ifndef B200FE_H_
+#define B200FE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FE_VERSION 1
+
+enum {
+  B200FE_OK = 0,
+  B200FE_E_INVALID = -1,      /* bad argument / option combination                                     */
+  B200FE_E_UNSUPPORTED = -2,  /* valid Kaldi option that the CUDA path does not implement               */
+  B200FE_E_CUDA = -3,         /* CUDA runtime error (text in b200fe_last_error)                          */
+  B200FE_E_WORKSPACE = -4,    /* workspace too small for the planned batch                              */
+  B200FE_E_SHORT = -5         /* an utterance is shorter than 2 samples (TA:142 assertion)              */
+};
+
+/* window_type, TA:86-113 (_feature_window_function) */
+enum { B200FE_WIN_HAMMING = 0, B200FE_WIN_HANNING = 1, B200FE_WIN_POVEY = 2, B200FE_WIN_RECTANGULAR = 3,
+       B200FE_WIN_BLACKMAN = 4 };
+
+/* Options of WavFrontend.__init__ (VF:92-123) + the Kaldi fbank options it forwards (TA:514-541). */
+typedef struct b200fe_config {
+  int32_t struct_size;        /* sizeof(b200fe_config), for ABI evolution                                */
+  int32_t sample_rate;        /* fs                      (VF:95, TA sample_frequency)  default 16000     */
+  float   frame_length_ms;    /* frame_length            (VF:98)                       default 25        */
+  float   frame_shift_ms;     /* frame_shift             (VF:99)                       default 10        */
+  int32_t n_mels;             /* n_mels / num_mel_bins   (VF:97)                       default 80        */
+  int32_t window_type;        /* window                  (VF:96) B200FE_WIN_*          default HAMMING   */
+  int32_t lfr_m;              /* lfr_m                   (VF:102)                      default 1         */
+  int32_t lfr_n;              /* lfr_n                   (VF:103)                      default 1         */
+  float   dither;             /* dither                  (VF:104)  0 = off                               */
+  int32_t snip_edges;         /* snip_edges              (VF:105)  only 1 is implemented                 */
+  int32_t upscale_samples;    /* upsacle_samples         (VF:106)  multiply input by 2^15                */
+  float   preemphasis;        /* preemphasis_coefficient (TA:527)                      default 0.97      */
+  int32_t remove_dc_offset;   /* remove_dc_offset        (TA:529)                      default 1         */
+  float   low_freq;           /* low_freq                (TA:524)                      default 20        */
+  float   high_freq;          /* high_freq (<=0: offset from Nyquist) (TA:522)         default 0         */
+  float   blackman_coeff;     /* blackman_coeff          (TA:516)                      default 0.42      */
+  float   log_floor;          /* floor applied to mel energies before log (TA:633): FLT_EPSILON          */
+  int32_t reserved[7];
+} b200fe_config;
+
+typedef struct b200fe_handle b200fe_handle;
+
+/* Fill `cfg` with the WavFrontend defaults above (Paraformer-zh would then set lfr_m=7, lfr_n=6, dither=0). */
+void b200fe_default_config(b200fe_config* cfg);
+
+/* Replaces WavFrontend.__init__ + load_cmvn's result (VF:92-123, VF:63-86).
+ * cmvn_host: NULL (no CMVN) or host float32 [2, n_mels*lfr_m]: row 0 = AddShift, row 1 = Rescale (VF:31-35).
+ * Builds the window (TA:86-113) and the mel filterbank (TA:436-511) once, on the host, and uploads them -
+ * the reference rebuilds both on every call (TA:201, TA:621). */
+int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handle** out);
+void b200fe_destroy(b200fe_handle* h);
+const char* b200fe_last_error(const b200fe_handle* h);   /* h may be NULL: error of the last failed create() */
+
+/* WavFrontend.output_size() (VF:125-126) = n_mels*lfr_m; and the derived sample counts (TA:137-140). */
+int b200fe_output_dim(const b200fe_handle* h);
+int b200fe_frame_samples(const b200fe_handle* h);        /* window_size   */
+int b200fe_shift_samples(const b200fe_handle* h);        /* window_shift  */
+int b200fe_fft_size(const b200fe_handle* h);             /* padded_window_size */
+
+/* Read back the tables built by create(), for parity tests against TA:86-113 / TA:436-511.
+ * window_out: [frame_samples] (without the 2^15 upscale), mel_out: [n_mels, fft_size/2] row-major. */
+int b200fe_get_tables(const b200fe_handle* h, float* window_out_host, float* mel_out_host);
+
+/* Frame / LFR-row counts for a batch, bit-exact with TA:65-70 (_get_strided) and VF:43 (apply_lfr), and the
+ * device workspace the batch needs.  lengths_host[i] = number of samples of utterance i.
+ * n_frames_out / n_rows_out may be NULL.  Utterances shorter than one frame follow VF:147's
+ * frame_length=min(frame_length, len/fs*1000) rule and yield one frame. */
+int b200fe_plan(b200fe_handle* h, const int64_t* lengths_host, int batch,
+                int64_t* n_frames_out, int64_t* n_rows_out, int64_t* max_rows_out, size_t* workspace_bytes);
+
+/* Replaces WavFrontend.forward (VF:128-168): fbank (TA:514-645) -> apply_lfr (VF:40-60) -> apply_cmvn (VF:23-37)
+ * -> pad_sequence, for a whole batch in one pass.
+ *   wave_dev      float32 PCM in [-1,1] (or already upscaled when upscale_samples=0)
+ *   offsets_host  [batch] start of utterance i inside wave_dev, in samples (length-packed buffers), or NULL
+ *                 for a dense [batch, row_stride] layout
+ *   lengths_host  [batch] samples per utterance (the reference takes lengths on the host too, VF:138)
+ *   wave_total    number of float32 elements addressable behind wave_dev (bounds the vector loads)
+ *   feats_dev     out, float32 [batch, rows_cap, output_dim]; rows >= n_rows[i] are zero-filled (pad_sequence)
+ *   feat_lens_dev out, int64 [batch] (VF:160), may be NULL
+ *   stats_dev     NULL, or float64 [2*output_dim + 1]: sum, sum of squares, row count of the un-normalised LFR
+ *                 features are ADDED to it (global CMVN statistics, funasr compute_audio_cmvn)
+ *   workspace_dev at least the bytes b200fe_plan reported for these lengths
+ */
+int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total,
+                   const int64_t* offsets_host, int64_t row_stride, const int64_t* lengths_host, int batch,
+                   float* feats_dev, int64_t rows_cap, int64_t* feat_lens_dev, double* stats_dev,
+                   uint64_t dither_seed, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Replaces WavFrontend.forward_lfr_cmvn (VF:198-218): LFR + CMVN of given [batch, frames_cap, n_mels] features. */
+int b200fe_lfr_cmvn(b200fe_handle* h, const float* fbank_dev, int64_t frames_cap, const int64_t* n_frames_host,
+                    int batch, float* feats_dev, int64_t rows_cap, int64_t* feat_lens_dev, void* workspace_dev,
+                    size_t workspace_bytes, void* stream);
+
+/* ---- streaming: replaces WavFrontendOnline.forward(input, lengths, cache=..., is_final=...) (upstream funasr
+ * wav_frontend.py, reached through vad_model.generate(cache=...) at R:voice-service/app/services/
+ * voice_interface.py:1585-1590) and the per-session np.concatenate accumulation at :1304-1311,1688-1746.
+ * The state slab keeps, per stream, the sample carry (input_cache), the LFR splice frames
+ * (lfr_splice_cache) and counters, resident in HBM. */
+int b200fe_stream_state_bytes(const b200fe_handle* h, int n_streams, int max_chunk_samples, size_t* bytes);
+int b200fe_stream_reset(b200fe_handle* h, void* state_dev, int n_streams, int max_chunk_samples,
+                        const int32_t* stream_ids_dev_or_null, int n, void* stream);
+/* chunks_dev [n, chunk_stride] float32; chunk_lens_dev [n]; stream_ids_dev [n] (distinct); is_final_dev [n] or
+ * NULL; feats_dev out [n, rows_cap, output_dim]; rows_out_dev out [n]. */
+int b200fe_stream_push(b200fe_handle* h, void* state_dev, int n_streams, int max_chunk_samples,
+                       const float* chunks_dev, int64_t chunk_stride, const int32_t* chunk_lens_dev,
+                       const int32_t* stream_ids_dev, const uint8_t* is_final_dev, int n,
+                       float* feats_dev, int64_t rows_cap, int32_t* rows_out_dev, void* stream);
+/* Upper bound of rows one push can emit for a chunk of max_chunk_samples (sizes rows_cap). */
+int b200fe_stream_max_rows(const b200fe_handle* h, int max_chunk_samples);
+
+/* ---- bench / test support: counter-based synthetic PCM, identical to synth.py on the host.
+ * x[u][n] = amp * (2*U01(hash(seed,u,n)) - 1) written at wave_dev[offsets_dev[u] + n], n < lengths_dev[u]. */
+int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int64_t* lengths_dev, int batch,
+                         uint64_t seed, float amp, void* stream);
+
+/* Kernel launches issued by this handle since create() (bench.py's gpu_launches). */
+int64_t b200fe_launch_count(const b200fe_handle* h);
+
+/* Roofline support: while enabled, every launch of the dominant (fused tile) kernel is bracketed by CUDA events
+ * recorded on the launching stream.  b200fe_profile_collect synchronises those events, returns the summed kernel
+ * time and the number of launches since the last collect, and clears the list. */
+int b200fe_profile_enable(b200fe_handle* h, int on);
+int b200fe_profile_collect(b200fe_handle* h, double* total_ms, int64_t* n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FE_H_ */

@@ -1,0 +1,334 @@
+"""GPU suite (-m gpu): the CUDA path against the oracle, the committed golden vectors and size-independent
+properties, all through the reference-shaped WavFrontend (torch extension -> C ABI -> sm_100a kernels) or through
+the raw C ABI with ctypes.  Nothing here reads /root/reference."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+from conftest import LOGMEL_ATOL, PARAFORMER
+
+from oracle import kaldi_fbank_np as kf
+from oracle import wav_frontend_np as wf
+from toolbox_for_asr_and_tts_b200 import StreamPool, WavFrontend, WavFrontendOnline, _native, stats_to_cmvn, synth
+
+pytestmark = pytest.mark.gpu
+SEED = 1234
+DEV = "cuda:0"
+
+
+def cmvn_atol(cmvn):
+    return LOGMEL_ATOL * float(np.abs(cmvn[1]).max())
+
+
+def make_fe(cmvn=None, **over):
+    conf = dict(PARAFORMER, dither=0.0)
+    conf.update(over)
+    return WavFrontend(cmvn=None if cmvn is None else torch.from_numpy(cmvn), **conf)
+
+
+def dense_batch(waves):
+    nmax = max(len(w) for w in waves)
+    buf = torch.zeros(len(waves), nmax)
+    for i, w in enumerate(waves):
+        buf[i, :len(w)] = torch.from_numpy(w)
+    return buf.to(DEV)
+
+
+def test_native_library_is_the_one_running():
+    ops = _native.ops()
+    assert torch.cuda.is_available()
+    fe = make_fe()
+    x = torch.zeros(1, 16000, device=DEV)
+    before = fe.launch_count()
+    fe(x, [16000])
+    assert fe.launch_count() > before
+
+
+def test_tables_match_reference_tables():
+    fe = make_fe()
+    win, mel = fe.tables()
+    assert np.abs(win.numpy() - kf.window_function("hamming", 400)).max() <= 5e-7
+    assert np.abs(mel.numpy() - kf.mel_banks(80, 512, 16000.0, dtype=np.float64)).max() <= 1e-7
+    try:
+        import torchaudio.compliance.kaldi as kaldi
+    except Exception:
+        return
+    w = kaldi._feature_window_function("hamming", 400, 0.42, torch.device("cpu"), torch.float32)
+    bank, _ = kaldi.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
+    assert (win - w).abs().max() <= 5e-7 and (mel - bank).abs().max() <= 3e-5
+
+
+@pytest.mark.parametrize("n", [399, 400, 401, 559, 560, 1000, 16000, 160000])
+def test_paraformer_against_golden(golden, cmvn, n):
+    fe = make_fe(cmvn)
+    x = torch.from_numpy(synth.uniform_pcm(SEED, n, n))[None].to(DEV)
+    feats, lens = fe(x, [n])
+    g = golden[f"paraformer_{n}"]
+    assert feats.dtype == torch.float32 and lens.dtype == torch.int64
+    assert tuple(feats.shape) == (1,) + g.shape and int(lens[0]) == g.shape[0]
+    err = np.abs(feats[0].cpu().numpy() - g).max()
+    assert err <= cmvn_atol(cmvn), err
+
+
+@pytest.mark.parametrize("n", [400, 16000])
+def test_povey_against_golden(golden, cmvn, n):
+    fe = make_fe(cmvn, window="povey")
+    x = torch.from_numpy(synth.uniform_pcm(SEED, n, n))[None].to(DEV)
+    feats, _ = fe(x, [n])
+    assert np.abs(feats[0].cpu().numpy() - golden[f"povey_{n}"]).max() <= cmvn_atol(cmvn)
+
+
+def test_forward_fbank_against_golden(golden):
+    fe = make_fe()
+    x = torch.from_numpy(synth.uniform_pcm(SEED, 16000, 16000))[None].to(DEV)
+    feats, lens = fe.forward_fbank(x, [16000])
+    assert tuple(feats.shape) == (1, 98, 80) and int(lens[0]) == 98
+    assert np.abs(feats[0].cpu().numpy() - golden["fbank_16000"]).max() <= LOGMEL_ATOL
+
+
+def test_ragged_batch_against_golden(golden, cmvn):
+    fe = make_fe(cmvn)
+    lens = golden["batch_input_lens"]
+    waves = [synth.uniform_pcm(SEED + 1, i, int(n)) for i, n in enumerate(lens)]
+    feats, flens = fe(dense_batch(waves), lens.tolist())
+    assert np.array_equal(flens.cpu().numpy(), golden["batch_lens"])
+    f = feats.cpu().numpy()
+    assert f.shape == golden["batch_feats"].shape
+    assert np.abs(f - golden["batch_feats"]).max() <= cmvn_atol(cmvn)
+    for i, k in enumerate(golden["batch_lens"]):
+        assert not f[i, k:].any()          # pad_sequence zeros, bit-exact
+
+
+def test_gaussian_with_dc_against_golden(golden, cmvn):
+    fe = make_fe(cmvn)
+    feats, _ = fe(torch.from_numpy(golden["gauss_input"])[None].to(DEV), [24000])
+    assert np.abs(feats[0].cpu().numpy() - golden["gauss_feats"]).max() <= cmvn_atol(cmvn)
+
+
+def test_counts_are_bit_exact_for_many_lengths():
+    fe = make_fe()
+    ns = list(range(400, 2400, 7)) + [15999, 16000, 16001, 479999, 480000]
+    nf, nr = fe.frame_counts(ns)
+    for n, a, b in zip(ns, nf.tolist(), nr.tolist()):
+        t = 1 + (n - 400) // 160
+        assert a == t and b == -(-t // 6), n
+
+
+def test_random_ragged_batch_against_oracle(cmvn):
+    """32 utterances, 0.2-6 s, against the oracle; log-mel error statistics are printed for DESIGN.md."""
+    fe = make_fe(cmvn)
+    lens = synth.utterance_lengths(21, 32, lo=3200, hi=96000)
+    waves = [synth.uniform_pcm(21, i, int(n)) for i, n in enumerate(lens)]
+    feats, flens = fe(dense_batch(waves), lens.tolist())
+    ref, rlens = wf.frontend_forward(waves, lens, cmvn=cmvn, **PARAFORMER)
+    assert np.array_equal(flens.cpu().numpy(), rlens)
+    d = np.abs(feats.cpu().numpy() - ref)
+    assert d.max() <= cmvn_atol(cmvn), d.max()
+    print("ragged batch: max-abs", d.max(), "mean-abs", d.mean())
+
+
+def test_packed_unaligned_offsets_equal_dense_bitwise(cmvn):
+    """Length-packed input with arbitrary (unaligned) offsets must give the dense-layout result bit for bit."""
+    fe = make_fe(cmvn)
+    lens = np.array([4001, 16003, 401, 7777, 32000, 1601], dtype=np.int64)
+    waves = [synth.uniform_pcm(31, i, int(n)) for i, n in enumerate(lens)]
+    dense, dl = fe(dense_batch(waves), lens.tolist())
+    for align, lead in ((1, 1), (1, 3), (4, 0), (2, 2)):
+        offs, total = synth.packed_offsets(lens, align=align)
+        offs = offs + lead
+        flat = torch.zeros(int(total) + lead + 8)
+        for o, w in zip(offs, waves):
+            flat[o:o + len(w)] = torch.from_numpy(w)
+        packed, pl = fe.forward_packed(flat.to(DEV), offs, lens)
+        assert torch.equal(pl, dl) and torch.equal(packed, dense), (align, lead)
+
+
+def test_short_utterances_follow_shrunken_frame_rule(cmvn):
+    """VF:147: frame_length = min(25, len/fs*1000): one frame, smaller window / FFT / mel bank."""
+    fe = make_fe(cmvn)
+    for n in (399, 300, 257, 256, 129, 64, 33):
+        x = synth.uniform_pcm(41, n, n)
+        feats, lens = fe(torch.from_numpy(x)[None].to(DEV), [n])
+        ref, rl = wf.frontend_forward([x], [n], cmvn=cmvn, **PARAFORMER)
+        assert int(lens[0]) == int(rl[0]) and tuple(feats.shape) == ref.shape
+        assert np.abs(feats.cpu().numpy() - ref).max() <= cmvn_atol(cmvn), n
+
+
+def test_forward_lfr_cmvn_is_bit_exact(cmvn):
+    fe = make_fe(cmvn)
+    rng = np.random.default_rng(3)
+    lens = [1, 5, 6, 7, 98, 333]
+    x = np.zeros((len(lens), max(lens), 80), dtype=np.float32)
+    for i, t in enumerate(lens):
+        x[i, :t] = rng.standard_normal((t, 80)).astype(np.float32) * 4 + 10
+    out, ol = fe.forward_lfr_cmvn(torch.from_numpy(x).to(DEV), lens)
+    for i, t in enumerate(lens):
+        ref = wf.apply_cmvn(wf.apply_lfr(x[i, :t], 7, 6), cmvn)
+        assert int(ol[i]) == ref.shape[0]
+        assert np.array_equal(out[i, :ref.shape[0]].cpu().numpy(), ref)
+        assert not out[i, ref.shape[0]:].any()
+
+
+def test_linearity_property_at_full_size():
+    """Size-independent property at BASELINE.json's full utterance size (30 s): the power spectrum is quadratic, so
+    scaling the input by 2 shifts every log-mel value by log(4) (well above the floor)."""
+    fe = make_fe(None, lfr_m=1, lfr_n=1)
+    x = torch.from_numpy(synth.uniform_pcm(51, 0, 480000))[None].to(DEV)
+    a, la = fe(x, [480000])
+    b, lb = fe(x * 2, [480000])
+    assert int(la[0]) == 2998 and torch.equal(la, lb)
+    assert (b - a - float(np.log(4.0))).abs().max() < 2e-5
+
+
+def test_time_shift_property():
+    """Dropping exactly one hop (160 samples) from the front shifts the frame sequence by one, bit for bit up to the
+    pairing of frames inside one FFT (tolerance covers that)."""
+    fe = make_fe(None, lfr_m=1, lfr_n=1)
+    w = synth.uniform_pcm(52, 0, 64000)
+    a, _ = fe(torch.from_numpy(w)[None].to(DEV), [64000])
+    b, _ = fe(torch.from_numpy(w[160:])[None].to(DEV), [64000 - 160])
+    assert (a[0, 1:] - b[0]).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("chunk", [9600, 3840, 6400, 960, 300])
+def test_streaming_concat_equals_offline(cmvn, chunk):
+    fe = make_fe(cmvn)
+    n_streams = 5
+    lens = [48000, 31999, 9600 * 3, 2000, 16000]
+    waves = [synth.uniform_pcm(61, i, n) for i, n in enumerate(lens)]
+    off, off_lens = fe(dense_batch(waves), lens)
+    pool = StreamPool(fe, n_streams=8, max_chunk_samples=9600, device=DEV)
+    got = [[] for _ in range(n_streams)]
+    pos = [0] * n_streams
+    while any(p < n for p, n in zip(pos, lens)):
+        ids, chunks, clens, fins = [], [], [], []
+        for s in range(n_streams):
+            if pos[s] < lens[s]:
+                m = min(chunk, lens[s] - pos[s])
+                c = np.zeros(9600, dtype=np.float32)
+                c[:m] = waves[s][pos[s]:pos[s] + m]
+                pos[s] += m
+                ids.append(s); chunks.append(c); clens.append(m); fins.append(1 if pos[s] >= lens[s] else 0)
+        feats, rows = pool.push(torch.from_numpy(np.stack(chunks)).to(DEV), torch.tensor(clens, dtype=torch.int32),
+                                torch.tensor(ids, dtype=torch.int32), torch.tensor(fins, dtype=torch.uint8))
+        rows = rows.cpu().tolist()
+        for k, s in enumerate(ids):
+            if rows[k]:
+                got[s].append(feats[k, :rows[k]].cpu())
+    for s in range(n_streams):
+        cat = torch.cat(got[s], dim=0) if got[s] else torch.zeros(0, 560)
+        assert cat.shape[0] == int(off_lens[s]), (s, chunk)
+        assert (cat - off[s, :cat.shape[0]].cpu()).abs().max() <= 2e-5, (s, chunk)
+
+
+def test_streaming_600ms_row_schedule_and_reference_shaped_api(cmvn):
+    """10 rows per 600 ms chunk from the first chunk on, 7 on the final flush, through the
+    upstream-shaped WavFrontendOnline.forward(input, lengths, cache=..., is_final=...)."""
+    fe = WavFrontendOnline(cmvn=torch.from_numpy(cmvn), max_chunk_samples=9600, **dict(PARAFORMER, dither=0.0))
+    off = make_fe(cmvn)
+    w = synth.uniform_pcm(62, 0, 160000)
+    full, fl = off(torch.from_numpy(w)[None].to(DEV), [160000])
+    cache, outs, per = {}, [], []
+    for s in range(0, 160000, 9600):
+        c = torch.from_numpy(w[s:s + 9600])[None].to(DEV)
+        f, l = fe(c, [c.shape[1]], cache=cache, is_final=(s + 9600 >= 160000))
+        per.append(int(l[0]))
+        if f.numel():
+            outs.append(f[0])
+    assert per[:3] == [10, 10, 10] and per[-1] == 7 and sum(per) == 167 == int(fl[0])
+    assert (torch.cat(outs) - full[0]).abs().max() <= 2e-5
+
+
+def test_global_cmvn_statistics():
+    """sum / sum of squares / count accumulated by the kernel equal float64 sums over the un-normalised features."""
+    fe = make_fe(None)
+    lens = synth.utterance_lengths(71, 24, lo=8000, hi=80000)
+    waves = [synth.uniform_pcm(71, i, int(n)) for i, n in enumerate(lens)]
+    stats = torch.zeros(2 * 560 + 1, dtype=torch.float64, device=DEV)
+    feats, fl = fe(dense_batch(waves), lens.tolist(), stats=stats)
+    rows = torch.cat([feats[i, :int(k)] for i, k in enumerate(fl)]).double()
+    ref = torch.cat([rows.sum(0), (rows * rows).sum(0), torch.tensor([float(rows.shape[0])], device=DEV, dtype=torch.float64)])
+    assert float(stats[-1]) == float(ref[-1])
+    rel = ((stats - ref).abs() / ref.abs().clamp(min=1.0)).max()
+    assert float(rel) < 1e-9, float(rel)
+    tab = stats_to_cmvn(stats)
+    normed = (rows.float().cpu() + tab[0]) * tab[1]
+    assert normed.mean(0).abs().max() < 1e-3 and (normed.std(0) - 1).abs().max() < 1e-2
+    # against the oracle's float64 statistics of its own features: equal within the feature tolerance
+    mats = [wf.frontend_forward([w], [len(w)], cmvn=None, **PARAFORMER)[0][0] for w in waves]
+    s, s2, n = wf.cmvn_stats(mats)
+    assert n == int(stats[-1])
+    assert np.abs(stats[:560].cpu().numpy() / n - s / n).max() < 1e-4
+
+
+def test_dither_is_statistically_kaldi_dither():
+    """dither != 0 cannot be bit-matched (TA:179-181 draws torch.randn per (frame, sample)); compare statistics on a
+    silent input, where the features are entirely the dither."""
+    fe = make_fe(None, lfr_m=1, lfr_n=1, dither=1.0)
+    n = 160000
+    x = torch.zeros(1, n, device=DEV)
+    a, _ = fe(x, [n])
+    b, _ = fe(x, [n])
+    assert not torch.equal(a, b)                     # new noise on every call, like torch.randn
+    rng = np.random.default_rng(0)
+    ref = kf.fbank(np.zeros(n, dtype=np.float32), num_mel_bins=80, dither=1.0, energy_floor=0.0, window_type="hamming",
+                   rng=rng)
+    got = a[0].cpu().numpy()
+    assert np.abs(got.mean(0) - ref.mean(0)).max() < 0.08
+    assert np.abs(got.std(0) - ref.std(0)).max() < 0.08
+    fe2 = make_fe(None, lfr_m=1, lfr_n=1, dither=1.0, dither_seed=5)
+    fe3 = make_fe(None, lfr_m=1, lfr_n=1, dither=1.0, dither_seed=5)
+    assert torch.equal(fe2(x, [n])[0], fe3(x, [n])[0])   # reproducible from the seed
+
+
+def test_cpu_tensor_is_rejected_and_unsupported_options_raise():
+    fe = make_fe()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fe(torch.zeros(1, 16000), [16000])
+    with pytest.raises(NotImplementedError):
+        make_fe(None, snip_edges=False)(torch.zeros(1, 16000, device=DEV), [16000])
+    with pytest.raises(RuntimeError, match="window size"):
+        fe(torch.zeros(1, 16, device=DEV), [1])
+
+
+def test_raw_c_abi_with_ctypes(cmvn):
+    """The C ABI as a foreign caller would use it: plain pointers and sizes, no torch types in the signatures."""
+    lib = _native.cdll()
+
+    class Cfg(ctypes.Structure):
+        _fields_ = [("struct_size", ctypes.c_int32), ("sample_rate", ctypes.c_int32), ("frame_length_ms", ctypes.c_float),
+                    ("frame_shift_ms", ctypes.c_float), ("n_mels", ctypes.c_int32), ("window_type", ctypes.c_int32),
+                    ("lfr_m", ctypes.c_int32), ("lfr_n", ctypes.c_int32), ("dither", ctypes.c_float),
+                    ("snip_edges", ctypes.c_int32), ("upscale_samples", ctypes.c_int32), ("preemphasis", ctypes.c_float),
+                    ("remove_dc_offset", ctypes.c_int32), ("low_freq", ctypes.c_float), ("high_freq", ctypes.c_float),
+                    ("blackman_coeff", ctypes.c_float), ("log_floor", ctypes.c_float), ("reserved", ctypes.c_int32 * 7)]
+    c = Cfg()
+    lib.b200fe_default_config(ctypes.byref(c))
+    c.lfr_m, c.lfr_n, c.dither = 7, 6, 0.0
+    h = ctypes.c_void_p()
+    cm = np.ascontiguousarray(cmvn, dtype=np.float32)
+    lib.b200fe_last_error.restype = ctypes.c_char_p
+    rc = lib.b200fe_create(ctypes.byref(c), cm.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h))
+    assert rc == 0, lib.b200fe_last_error(None)
+    try:
+        n = 16000
+        lens = (ctypes.c_int64 * 1)(n)
+        nf, nr, mx = (ctypes.c_int64 * 1)(), (ctypes.c_int64 * 1)(), ctypes.c_int64()
+        ws = ctypes.c_size_t()
+        assert lib.b200fe_plan(h, lens, 1, nf, nr, ctypes.byref(mx), ctypes.byref(ws)) == 0
+        assert (nf[0], nr[0], mx.value) == (98, 17, 17)
+        x = torch.from_numpy(synth.uniform_pcm(SEED, n, n)).to(DEV)
+        feats = torch.empty(1, 17, 560, device=DEV)
+        flen = torch.empty(1, dtype=torch.int64, device=DEV)
+        work = torch.empty(max(ws.value, 256), dtype=torch.uint8, device=DEV)
+        rc = lib.b200fe_forward(h, ctypes.c_void_p(x.data_ptr()), ctypes.c_int64(n), None, ctypes.c_int64(n), lens, 1,
+                                ctypes.c_void_p(feats.data_ptr()), ctypes.c_int64(17), ctypes.c_void_p(flen.data_ptr()),
+                                None, ctypes.c_uint64(0), ctypes.c_void_p(work.data_ptr()), ctypes.c_size_t(work.numel()),
+                                None)
+        assert rc == 0, lib.b200fe_last_error(h)
+        torch.cuda.synchronize()
+        g = dict(np.load(__import__("conftest").GOLDEN))["paraformer_16000"]
+        assert int(flen[0]) == 17 and np.abs(feats[0].cpu().numpy() - g).max() <= cmvn_atol(cmvn)
+    finally:
+        lib.b200fe_destroy(h)

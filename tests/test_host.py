@@ -1,0 +1,137 @@
+"""CPU suite, part 2: host logic and the C-ABI library surface (no compute calls - there is no GPU here)."""
+import ctypes
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from toolbox_for_asr_and_tts_b200 import _native, sharding, synth
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _native.cdll()
+    syms = _native.declared_symbols()
+    assert len(syms) >= 18
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_default_config_matches_reference_defaults():
+    """VF:92-107 defaults, through the C struct."""
+    lib = _native.cdll()
+
+    class Cfg(ctypes.Structure):
+        _fields_ = [("struct_size", ctypes.c_int32), ("sample_rate", ctypes.c_int32), ("frame_length_ms", ctypes.c_float),
+                    ("frame_shift_ms", ctypes.c_float), ("n_mels", ctypes.c_int32), ("window_type", ctypes.c_int32),
+                    ("lfr_m", ctypes.c_int32), ("lfr_n", ctypes.c_int32), ("dither", ctypes.c_float),
+                    ("snip_edges", ctypes.c_int32), ("upscale_samples", ctypes.c_int32), ("preemphasis", ctypes.c_float),
+                    ("remove_dc_offset", ctypes.c_int32), ("low_freq", ctypes.c_float), ("high_freq", ctypes.c_float),
+                    ("blackman_coeff", ctypes.c_float), ("log_floor", ctypes.c_float), ("reserved", ctypes.c_int32 * 7)]
+    c = Cfg()
+    lib.b200fe_default_config(ctypes.byref(c))
+    assert c.struct_size == ctypes.sizeof(Cfg)
+    assert (c.sample_rate, c.n_mels, c.window_type, c.lfr_m, c.lfr_n) == (16000, 80, 0, 1, 1)
+    assert (c.frame_length_ms, c.frame_shift_ms, c.dither) == (25.0, 10.0, 1.0)
+    assert c.snip_edges == 1 and c.upscale_samples == 1 and c.remove_dc_offset == 1
+    assert abs(c.preemphasis - 0.97) < 1e-7 and c.low_freq == 20.0 and c.high_freq == 0.0
+    assert c.log_floor == np.finfo(np.float32).eps
+
+
+def test_create_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from toolbox_for_asr_and_tts_b200 import WavFrontend
+    fe = WavFrontend(lfr_m=7, lfr_n=6, dither=0.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fe(torch.zeros(1, 16000), [16000])
+
+
+def test_invalid_window_raises_like_reference():
+    from toolbox_for_asr_and_tts_b200 import WavFrontend
+    with pytest.raises(Exception, match="Invalid window type"):
+        WavFrontend(window="kaiser")
+
+
+def test_synth_is_deterministic_and_bounded():
+    a = synth.uniform_pcm(1234, 7, 5000)
+    b = synth.uniform_pcm(1234, 7, 5000)
+    assert np.array_equal(a, b) and a.dtype == np.float32
+    assert np.abs(a).max() <= 0.3 and abs(float(a.mean())) < 0.02 and 0.16 < float(a.std()) < 0.18
+    assert not np.array_equal(a, synth.uniform_pcm(1234, 8, 5000))
+    assert np.array_equal(a[:100], synth.uniform_pcm(1234, 7, 100))   # counter based: prefix-stable
+    lens = synth.utterance_lengths(0, 256)
+    assert lens.min() >= 16000 and lens.max() <= 480000
+    offs, total = synth.packed_offsets(lens)
+    assert (offs % 4 == 0).all() and total >= lens.sum() and (np.diff(offs) >= lens[:-1]).all()
+
+
+def test_partition_is_balanced_and_complete():
+    lens = synth.utterance_lengths(3, 257)
+    parts = sharding.partition_utterances(lens, 8)
+    allidx = np.sort(np.concatenate(parts))
+    assert np.array_equal(allidx, np.arange(257))
+    loads = np.array([lens[p].sum() for p in parts])
+    assert loads.max() - loads.min() <= lens.max()
+    assert sharding.stream_owner(4095, 8) == 7 and sharding.stream_owner(8, 8) == 0
+
+
+def test_stats_to_cmvn():
+    from toolbox_for_asr_and_tts_b200 import stats_to_cmvn
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1000, 6)) * 2 + 3
+    stats = torch.tensor(np.concatenate([x.sum(0), (x * x).sum(0), [1000.0]]), dtype=torch.float64)
+    tab = stats_to_cmvn(stats).numpy()
+    assert np.allclose(tab[0], -x.mean(0), atol=1e-5) and np.allclose(tab[1], 1 / x.std(0), atol=1e-5)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO_ROOT"])
+from toolbox_for_asr_and_tts_b200 import sharding, synth
+from oracle import wav_frontend_np as wf
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+lens = synth.utterance_lengths(11, 12, lo=2000, hi=9000)
+mine = sharding.partition_utterances(lens, world)[rank]
+conf = dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6)
+mats = []
+for u in mine:
+    f, l = wf.frontend_forward([synth.uniform_pcm(11, int(u), int(lens[u]))], [int(lens[u])], cmvn=None, **conf)
+    mats.append(f[0])
+s, s2, n = wf.cmvn_stats(mats)
+stats = torch.tensor(np.concatenate([s, s2, [float(n)]]), dtype=torch.float64)
+sharding.allreduce_stats(stats)
+if rank == 0:
+    allm = []
+    for u in range(len(lens)):
+        f, l = wf.frontend_forward([synth.uniform_pcm(11, u, int(lens[u]))], [int(lens[u])], cmvn=None, **conf)
+        allm.append(f[0])
+    S, S2, N = wf.cmvn_stats(allm)
+    ref = np.concatenate([S, S2, [float(N)]])
+    got = stats.numpy()
+    assert got[-1] == ref[-1], (got[-1], ref[-1])
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-12
+    print("GLOO_OK", int(got[-1]))
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharding_and_stats_allreduce(tmp_path):
+    """world_size 2 on CPU: utterances are sharded without any data-path collective; the one collective (CMVN statistics)
+    reproduces the single-process float64 sums."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, REPO_ROOT=str(ROOT), MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", WORLD_SIZE="2",
+               OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GLOO_OK" in outs[0]

@@ -1,0 +1,544 @@
+// libb200fe.so - host side of the C ABI declared in include/b200fe.h.
+//
+// No torch types here: plain pointers, sizes and a cudaStream_t.  There is no CPU fallback: every entry point that
+// computes launches sm_100a kernels, and create() fails when no CUDA device is present.
+#include "../../include/b200fe.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "fbank_tile.cuh"
+#include "stream_kernel.cuh"
+
+using namespace b200fe;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct PinnedSlot {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool busy = false;
+};
+
+}  // namespace
+
+struct b200fe_handle {
+  b200fe_config cfg;
+  int L = 0, S = 0, nfft = 0, D = 0, rows_per_tile = 0, e_cap = 0;
+  size_t smem_bytes = 0;
+  int n_sms = 0;
+  bool has_cmvn = false;
+  std::vector<float> window_host;   // [L], without upscale
+  std::vector<float> mel_host;      // [n_mels, nfft/2]
+  float* d_window = nullptr;        // [512]
+  float2* d_twiddle = nullptr;      // [17*16]
+  float* d_mel_w = nullptr;         // [kMaxNnz]
+  int* d_mel_desc = nullptr;        // [kMaxMels]
+  float* d_cmvn = nullptr;          // [2*D]
+  // dense mel banks for shrunken frames (VF:147), keyed by fft size
+  std::map<int, int> short_mel_off;
+  float* d_short_mel = nullptr;
+  size_t short_mel_floats = 0;
+  std::mutex mu;
+  PinnedSlot slots[4];
+  int next_slot = 0;
+  long long launches = 0;
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  mutable std::string err;
+};
+
+namespace {
+
+int fail(const b200fe_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(h, B200FE_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+  } while (0)
+
+int next_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return x == 0 ? 1 : p;
+}
+
+// TA:86-113, evaluated in double and rounded once
+void build_window(int type, int n, double blackman, std::vector<float>& w) {
+  w.resize(n);
+  const double a = 2.0 * M_PI / (n - 1);
+  for (int i = 0; i < n; ++i) {
+    double v;
+    switch (type) {
+      case B200FE_WIN_HAMMING: v = 0.54 - 0.46 * cos(a * i); break;
+      case B200FE_WIN_HANNING: v = 0.5 - 0.5 * cos(a * i); break;
+      case B200FE_WIN_POVEY: v = pow((double)(float)(0.5 - 0.5 * cos(a * i)), 0.85); break;
+      case B200FE_WIN_RECTANGULAR: v = 1.0; break;
+      default: v = blackman - 0.5 * cos(a * i) + (0.5 - blackman) * cos(2 * a * i); break;
+    }
+    w[i] = (float)v;
+  }
+}
+
+// TA:436-511 (vtln_warp = 1): triangular filters in the mel domain, [n_mels, nfft/2]
+int build_mel(int n_mels, int nfft, double fs, double low, double high, std::vector<float>& bank) {
+  const int nb = nfft / 2;
+  const double nyq = 0.5 * fs;
+  if (high <= 0.0) high += nyq;
+  if (!(0.0 <= low && low < nyq && 0.0 < high && high <= nyq && low < high)) return -1;
+  const double bw = fs / nfft;
+  const double mlo = 1127.0 * log(1.0 + low / 700.0), mhi = 1127.0 * log(1.0 + high / 700.0);
+  const double delta = (mhi - mlo) / (n_mels + 1);
+  bank.assign((size_t)n_mels * nb, 0.f);
+  for (int m = 0; m < n_mels; ++m) {
+    const double left = mlo + m * delta, center = mlo + (m + 1.0) * delta, right = mlo + (m + 2.0) * delta;
+    for (int k = 0; k < nb; ++k) {
+      const double mel = 1127.0 * log(1.0 + bw * k / 700.0);
+      const double up = (mel - left) / (center - left), down = (right - mel) / (right - center);
+      const double v = fmax(0.0, fmin(up, down));
+      bank[(size_t)m * nb + k] = (float)v;
+    }
+  }
+  return 0;
+}
+
+int frame_count(long long n, int win, int shift) { return n < win ? 0 : (int)(1 + (n - win) / shift); }
+int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// VF:147 + TA:137-139: window size of an utterance shorter than the configured frame
+int short_window(const b200fe_config& c, long long n) {
+  const double fl = (double)n / (double)c.sample_rate * 1000.0;
+  return (int)((double)c.sample_rate * fl * 0.001);
+}
+
+struct Plan {
+  std::vector<UttDesc> utts;
+  std::vector<ShortDesc> shorts;
+  int n_tiles = 0;
+  long long max_rows = 0;
+  long long total_rows = 0;
+};
+
+int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, int64_t row_stride, int batch,
+              Plan& pl) {
+  pl.utts.resize(batch);
+  pl.shorts.clear();
+  int tile = 0;
+  for (int u = 0; u < batch; ++u) {
+    const long long n = lengths[u];
+    UttDesc d;
+    d.wave_off = offsets ? offsets[u] : (long long)u * row_stride;
+    d.n_samples = (int)n;
+    d.tile_begin = tile;
+    if (n >= h->L) {
+      d.n_frames = frame_count(n, h->L, h->S);
+      d.n_rows = ceil_div(d.n_frames, h->cfg.lfr_n);
+      tile += ceil_div(d.n_rows, h->rows_per_tile);
+    } else {
+      const int win = short_window(h->cfg, n);
+      if (win < 2 || win > n) return fail(h, B200FE_E_SHORT, "choose a window size " + std::to_string(win) +
+                                          " that is [2, " + std::to_string(n) + "]");
+      ShortDesc s;
+      s.wave_off = d.wave_off;
+      s.utt = u;
+      s.n_samples = (int)n;
+      s.win = win;
+      s.nfft = next_pow2(win);
+      s.n_frames = frame_count(n, win, h->S);
+      s.n_rows = ceil_div(s.n_frames, h->cfg.lfr_n);
+      s.mel_off = 0;
+      pl.shorts.push_back(s);
+      d.n_frames = 0;          // the tile kernel skips it (no tiles); rows come from the short path
+      d.n_rows = s.n_rows;
+    }
+    pl.max_rows = d.n_rows > pl.max_rows ? d.n_rows : pl.max_rows;
+    pl.total_rows += d.n_rows;
+    pl.utts[u] = d;
+  }
+  pl.n_tiles = tile;
+  return 0;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+size_t workspace_need(int batch) { return align256((size_t)batch * sizeof(UttDesc)) + align256((size_t)batch * sizeof(ShortDesc)); }
+
+// stream-ordered upload through a small ring of pinned buffers
+int upload(b200fe_handle* h, const void* src, size_t bytes, void* dst, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  PinnedSlot& s = h->slots[h->next_slot];
+  h->next_slot = (h->next_slot + 1) & 3;
+  if (s.busy) {
+    CUDA_TRY(h, cudaEventSynchronize(s.ev));
+    s.busy = false;
+  }
+  if (s.cap < bytes) {
+    if (s.ptr) cudaFreeHost(s.ptr);
+    s.ptr = nullptr;
+    s.cap = 0;
+    size_t cap = bytes < 65536 ? 65536 : bytes * 2;
+    CUDA_TRY(h, cudaMallocHost(&s.ptr, cap));
+    s.cap = cap;
+  }
+  if (!s.ev) CUDA_TRY(h, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  memcpy(s.ptr, src, bytes);
+  CUDA_TRY(h, cudaMemcpyAsync(dst, s.ptr, bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaEventRecord(s.ev, st));
+  s.busy = true;
+  return 0;
+}
+
+template <int NROWS, bool EXACT>
+int launch_tile(b200fe_handle* h, const TileParams& p, int grid, bool dither, bool stats, cudaStream_t st) {
+#define LAUNCH(DI, STT)                                                                                         \
+  do {                                                                                                          \
+    auto k = fbank_lfr_cmvn_tile_kernel<NROWS, EXACT, DI, STT>;                                                 \
+    CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));      \
+    k<<<grid, kCtaThreads, h->smem_bytes, st>>>(p);                                                             \
+  } while (0)
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profile) {
+    CUDA_TRY(h, cudaEventCreate(&e0));
+    CUDA_TRY(h, cudaEventCreate(&e1));
+    CUDA_TRY(h, cudaEventRecord(e0, st));
+  }
+  if (dither) { if (stats) LAUNCH(true, true); else LAUNCH(true, false); }
+  else        { if (stats) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+  if (h->profile) {
+    CUDA_TRY(h, cudaEventRecord(e1, st));
+    h->prof_events.emplace_back(e0, e1);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int ensure_short_banks(b200fe_handle* h, Plan& pl, cudaStream_t st) {
+  bool grow = false;
+  for (auto& s : pl.shorts)
+    if (!h->short_mel_off.count(s.nfft)) grow = true;
+  if (grow) {
+    // (re)build all banks for fft sizes 2..512; 80 * (1+2+..+256) floats = 164 KB, once per handle
+    std::vector<float> all;
+    for (int nfft = 2; nfft <= 512; nfft <<= 1) {
+      std::vector<float> b;
+      if (build_mel(h->cfg.n_mels, nfft, h->cfg.sample_rate, h->cfg.low_freq, h->cfg.high_freq, b) != 0)
+        return fail(h, B200FE_E_INVALID, "bad low/high frequency");
+      h->short_mel_off[nfft] = (int)all.size();
+      all.insert(all.end(), b.begin(), b.end());
+    }
+    CUDA_TRY(h, cudaMalloc(&h->d_short_mel, all.size() * sizeof(float)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_short_mel, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    h->short_mel_floats = all.size();
+  }
+  for (auto& s : pl.shorts) s.mel_off = h->short_mel_off[s.nfft];
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void b200fe_default_config(b200fe_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(b200fe_config);
+  c->sample_rate = 16000;
+  c->frame_length_ms = 25.f;
+  c->frame_shift_ms = 10.f;
+  c->n_mels = 80;
+  c->window_type = B200FE_WIN_HAMMING;
+  c->lfr_m = 1;
+  c->lfr_n = 1;
+  c->dither = 1.0f;
+  c->snip_edges = 1;
+  c->upscale_samples = 1;
+  c->preemphasis = 0.97f;
+  c->remove_dc_offset = 1;
+  c->low_freq = 20.f;
+  c->high_freq = 0.f;
+  c->blackman_coeff = 0.42f;
+  c->log_floor = 1.1920928955078125e-07f;
+}
+
+int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handle** out) {
+  if (!cfg || !out) return fail(nullptr, B200FE_E_INVALID, "null argument");
+  if (cfg->struct_size != (int32_t)sizeof(b200fe_config)) return fail(nullptr, B200FE_E_INVALID, "b200fe_config size mismatch");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, B200FE_E_CUDA, "no CUDA device: the B200 front-end has no CPU fallback");
+  const int L = (int)((double)cfg->sample_rate * (double)cfg->frame_length_ms * 0.001);
+  const int S = (int)((double)cfg->sample_rate * (double)cfg->frame_shift_ms * 0.001);
+  if (L < 2 || S <= 0) return fail(nullptr, B200FE_E_INVALID, "bad frame length / shift");
+  const int nfft = next_pow2(L);
+  if (nfft != kNfft) return fail(nullptr, B200FE_E_UNSUPPORTED, "only frames that pad to a 512-point FFT are implemented (257..512 samples)");
+  if (cfg->n_mels < 4 || cfg->n_mels > kMaxMels || (cfg->n_mels & 3)) return fail(nullptr, B200FE_E_UNSUPPORTED, "n_mels must be a multiple of 4 in [4, 128]");
+  if (cfg->lfr_m < 1 || cfg->lfr_n < 1 || cfg->lfr_m > kFMax) return fail(nullptr, B200FE_E_INVALID, "bad lfr_m / lfr_n");
+  if (cfg->lfr_m * cfg->n_mels > 8 * kCtaThreads) return fail(nullptr, B200FE_E_UNSUPPORTED, "n_mels*lfr_m > 1024");
+  if (!cfg->snip_edges) return fail(nullptr, B200FE_E_UNSUPPORTED, "snip_edges=False is not implemented");
+  if (cfg->window_type < 0 || cfg->window_type > B200FE_WIN_BLACKMAN) return fail(nullptr, B200FE_E_INVALID, "Invalid window type");
+  if (!(cfg->preemphasis >= 0.f && cfg->preemphasis <= 1.f)) return fail(nullptr, B200FE_E_INVALID, "`preemphasis_coefficient` must be between [0,1]");
+
+  b200fe_handle* h = new b200fe_handle();
+  h->cfg = *cfg;
+  h->L = L; h->S = S; h->nfft = nfft;
+  h->D = cfg->lfr_m * cfg->n_mels;
+  h->rows_per_tile = (kFMax - cfg->lfr_m) / cfg->lfr_n + 1;
+  h->e_cap = (((kFMax - 1) * S + L + 8) + 3) & ~3;
+  h->smem_bytes = tile_smem_bytes(h->e_cap, cfg->n_mels);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, dev);
+  h->n_sms = prop.multiProcessorCount;
+  if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+    delete h;
+    return fail(nullptr, B200FE_E_UNSUPPORTED, "frame shift too large for the shared-memory tile");
+  }
+  auto bail = [&](int code, const std::string& m) { b200fe_destroy(h); return fail(nullptr, code, m); };
+#define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(B200FE_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } while (0)
+
+  build_window(cfg->window_type, L, cfg->blackman_coeff, h->window_host);
+  std::vector<float> win512(512, 0.f);
+  const float up = cfg->upscale_samples ? 32768.f : 1.f;
+  for (int i = 0; i < L; ++i) win512[i] = h->window_host[i] * up;   // power-of-two scale: exact
+  if (build_mel(cfg->n_mels, nfft, cfg->sample_rate, cfg->low_freq, cfg->high_freq, h->mel_host) != 0)
+    return bail(B200FE_E_INVALID, "Bad values in options: low-freq / high-freq vs. nyquist");
+
+  // sparse filterbank: per filter a contiguous run of non-zero bins
+  std::vector<float> mw(kMaxNnz, 0.f);
+  std::vector<int> md(kMaxMels, 0);
+  int off = 0;
+  const int nb = nfft / 2;
+  for (int m = 0; m < cfg->n_mels; ++m) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < nb; ++k)
+      if (h->mel_host[(size_t)m * nb + k] > 0.f) { if (lo < 0) lo = k; hi = k; }
+    const int cnt = lo < 0 ? 0 : hi - lo + 1;
+    if (lo == 0 || off + cnt > kMaxNnz) return bail(B200FE_E_UNSUPPORTED, "mel filterbank does not fit the sparse layout");
+    for (int q = 0; q < cnt; ++q) mw[off + q] = 0.25f * h->mel_host[(size_t)m * nb + lo + q];
+    md[m] = (lo < 0 ? 1 : lo) | (cnt << 9) | (off << 18);
+    off += cnt;
+  }
+  std::vector<float2> tw(17 * 16);
+  for (int r = 0; r < 17; ++r)
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const int ph = (n2 * r) & 511;
+      tw[r * 16 + n2] = make_float2((float)cos(2.0 * M_PI * ph / 512.0), (float)(-sin(2.0 * M_PI * ph / 512.0)));
+    }
+  CK(cudaMalloc(&h->d_window, 512 * sizeof(float)));
+  CK(cudaMalloc(&h->d_twiddle, tw.size() * sizeof(float2)));
+  CK(cudaMalloc(&h->d_mel_w, kMaxNnz * sizeof(float)));
+  CK(cudaMalloc(&h->d_mel_desc, kMaxMels * sizeof(int)));
+  CK(cudaMemcpy(h->d_window, win512.data(), 512 * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_mel_w, mw.data(), kMaxNnz * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_mel_desc, md.data(), kMaxMels * sizeof(int), cudaMemcpyHostToDevice));
+  if (cmvn_host) {
+    CK(cudaMalloc(&h->d_cmvn, 2 * h->D * sizeof(float)));
+    CK(cudaMemcpy(h->d_cmvn, cmvn_host, 2 * h->D * sizeof(float), cudaMemcpyHostToDevice));
+    h->has_cmvn = true;
+  }
+#undef CK
+  *out = h;
+  return B200FE_OK;
+}
+
+void b200fe_destroy(b200fe_handle* h) {
+  if (!h) return;
+  cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_mel_w); cudaFree(h->d_mel_desc);
+  cudaFree(h->d_cmvn); cudaFree(h->d_short_mel);
+  for (auto& s : h->slots) {
+    if (s.ev) { cudaEventSynchronize(s.ev); cudaEventDestroy(s.ev); }
+    if (s.ptr) cudaFreeHost(s.ptr);
+  }
+  delete h;
+}
+
+const char* b200fe_last_error(const b200fe_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int b200fe_output_dim(const b200fe_handle* h) { return h ? h->D : B200FE_E_INVALID; }
+int b200fe_frame_samples(const b200fe_handle* h) { return h ? h->L : B200FE_E_INVALID; }
+int b200fe_shift_samples(const b200fe_handle* h) { return h ? h->S : B200FE_E_INVALID; }
+int b200fe_fft_size(const b200fe_handle* h) { return h ? h->nfft : B200FE_E_INVALID; }
+int64_t b200fe_launch_count(const b200fe_handle* h) { return h ? h->launches : 0; }
+
+int b200fe_profile_enable(b200fe_handle* h, int on) {
+  if (!h) return B200FE_E_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->profile = on != 0;
+  return B200FE_OK;
+}
+
+int b200fe_profile_collect(b200fe_handle* h, double* total_ms, int64_t* n_launches) {
+  if (!h) return B200FE_E_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  double tot = 0.0;
+  for (auto& pr : h->prof_events) {
+    CUDA_TRY(h, cudaEventSynchronize(pr.second));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, pr.first, pr.second));
+    tot += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  if (total_ms) *total_ms = tot;
+  if (n_launches) *n_launches = (int64_t)h->prof_events.size();
+  h->prof_events.clear();
+  return B200FE_OK;
+}
+
+int b200fe_get_tables(const b200fe_handle* h, float* window_out, float* mel_out) {
+  if (!h) return B200FE_E_INVALID;
+  if (window_out) memcpy(window_out, h->window_host.data(), h->window_host.size() * sizeof(float));
+  if (mel_out) memcpy(mel_out, h->mel_host.data(), h->mel_host.size() * sizeof(float));
+  return B200FE_OK;
+}
+
+int b200fe_plan(b200fe_handle* h, const int64_t* lengths_host, int batch, int64_t* n_frames_out, int64_t* n_rows_out,
+                int64_t* max_rows_out, size_t* workspace_bytes) {
+  if (!h || !lengths_host || batch < 0) return fail(h, B200FE_E_INVALID, "null argument");
+  Plan pl;
+  int rc = make_plan(h, lengths_host, nullptr, 0, batch, pl);
+  if (rc) return rc;
+  size_t si = 0;
+  for (int u = 0; u < batch; ++u) {
+    int nf = pl.utts[u].n_frames;
+    if (lengths_host[u] < h->L) nf = pl.shorts[si++].n_frames;
+    if (n_frames_out) n_frames_out[u] = nf;
+    if (n_rows_out) n_rows_out[u] = pl.utts[u].n_rows;
+  }
+  if (max_rows_out) *max_rows_out = pl.max_rows;
+  if (workspace_bytes) *workspace_bytes = workspace_need(batch);
+  return B200FE_OK;
+}
+
+int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, const int64_t* offsets_host,
+                   int64_t row_stride, const int64_t* lengths_host, int batch, float* feats_dev, int64_t rows_cap,
+                   int64_t* feat_lens_dev, double* stats_dev, uint64_t dither_seed, void* workspace_dev,
+                   size_t workspace_bytes, void* stream) {
+  if (!h) return B200FE_E_INVALID;
+  if (batch == 0) return B200FE_OK;
+  if (!wave_dev || !lengths_host || !feats_dev || !workspace_dev || batch < 0)
+    return fail(h, B200FE_E_INVALID, "null argument");
+  if (workspace_bytes < workspace_need(batch)) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(h->mu);
+  Plan pl;
+  int rc = make_plan(h, lengths_host, offsets_host, row_stride, batch, pl);
+  if (rc) return rc;
+  if (pl.max_rows > rows_cap) return fail(h, B200FE_E_INVALID, "rows_cap smaller than the longest utterance's row count");
+  for (int u = 0; u < batch; ++u) {
+    const long long end = pl.utts[u].wave_off + lengths_host[u];
+    if (pl.utts[u].wave_off < 0 || end > wave_total) return fail(h, B200FE_E_INVALID, "utterance outside the wave buffer");
+  }
+  UttDesc* d_utts = reinterpret_cast<UttDesc*>(workspace_dev);
+  ShortDesc* d_shorts = reinterpret_cast<ShortDesc*>((char*)workspace_dev + align256((size_t)batch * sizeof(UttDesc)));
+  if ((rc = upload(h, pl.utts.data(), (size_t)batch * sizeof(UttDesc), d_utts, st))) return rc;
+
+  // 1. padding rows + feat_lens
+  {
+    const long long per_utt = rows_cap * (long long)h->D / 4;
+    int gx = (int)((per_utt + 256 * 8 - 1) / (256 * 8));
+    gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
+    pad_rows_kernel<<<dim3(gx, batch), 256, 0, st>>>(d_utts, feats_dev, rows_cap, h->D, (long long*)feat_lens_dev);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
+  // 2. the fused tile kernel over all regular utterances
+  if (pl.n_tiles > 0) {
+    TileParams p;
+    p.wave = wave_dev; p.wave_total = wave_total; p.utts = d_utts; p.batch = batch; p.n_tiles = pl.n_tiles;
+    p.feats = feats_dev; p.rows_cap = rows_cap; p.stats = stats_dev;
+    p.frame_len = h->L; p.frame_shift = h->S; p.n_mels = h->cfg.n_mels;
+    p.lfr_m = h->cfg.lfr_m; p.lfr_n = h->cfg.lfr_n; p.rows_per_tile = h->rows_per_tile; p.e_cap = h->e_cap;
+    p.preemph = h->cfg.preemphasis; p.remove_dc = h->cfg.remove_dc_offset; p.log_floor = h->cfg.log_floor;
+    p.dither = h->cfg.dither / (h->cfg.upscale_samples ? 32768.f : 1.f);   // TA:179 adds it after the 2^15 upscale
+    p.seed = dither_seed;
+    p.window = h->d_window; p.twiddle = h->d_twiddle; p.mel_w = h->d_mel_w; p.mel_desc = h->d_mel_desc;
+    p.cmvn = h->d_cmvn;
+    const int grid = pl.n_tiles < 3 * h->n_sms ? pl.n_tiles : 3 * h->n_sms;
+    const bool dither = h->cfg.dither != 0.f, stats = stats_dev != nullptr;
+    if (h->L == 400) rc = launch_tile<25, true>(h, p, grid, dither, stats, st);
+    else rc = launch_tile<32, false>(h, p, grid, dither, stats, st);
+    if (rc) return rc;
+  }
+  // 3. utterances shorter than one frame (VF:147)
+  if (!pl.shorts.empty()) {
+    if (h->cfg.dither != 0.f) return fail(h, B200FE_E_UNSUPPORTED, "dither on utterances shorter than one frame");
+    if ((rc = ensure_short_banks(h, pl, st))) return rc;
+    if ((rc = upload(h, pl.shorts.data(), pl.shorts.size() * sizeof(ShortDesc), d_shorts, st))) return rc;
+    short_utt_kernel<<<(int)pl.shorts.size(), 256, 0, st>>>(
+        wave_dev, d_shorts, h->d_short_mel, h->S, h->cfg.n_mels, h->cfg.lfr_m, h->cfg.lfr_n, h->cfg.window_type,
+        h->cfg.blackman_coeff, h->cfg.preemphasis, h->cfg.remove_dc_offset, h->cfg.upscale_samples ? 32768.f : 1.f,
+        h->cfg.log_floor, h->d_cmvn, feats_dev, rows_cap);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
+  if (stats_dev) {
+    add_count_kernel<<<1, 1, 0, st>>>(stats_dev + 2 * h->D, (double)pl.total_rows);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
+  return B200FE_OK;
+}
+
+int b200fe_lfr_cmvn(b200fe_handle* h, const float* fbank_dev, int64_t frames_cap, const int64_t* n_frames_host, int batch,
+                    float* feats_dev, int64_t rows_cap, int64_t* feat_lens_dev, void* workspace_dev,
+                    size_t workspace_bytes, void* stream) {
+  if (!h) return B200FE_E_INVALID;
+  if (batch == 0) return B200FE_OK;
+  if (!fbank_dev || !n_frames_host || !feats_dev || !workspace_dev) return fail(h, B200FE_E_INVALID, "null argument");
+  if (workspace_bytes < workspace_need(batch)) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(h->mu);
+  std::vector<UttDesc> utts(batch);
+  long long max_rows = 0;
+  for (int u = 0; u < batch; ++u) {
+    UttDesc d{};
+    d.n_frames = (int)n_frames_host[u];
+    if (d.n_frames < 0 || d.n_frames > frames_cap) return fail(h, B200FE_E_INVALID, "bad frame count");
+    d.n_rows = ceil_div(d.n_frames, h->cfg.lfr_n);
+    max_rows = d.n_rows > max_rows ? d.n_rows : max_rows;
+    utts[u] = d;
+  }
+  if (max_rows > rows_cap) return fail(h, B200FE_E_INVALID, "rows_cap too small");
+  UttDesc* d_utts = reinterpret_cast<UttDesc*>(workspace_dev);
+  int rc = upload(h, utts.data(), (size_t)batch * sizeof(UttDesc), d_utts, st);
+  if (rc) return rc;
+  pad_rows_kernel<<<dim3(16, batch), 256, 0, st>>>(d_utts, feats_dev, rows_cap, h->D, (long long*)feat_lens_dev);
+  CUDA_TRY(h, cudaGetLastError());
+  lfr_cmvn_kernel<<<dim3(32, batch), 256, 0, st>>>(fbank_dev, frames_cap, d_utts, h->cfg.n_mels, h->cfg.lfr_m,
+                                                   h->cfg.lfr_n, h->d_cmvn, feats_dev, rows_cap);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 2;
+  return B200FE_OK;
+}
+
+int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int64_t* lengths_dev, int batch, uint64_t seed,
+                         float amp, void* stream) {
+  if (!wave_dev || !offsets_dev || !lengths_dev || batch <= 0) return B200FE_E_INVALID;
+  synth_uniform_kernel<<<dim3(64, batch), 256, 0, (cudaStream_t)stream>>>(
+      wave_dev, (const long long*)offsets_dev, (const long long*)lengths_dev, batch, seed, amp);
+  return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
+}
+
+}  // extern "C"
+
+#include "stream_api.inl"

@@ -1,0 +1,458 @@
+// Fused front-end kernel for sm_100a: framing + DC removal + pre-emphasis + window -> 512-point power
+// spectrum -> sparse Kaldi mel -> log -> LFR stack -> CMVN, one persistent CTA per tile of LFR rows.
+//
+// Replaces, for a whole ragged batch in one launch, what the reference runs per utterance on the CPU:
+//   TA:154-217 (_get_window), TA:616-618 (rfft/abs/pow), TA:621-633 (mel mm + log), VF:40-60 (apply_lfr),
+//   VF:23-37 (apply_cmvn), VF:163-166 (pad_sequence).
+//
+// Work decomposition ("fbank tile kernel"):
+//   * tile  = rows_per_tile LFR rows of one utterance = F <= kFMax consecutive frames (1 frame of halo is recomputed
+//             between neighbouring tiles);  persistent CTAs stride over the tile list.
+//   * stage = the tile's samples are read ONCE from HBM with 128-bit loads, pre-emphasised and kept in shared memory
+//             (each sample feeds 2.5 frames).
+//   * FFT   = two real frames are packed into one 512-point complex FFT (frame A real, frame B imaginary) done by a
+//             group of 16 threads: a 32-point register FFT per thread, ONE shared-memory transpose, then two 16-point
+//             register FFTs per thread (columns k1 and 32-k1, so the conjugate pairs needed to separate the two
+//             frames are thread-local).  No shuffles on the FFT path; a warp (2 groups = 4 frames) never waits for
+//             another warp inside a tile.
+//   * mel   = power spectra of the warp's 4 frames are interleaved [bin][4] so one 128-bit shared load feeds 4 FMAs;
+//             the filterbank is stored sparse (<= 2 non-zeros per FFT bin).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft_codelets.cuh"
+
+namespace b200fe {
+
+constexpr int kGroup = 16;          // threads per frame pair
+constexpr int kCtaThreads = 128;    // 4 warps, 8 groups
+constexpr int kWarps = kCtaThreads / 32;
+constexpr int kFMax = 32;           // frames per tile (upper bound)
+constexpr int kXRow = 18;           // float2 per transpose row: 16 + 2 pad -> 144 B, conflict-free 128-bit reads
+constexpr int kXGroupFloat2 = 32 * kXRow;
+constexpr int kMaxMels = 128;
+constexpr int kMaxNnz = 512;        // every FFT bin feeds at most 2 triangular filters
+constexpr int kNfft = 512;
+
+struct UttDesc {          // built on the host by b200fe_plan/forward
+  long long wave_off;     // first sample of the utterance inside the wave buffer
+  int n_samples;
+  int n_frames;           // T      (TA:65-70)
+  int n_rows;             // T_lfr  (VF:43)
+  int tile_begin;         // index of the utterance's first tile in the launch-wide tile list
+};
+
+struct TileParams {
+  const float* wave;
+  long long wave_total;
+  const UttDesc* utts;
+  int batch;
+  int n_tiles;
+  float* feats;           // [batch, rows_cap, out_dim]
+  long long rows_cap;
+  double* stats;          // nullptr or [2*out_dim + 1]
+  int frame_len;          // L  (window_size, <= 512)
+  int frame_shift;        // S
+  int n_mels;
+  int lfr_m, lfr_n, rows_per_tile;
+  int e_cap;              // floats reserved for the staged samples
+  float preemph;
+  int remove_dc;
+  float log_floor;
+  float dither;
+  unsigned long long seed;
+  const float* window;    // [512] window * (2^15 if upscale), zero beyond L
+  const float2* twiddle;  // [17][16]  exp(-2*pi*i*n2*r/512)
+  const float* mel_w;     // [kMaxNnz] packed non-zero weights (x 0.25: the spectra below are 4*|X|^2)
+  const int* mel_desc;    // [n_mels]  lo | cnt << 9 | off << 18
+  const float* cmvn;      // nullptr or [2][out_dim]
+};
+
+__host__ __device__ inline size_t tile_smem_bytes(int e_cap, int n_mels) {
+  size_t b = 0;
+  b += (size_t)e_cap * 4;                           // staged, pre-emphasised samples
+  b += 2 * kFMax * 4;                               // raw first / last sample of each frame
+  b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;      // transpose buffers (aliased by the power spectra)
+  b += (size_t)kFMax * n_mels * 4;                  // log-mel of the tile
+  b += 17 * 16 * 8;                                 // twiddles
+  b += kMaxNnz * 4 + kMaxMels * 4;                  // sparse filterbank
+  return b;
+}
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// counter-based N(0,1) for dither: one value per (utterance, absolute frame, sample-in-frame), cf. TA:179-181
+__device__ __forceinline__ float dither_normal(unsigned long long seed, unsigned utt, unsigned frame, unsigned n) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)utt + 1) +
+                         0xD1B54A32D192ED03ull * ((unsigned long long)frame * 1024ull + n);
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u1 = ((unsigned)(z >> 40) + 1u) * (1.0f / 16777216.0f);  // (0, 1]
+  const float u2 = (unsigned)(z & 0xFFFFFFu) * (1.0f / 16777216.0f);  // [0, 1)
+  return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530717958647692f * u2);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fbank_quad: log-mel of 4 consecutive frames (tile-local frames 4*quad .. 4*quad+3) by one warp.
+//   e_base   staged pre-emphasised samples, e_base[f*S + n] = x[n] - preemph*x[n-1] of tile-local frame f
+//   x0_s/xl_s raw first / last sample of every tile-local frame
+//   win      this thread's window taps (n = 16*i + j), already scaled by 2^15 when upscaling
+//   xg       this 16-thread group's transpose buffer; pbuf4 = the warp's [bin][4] spectra (aliases the warp's xg's)
+//   logmel   shared [F][M] destination
+// NROWS = ceil(frame_len / 16): rows of 16 samples that can be non-zero (25 for 400-sample frames, else 32).
+// EXACT: frame_len == 16*NROWS, so no per-sample bounds predicate is needed in the stage-1 load.
+template <int NROWS, bool EXACT, bool DITHER>
+__device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_s, const float* xl_s, int F, int quad,
+                                           int S, int L, const float (&win)[NROWS], float2* xg, float4* pbuf4,
+                                           const float2* tw_s, const float* melw_s, const int* meld_s, int M,
+                                           float preemph, int remove_dc, float log_floor, float dither,
+                                           unsigned long long seed, unsigned utt, unsigned frame_abs0, float* logmel,
+                                           int j, int grp_in_warp, int lane) {
+  const int fA = 4 * quad + 2 * grp_in_warp;   // tile-local frame of the real lane; fA + 1 is the imaginary lane
+  const bool vA = fA < F, vB = fA + 1 < F;
+  float re[32], im[32];
+  {
+    // stage 1 load: thread j owns samples n = 16*i + j of both frames
+    const float* eA = e_base + fA * S + j;
+    const float* eB = eA + S;
+#pragma unroll
+    for (int i = 0; i < NROWS; ++i) {
+      const bool in = EXACT || (16 * i + j < L);
+      re[i] = (vA && in) ? eA[16 * i] : 0.f;
+      im[i] = (vB && in) ? eB[16 * i] : 0.f;
+    }
+    float x0A = 0.f, xlA = 0.f, x0B = 0.f, xlB = 0.f;
+    if (vA) { x0A = x0_s[fA]; xlA = xl_s[fA]; }
+    if (vB) { x0B = x0_s[fA + 1]; xlB = xl_s[fA + 1]; }
+    if constexpr (DITHER) {
+      // x'[n] = x[n] + dither*g(frame, n)  (TA:179-181: independent noise per (frame, sample));
+      // the pre-emphasised value picks up dither*(g(n) - preemph*g(n-1))
+      const unsigned fa = frame_abs0 + (unsigned)fA;
+#pragma unroll
+      for (int i = 0; i < NROWS; ++i) {
+        const int n = 16 * i + j;
+        if (n < L) {
+          const int nm = n > 0 ? n - 1 : 0;
+          if (vA) re[i] += dither * (dither_normal(seed, utt, fa, n) - preemph * dither_normal(seed, utt, fa, nm));
+          if (vB) im[i] += dither * (dither_normal(seed, utt, fa + 1, n) - preemph * dither_normal(seed, utt, fa + 1, nm));
+        }
+      }
+      if (vA) { x0A += dither * dither_normal(seed, utt, fa, 0); xlA += dither * dither_normal(seed, utt, fa, L - 1); }
+      if (vB) { x0B += dither * dither_normal(seed, utt, fa + 1, 0); xlB += dither * dither_normal(seed, utt, fa + 1, L - 1); }
+    }
+    if (j == 0) {  // replicate rule at the frame start: y[0] = x[0] - preemph * x[0]  (TA:193-198)
+      re[0] = fmaf(-preemph, x0A, x0A);
+      im[0] = fmaf(-preemph, x0B, x0B);
+    }
+    float sA = 0.f, sB = 0.f;
+#pragma unroll
+    for (int i = 0; i < NROWS; ++i) { sA += re[i]; sB += im[i]; }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+      sA += __shfl_xor_sync(0xffffffffu, sA, o);
+      sB += __shfl_xor_sync(0xffffffffu, sB, o);
+    }
+    // (1-preemph) * mean(frame), recovered from the sum of the pre-emphasised samples
+    float mA = 0.f, mB = 0.f;
+    if (remove_dc) {
+      const float invL = 1.0f / (float)L;
+      mA = (sA - preemph * (xlA - x0A)) * invL;
+      mB = (sB - preemph * (xlB - x0B)) * invL;
+    }
+#pragma unroll
+    for (int i = 0; i < NROWS; ++i) {
+      re[i] = (re[i] - mA) * win[i];
+      im[i] = (im[i] - mB) * win[i];
+    }
+#pragma unroll
+    for (int i = NROWS; i < 32; ++i) { re[i] = 0.f; im[i] = 0.f; }
+  }
+  fft_dif<32, NROWS>(re, im);
+
+  // ---- the one transpose: row k1 of the group's buffer <- Y[n2 = j][k1]
+  __syncwarp();   // the previous quad's mel reads of the aliased spectra are done
+  static_for<0, 32>([&](auto ic) {
+    constexpr int k1 = decltype(ic)::value;
+    constexpr int pos = bitrev<32>(k1);
+    xg[k1 * kXRow + j] = make_float2(re[pos], im[pos]);
+  });
+  __syncwarp();
+
+  // ---- stage 2: this thread owns columns cA = j and cB = 32 - rowB  (thread 0: columns 0 and 16)
+  const int rowB = j == 0 ? 16 : j;
+  float ar[16], ai[16], br[16], bi[16];
+  {
+    const float4* rowA4 = reinterpret_cast<const float4*>(xg + j * kXRow);
+    const float4* rowB4 = reinterpret_cast<const float4*>(xg + (32 - rowB) * kXRow);
+    const float4* twA4 = reinterpret_cast<const float4*>(tw_s + j * 16);
+    const float4* twB4 = reinterpret_cast<const float4*>(tw_s + rowB * 16);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const float4 ya = rowA4[h], yb = rowB4[h], ta = twA4[h], tb = twB4[h];
+      // column A: Y * W512^(n2*cA);  column B: Y * conj(W512^(n2*rowB)), whose FFT comes out rotated by one bin
+      ar[2 * h] = fmaf(ya.x, ta.x, -(ya.y * ta.y));
+      ai[2 * h] = fmaf(ya.x, ta.y, ya.y * ta.x);
+      ar[2 * h + 1] = fmaf(ya.z, ta.z, -(ya.w * ta.w));
+      ai[2 * h + 1] = fmaf(ya.z, ta.w, ya.w * ta.z);
+      br[2 * h] = fmaf(yb.x, tb.x, yb.y * tb.y);
+      bi[2 * h] = fmaf(yb.y, tb.x, -(yb.x * tb.y));
+      br[2 * h + 1] = fmaf(yb.z, tb.z, yb.w * tb.w);
+      bi[2 * h + 1] = fmaf(yb.w, tb.z, -(yb.z * tb.w));
+    }
+  }
+  fft_dif<16>(ar, ai);
+  fft_dif<16>(br, bi);
+  __syncwarp();   // every lane has consumed the transpose buffer; it is reused for the spectra below
+
+  // ---- separate the two real frames: slot i pairs Z[k] (first) with Z[512-k] (second).
+  //      general thread: first = A[i], second = B[15-i];  thread 0 pairs inside its own two columns.
+  {
+    const bool t0 = (j == 0);
+    // natural-order accessors: A[k2] sits at bitrev(k2);  B[k2] = FFT16(B')[(k2+1) & 15]
+#define A_RE(k) ar[bitrev<16>(k)]
+#define A_IM(k) ai[bitrev<16>(k)]
+#define B_RE(k) br[bitrev<16>(((k) + 1) & 15)]
+#define B_IM(k) bi[bitrev<16>(((k) + 1) & 15)]
+    static_for<8, 15>([&](auto ic) {
+      constexpr int q = decltype(ic)::value;
+      const float tr = B_RE(q), ti = B_IM(q);
+      B_RE(q) = t0 ? A_RE(q + 1) : tr;
+      B_IM(q) = t0 ? A_IM(q + 1) : ti;
+      A_RE(q) = t0 ? tr : A_RE(q);
+      A_IM(q) = t0 ? ti : A_IM(q);
+    });
+    A_RE(15) = t0 ? B_RE(15) : A_RE(15);
+    A_IM(15) = t0 ? B_IM(15) : A_IM(15);
+    const int binA = j, binB = 32 - rowB;
+    float2* pb2 = reinterpret_cast<float2*>(pbuf4) + grp_in_warp;   // [bin][2 groups] of (frame A, frame B)
+    static_for<0, 16>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      const float ur = A_RE(i), ui = A_IM(i);
+      const float vr = B_RE(15 - i), vi = B_IM(15 - i);
+      const float s1 = ur + vr, d1 = ui - vi, s2 = ui + vi, d2 = ur - vr;
+      const float pA = fmaf(s1, s1, d1 * d1);   // 4 * |X_A[k]|^2
+      const float pB = fmaf(s2, s2, d2 * d2);   // 4 * |X_B[k]|^2
+      const int bin = i < 8 ? binA + 32 * i : binB + 32 * (15 - i);
+      if (!(t0 && i == 0)) pb2[2 * bin] = make_float2(pA, pB);
+    });
+#undef A_RE
+#undef A_IM
+#undef B_RE
+#undef B_IM
+  }
+  __syncwarp();
+
+  // ---- sparse mel + log for the warp's 4 frames: lane <-> filter
+  for (int m = lane; m < M; m += 32) {
+    const int d = meld_s[m];
+    const int lo = d & 511, cnt = (d >> 9) & 511, off = d >> 18;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < cnt; ++q) {
+      const float w = melw_s[off + q];
+      const float4 s = pbuf4[lo + q];
+      acc.x = fmaf(w, s.x, acc.x);
+      acc.y = fmaf(w, s.y, acc.y);
+      acc.z = fmaf(w, s.z, acc.z);
+      acc.w = fmaf(w, s.w, acc.w);
+    }
+    const int fr = 4 * quad;
+    if (fr < F) logmel[fr * M + m] = __logf(fmaxf(acc.x, log_floor));
+    if (fr + 1 < F) logmel[(fr + 1) * M + m] = __logf(fmaxf(acc.y, log_floor));
+    if (fr + 2 < F) logmel[(fr + 2) * M + m] = __logf(fmaxf(acc.z, log_floor));
+    if (fr + 3 < F) logmel[(fr + 3) * M + m] = __logf(fmaxf(acc.w, log_floor));
+  }
+}
+
+template <bool STATS>
+struct StatsAcc {
+  double sum[2][4], sq[2][4];
+};
+template <>
+struct StatsAcc<false> {};
+
+template <int NROWS, bool EXACT, bool DITHER, bool STATS>
+__global__ void __launch_bounds__(kCtaThreads, 3)
+fbank_lfr_cmvn_tile_kernel(const TileParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* e_s = reinterpret_cast<float*>(smem_raw);
+  float* x0_s = e_s + p.e_cap;
+  float* xl_s = x0_s + kFMax;
+  float2* xbuf = reinterpret_cast<float2*>(xl_s + kFMax);
+  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
+  float2* tw_s = reinterpret_cast<float2*>(logmel_s + kFMax * p.n_mels);
+  float* melw_s = reinterpret_cast<float*>(tw_s + 17 * 16);
+  int* meld_s = reinterpret_cast<int*>(melw_s + kMaxNnz);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int j = tid & (kGroup - 1);     // position inside the 16-thread group: n2 in stage 1, column id in stage 2
+  const int grp_in_warp = lane >> 4;    // 0 / 1
+  const int L = p.frame_len, S = p.frame_shift, M = p.n_mels;
+  const int D = p.lfr_m * M;
+  const int lfr_left = (p.lfr_m - 1) / 2;
+
+  // ---- per-CTA constants: tables to shared memory, this thread's window taps to registers
+  for (int i = tid; i < 17 * 16; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  for (int i = tid; i < kMaxNnz; i += kCtaThreads) melw_s[i] = p.mel_w[i];
+  for (int i = tid; i < kMaxMels; i += kCtaThreads) meld_s[i] = i < M ? p.mel_desc[i] : 0;
+  float win[NROWS];
+#pragma unroll
+  for (int i = 0; i < NROWS; ++i) win[i] = p.window[16 * i + j];
+
+  // output columns handled by this thread in the LFR/CMVN phase (float4 granularity), fixed for the CTA's lifetime
+  const int D4 = D >> 2, M4 = M >> 2;
+  float4 cm_shift[2], cm_scale[2];
+  int col_j[2], col_d[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int c4 = tid + c * kCtaThreads;
+    cm_shift[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cm_scale[c] = make_float4(1.f, 1.f, 1.f, 1.f);
+    col_j[c] = 0;
+    col_d[c] = 0;
+    if (c4 < D4) {
+      col_j[c] = c4 / M4;
+      col_d[c] = c4 - col_j[c] * M4;
+      if (p.cmvn) {
+        cm_shift[c] = *reinterpret_cast<const float4*>(p.cmvn + 4 * c4);
+        cm_scale[c] = *reinterpret_cast<const float4*>(p.cmvn + D + 4 * c4);
+      }
+    }
+  }
+  StatsAcc<STATS> st;
+  if constexpr (STATS) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st.sum[c][k] = st.sq[c][k] = 0.0;
+  }
+  __syncthreads();
+
+  const unsigned wave_mis = (unsigned)((reinterpret_cast<uintptr_t>(p.wave) >> 2) & 3);
+  float2* xg = xbuf + (warp * 2 + grp_in_warp) * kXGroupFloat2;                 // this group's transpose buffer
+  float4* pbuf4 = reinterpret_cast<float4*>(xbuf + warp * 2 * kXGroupFloat2);   // this warp's [bin][4 frames] spectra
+
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    // ---- locate the tile: last utterance whose tile_begin <= tile (utterances without tiles share the next begin)
+    int utt;
+    {
+      int lo = 0, hi = p.batch - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (p.utts[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+      }
+      utt = lo;
+    }
+    const UttDesc ud = p.utts[utt];
+    const int T = ud.n_frames;
+    const int row0 = (tile - ud.tile_begin) * p.rows_per_tile;
+    const int nrow = min(p.rows_per_tile, ud.n_rows - row0);
+    const int f_lo = min(max(p.lfr_n * row0 - lfr_left, 0), T - 1);
+    const int f_hi = min(max(p.lfr_n * (row0 + nrow - 1) - lfr_left + p.lfr_m - 1, 0), T - 1);
+    const int F = f_hi - f_lo + 1;                            // <= kFMax by construction of rows_per_tile
+    const long long g0 = ud.wave_off + (long long)f_lo * S;   // absolute index of the tile's first sample
+    const int a_off = (int)((wave_mis + (unsigned)(g0 & 3)) & 3);
+    const long long ga = g0 - a_off;                          // 16-byte aligned load grid
+    const int n_s = (F - 1) * S + L;
+
+    // ---- stage: HBM -> (pre-emphasis) -> shared, 128-bit both ways
+    {
+      const int nv = (a_off + n_s + 3) >> 2;
+      for (int v0 = warp * 32; v0 < nv; v0 += kCtaThreads) {
+        const int v = v0 + lane;
+        const long long ab = ga + 4ll * v;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < nv) {
+          if (ab >= 0 && ab + 3 < p.wave_total) {
+            x = ldg_stream4(p.wave + ab);
+          } else {
+            if (ab >= 0 && ab < p.wave_total) x.x = p.wave[ab];
+            if (ab + 1 >= 0 && ab + 1 < p.wave_total) x.y = p.wave[ab + 1];
+            if (ab + 2 >= 0 && ab + 2 < p.wave_total) x.z = p.wave[ab + 2];
+            if (ab + 3 >= 0 && ab + 3 < p.wave_total) x.w = p.wave[ab + 3];
+          }
+        }
+        float prev = __shfl_up_sync(0xffffffffu, x.w, 1);
+        if (lane == 0) prev = (v < nv && ab >= 1 && ab - 1 < p.wave_total) ? p.wave[ab - 1] : 0.f;
+        if (v < nv) {
+          float4 e;
+          e.x = fmaf(-p.preemph, prev, x.x);
+          e.y = fmaf(-p.preemph, x.x, x.y);
+          e.z = fmaf(-p.preemph, x.y, x.z);
+          e.w = fmaf(-p.preemph, x.z, x.w);
+          *reinterpret_cast<float4*>(e_s + 4 * v) = e;
+        }
+      }
+      if (tid < F) {
+        x0_s[tid] = p.wave[g0 + (long long)tid * S];
+        xl_s[tid] = p.wave[g0 + (long long)tid * S + L - 1];
+      }
+    }
+    __syncthreads();
+
+    // ---- per warp: quads of 4 frames (2 groups x 2 frames), no CTA-wide sync inside
+    for (int quad = warp; 4 * quad < F; quad += kWarps)
+      fbank_quad<NROWS, EXACT, DITHER>(e_s + a_off, x0_s, xl_s, F, quad, S, L, win, xg, pbuf4, tw_s, melw_s, meld_s, M,
+                                       p.preemph, p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)utt,
+                                       (unsigned)f_lo, logmel_s, j, grp_in_warp, lane);
+    __syncthreads();
+
+    // ---- LFR stack + CMVN, written straight into the padded [batch, rows_cap, D] output
+    {
+      float* out_u = p.feats + ((long long)utt * p.rows_cap + row0) * D;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int c4 = tid + c * kCtaThreads;
+        if (c4 < D4) {
+          for (int r = 0; r < nrow; ++r) {
+            int f = p.lfr_n * (row0 + r) + col_j[c] - lfr_left;
+            f = min(max(f, 0), T - 1) - f_lo;
+            const float4 v = *reinterpret_cast<const float4*>(logmel_s + f * M + 4 * col_d[c]);
+            if constexpr (STATS) {
+              st.sum[c][0] += v.x; st.sum[c][1] += v.y; st.sum[c][2] += v.z; st.sum[c][3] += v.w;
+              st.sq[c][0] += (double)v.x * v.x; st.sq[c][1] += (double)v.y * v.y;
+              st.sq[c][2] += (double)v.z * v.z; st.sq[c][3] += (double)v.w * v.w;
+            }
+            float4 o;
+            o.x = (v.x + cm_shift[c].x) * cm_scale[c].x;
+            o.y = (v.y + cm_shift[c].y) * cm_scale[c].y;
+            o.z = (v.z + cm_shift[c].z) * cm_scale[c].z;
+            o.w = (v.w + cm_shift[c].w) * cm_scale[c].w;
+            stg_stream4(out_u + (long long)r * D + 4 * c4, o);
+          }
+        }
+      }
+    }
+    __syncthreads();   // the tile's shared buffers are free again
+  }
+
+  if constexpr (STATS) {
+    if (p.stats) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int c4 = tid + c * kCtaThreads;
+        if (c4 < D4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            atomicAdd(p.stats + 4 * c4 + k, st.sum[c][k]);
+            atomicAdd(p.stats + D + 4 * c4 + k, st.sq[c][k]);
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace b200fe

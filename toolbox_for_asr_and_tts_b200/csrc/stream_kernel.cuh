@@ -1,0 +1,217 @@
+// Chunked-streaming front-end: one CTA per (stream, tick).  The per-stream state (sample carry = upstream
+// WavFrontendOnline `input_cache`, LFR splice frames = `lfr_splice_cache`, counters) lives in one HBM slab, so the
+// host never concatenates audio (cf. the np.concatenate growth at R:voice-service/app/services/
+// voice_interface.py:1304-1311,1688-1746) and nothing crosses PCIe but the new chunk and the new rows.
+//
+// Semantics (oracle/wav_frontend_np.py::OnlineFrontend): frames are cut from [carry | chunk]; LFR row i is emitted as
+// soon as frame lfr_n*i + lfr_m-1-(lfr_m-1)/2 exists; `is_final` flushes the remaining rows up to ceil(T/lfr_n) with
+// the last frame replicated and resets the stream.  Concatenated outputs equal the offline output.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fbank_tile.cuh"
+
+namespace b200fe {
+
+struct StreamLayout {
+  int n_streams;
+  int carry_cap;    // floats per stream (>= frame_len - 1, multiple of 4)
+  int cache_cap;    // frames per stream: max(lfr_m - 1, 1)
+  int n_mels;
+  __host__ __device__ size_t counters_bytes() const { return ((size_t)4 * n_streams * sizeof(int) + 255) & ~(size_t)255; }
+  __host__ __device__ size_t carry_bytes() const { return ((size_t)n_streams * carry_cap * sizeof(float) + 255) & ~(size_t)255; }
+  __host__ __device__ size_t cache_bytes() const { return ((size_t)n_streams * cache_cap * n_mels * sizeof(float) + 255) & ~(size_t)255; }
+  __host__ __device__ size_t total_bytes() const { return counters_bytes() + carry_bytes() + cache_bytes(); }
+  __host__ __device__ int* counters(void* base) const { return reinterpret_cast<int*>(base); }
+  __host__ __device__ float* carry(void* base) const { return reinterpret_cast<float*>((char*)base + counters_bytes()); }
+  __host__ __device__ float* cache(void* base) const { return reinterpret_cast<float*>((char*)base + counters_bytes() + carry_bytes()); }
+};
+
+struct StreamParams {
+  void* state;
+  StreamLayout lay;
+  const float* chunks;
+  long long chunk_stride;
+  const int* chunk_lens;
+  const int* stream_ids;
+  const unsigned char* is_final;
+  int n;
+  int max_chunk;
+  int nf_max;             // frames one push can create
+  float* feats;           // [n, rows_cap, D]
+  long long rows_cap;
+  int* rows_out;          // [n]
+  int frame_len, frame_shift, n_mels, lfr_m, lfr_n;
+  int e_cap;
+  float preemph;
+  int remove_dc;
+  float log_floor;
+  float dither;
+  unsigned long long seed;
+  const float* window;
+  const float2* twiddle;
+  const float* mel_w;
+  const int* mel_desc;
+  const float* cmvn;
+};
+
+__host__ __device__ inline size_t stream_smem_bytes(int e_cap, int nf_max, int cache_cap, int n_mels) {
+  size_t b = 0;
+  b += (size_t)e_cap * 4;
+  b += (size_t)2 * ((nf_max + 3) & ~3) * 4;
+  b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;
+  b += (size_t)(cache_cap + nf_max) * n_mels * 4;
+  b += 17 * 16 * 8;
+  b += kMaxNnz * 4 + kMaxMels * 4;
+  return b;
+}
+
+__global__ void stream_reset_kernel(void* state, StreamLayout lay, const int* ids, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = ids ? ids[i] : i;
+  if (s < 0 || s >= lay.n_streams) return;
+  int* c = lay.counters(state);
+  c[s] = 0;
+  c[lay.n_streams + s] = 0;
+  c[2 * lay.n_streams + s] = 0;
+  c[3 * lay.n_streams + s] = 0;
+}
+
+template <int NROWS, bool EXACT, bool DITHER>
+__global__ void __launch_bounds__(kCtaThreads, 2)
+stream_push_kernel(const StreamParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nfp = (p.nf_max + 3) & ~3;
+  float* e_s = reinterpret_cast<float*>(smem_raw);
+  float* x0_s = e_s + p.e_cap;
+  float* xl_s = x0_s + nfp;
+  float2* xbuf = reinterpret_cast<float2*>(xl_s + nfp);
+  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
+  float2* tw_s = reinterpret_cast<float2*>(logmel_s + (p.lay.cache_cap + p.nf_max) * p.n_mels);
+  float* melw_s = reinterpret_cast<float*>(tw_s + 17 * 16);
+  int* meld_s = reinterpret_cast<int*>(melw_s + kMaxNnz);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = tid & (kGroup - 1), grp_in_warp = lane >> 4;
+  const int L = p.frame_len, S = p.frame_shift, M = p.n_mels;
+  const int D = p.lfr_m * M, lfr_left = (p.lfr_m - 1) / 2;
+  const int b = blockIdx.x;
+  const int sid = p.stream_ids[b];
+  if (sid < 0 || sid >= p.lay.n_streams) {
+    if (tid == 0) p.rows_out[b] = 0;
+    return;
+  }
+  int* cnt = p.lay.counters(p.state);
+  const int NS = p.lay.n_streams;
+  const int carry_len = cnt[sid], t_seen = cnt[NS + sid], rows_done = cnt[2 * NS + sid], cache_len = cnt[3 * NS + sid];
+  float* carry = p.lay.carry(p.state) + (size_t)sid * p.lay.carry_cap;
+  float* cache = p.lay.cache(p.state) + (size_t)sid * p.lay.cache_cap * M;
+  const float* chunk = p.chunks + (long long)b * p.chunk_stride;
+  const int n_new = min(max(p.chunk_lens[b], 0), p.max_chunk);
+  const bool fin = p.is_final && p.is_final[b];
+
+  for (int i = tid; i < 17 * 16; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  for (int i = tid; i < kMaxNnz; i += kCtaThreads) melw_s[i] = p.mel_w[i];
+  for (int i = tid; i < kMaxMels; i += kCtaThreads) meld_s[i] = i < M ? p.mel_desc[i] : 0;
+  float win[NROWS];
+#pragma unroll
+  for (int i = 0; i < NROWS; ++i) win[i] = p.window[16 * i + j];
+
+  // splice frames of earlier ticks come first in the tile's log-mel buffer
+  for (int i = tid; i < cache_len * M; i += kCtaThreads) logmel_s[i] = cache[i];
+
+  // stage [carry | chunk] with pre-emphasis
+  const int n = carry_len + n_new;
+  const int nf = n >= L ? (n - L) / S + 1 : 0;
+  for (int i = tid; i < n; i += kCtaThreads) {
+    const float x = i < carry_len ? carry[i] : chunk[i - carry_len];
+    const float xp = i == 0 ? 0.f : (i - 1 < carry_len ? carry[i - 1] : chunk[i - 1 - carry_len]);
+    e_s[i] = fmaf(-p.preemph, xp, x);
+  }
+  for (int f = tid; f < nf; f += kCtaThreads) {
+    const int a = f * S, z = f * S + L - 1;
+    x0_s[f] = a < carry_len ? carry[a] : chunk[a - carry_len];
+    xl_s[f] = z < carry_len ? carry[z] : chunk[z - carry_len];
+  }
+  // samples that stay behind for the next tick (read before anything overwrites the carry)
+  const int new_carry = n - nf * S;
+  float keep[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int k = tid + q * kCtaThreads;
+    keep[q] = 0.f;
+    if (k < new_carry) {
+      const int src = nf * S + k;
+      keep[q] = src < carry_len ? carry[src] : chunk[src - carry_len];
+    }
+  }
+  __syncthreads();
+
+  float2* xg = xbuf + (warp * 2 + grp_in_warp) * kXGroupFloat2;
+  float4* pbuf4 = reinterpret_cast<float4*>(xbuf + warp * 2 * kXGroupFloat2);
+  for (int quad = warp; 4 * quad < nf; quad += kWarps)
+    fbank_quad<NROWS, EXACT, DITHER>(e_s, x0_s, xl_s, nf, quad, S, L, win, xg, pbuf4, tw_s, melw_s, meld_s, M, p.preemph,
+                                     p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)sid, (unsigned)t_seen,
+                                     logmel_s + cache_len * M, j, grp_in_warp, lane);
+  __syncthreads();
+
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int k = tid + q * kCtaThreads;
+    if (k < new_carry) carry[k] = keep[q];
+  }
+
+  // rows that became available
+  const int T = t_seen + nf;
+  const int base_abs = t_seen - cache_len;         // absolute index of logmel_s row 0
+  const int need = p.lfr_m - 1 - lfr_left;
+  const int rows_all = T > 0 ? (T + p.lfr_n - 1) / p.lfr_n : 0;
+  int rows_total = fin ? rows_all : (T - 1 >= need ? (T - 1 - need) / p.lfr_n + 1 : 0);
+  rows_total = min(rows_total, rows_all);
+  rows_total = max(rows_total, rows_done);
+  int n_emit = rows_total - rows_done;
+  if (n_emit > p.rows_cap) n_emit = (int)p.rows_cap;
+  {
+    float* out = p.feats + (long long)b * p.rows_cap * D;
+    const int D4 = D >> 2, M4 = M >> 2;
+    for (int c4 = tid; c4 < D4; c4 += kCtaThreads) {
+      const int cj = c4 / M4, cd = c4 - cj * M4;
+      float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (p.cmvn) {
+        sh = *reinterpret_cast<const float4*>(p.cmvn + 4 * c4);
+        sc = *reinterpret_cast<const float4*>(p.cmvn + D + 4 * c4);
+      }
+      for (int r = 0; r < n_emit; ++r) {
+        int f = p.lfr_n * (rows_done + r) + cj - lfr_left;
+        f = min(max(f, 0), T - 1) - base_abs;
+        const float4 v = *reinterpret_cast<const float4*>(logmel_s + f * M + 4 * cd);
+        float4 o;
+        o.x = (v.x + sh.x) * sc.x;
+        o.y = (v.y + sh.y) * sc.y;
+        o.z = (v.z + sh.z) * sc.z;
+        o.w = (v.w + sh.w) * sc.w;
+        *reinterpret_cast<float4*>(out + (long long)r * D + 4 * c4) = o;
+      }
+    }
+  }
+  // frames the next rows still need (always at least the newest frame, for right replication on the final flush)
+  int keep_from = max(rows_total * p.lfr_n - lfr_left, 0);
+  keep_from = min(keep_from, max(T - 1, 0));
+  keep_from = max(keep_from, base_abs);
+  keep_from = max(keep_from, T - p.lay.cache_cap);
+  const int new_cache = T > 0 ? T - keep_from : 0;
+  for (int i = tid; i < new_cache * M; i += kCtaThreads) cache[i] = logmel_s[(keep_from - base_abs) * M + i];
+
+  if (tid == 0) {
+    p.rows_out[b] = n_emit;
+    if (fin) {
+      cnt[sid] = 0; cnt[NS + sid] = 0; cnt[2 * NS + sid] = 0; cnt[3 * NS + sid] = 0;
+    } else {
+      cnt[sid] = new_carry; cnt[NS + sid] = T; cnt[2 * NS + sid] = rows_total; cnt[3 * NS + sid] = new_cache;
+    }
+  }
+}
+
+}  // namespace b200fe

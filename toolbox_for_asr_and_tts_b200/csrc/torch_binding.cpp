@@ -1,0 +1,261 @@
+// torch C++ extension over the C ABI of libb200fe.so (include/b200fe.h).
+//
+// Registers `torch.ops.b200fe.*`.  at::Tensor stops here: below this file only raw device pointers, sizes and the
+// current CUDA stream cross into the library.  PyTorch is used for device memory (caching allocator) and streams.
+// No CPU fallback: every op checks that its tensors are CUDA tensors and raises otherwise.
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/library.h>
+
+#include <tuple>
+#include <vector>
+
+#include "../../include/b200fe.h"
+
+namespace {
+
+b200fe_handle* H(int64_t h) { return reinterpret_cast<b200fe_handle*>(static_cast<intptr_t>(h)); }
+
+void check(int rc, b200fe_handle* h, const char* what) {
+  if (rc == B200FE_OK) return;
+  const char* msg = b200fe_last_error(h);
+  const std::string text = std::string(what) + ": " + (msg ? msg : "");
+  TORCH_CHECK_NOT_IMPLEMENTED(rc != B200FE_E_UNSUPPORTED, text);
+  TORCH_CHECK(false, text);
+}
+
+void* cur_stream() { return static_cast<void*>(at::cuda::getCurrentCUDAStream().stream()); }
+
+int64_t fe_create(int64_t fs, double frame_length, double frame_shift, int64_t n_mels, int64_t window_type, int64_t lfr_m,
+                  int64_t lfr_n, double dither, bool snip_edges, bool upscale, double preemph, bool remove_dc,
+                  double low_freq, double high_freq, double blackman_coeff, const c10::optional<at::Tensor>& cmvn) {
+  b200fe_config c;
+  b200fe_default_config(&c);
+  c.sample_rate = (int32_t)fs;
+  c.frame_length_ms = (float)frame_length;
+  c.frame_shift_ms = (float)frame_shift;
+  c.n_mels = (int32_t)n_mels;
+  c.window_type = (int32_t)window_type;
+  c.lfr_m = (int32_t)lfr_m;
+  c.lfr_n = (int32_t)lfr_n;
+  c.dither = (float)dither;
+  c.snip_edges = snip_edges;
+  c.upscale_samples = upscale;
+  c.preemphasis = (float)preemph;
+  c.remove_dc_offset = remove_dc;
+  c.low_freq = (float)low_freq;
+  c.high_freq = (float)high_freq;
+  c.blackman_coeff = (float)blackman_coeff;
+  const float* cm = nullptr;
+  at::Tensor cm_host;
+  if (cmvn.has_value() && cmvn->defined()) {
+    cm_host = cmvn->to(at::kCPU, at::kFloat).contiguous();
+    TORCH_CHECK(cm_host.dim() == 2 && cm_host.size(0) == 2 && cm_host.size(1) >= n_mels * lfr_m,
+                "cmvn must be [2, >= n_mels*lfr_m]");
+    if (cm_host.size(1) != n_mels * lfr_m) cm_host = cm_host.slice(1, 0, n_mels * lfr_m).contiguous();
+    cm = cm_host.data_ptr<float>();
+  }
+  b200fe_handle* h = nullptr;
+  check(b200fe_create(&c, cm, &h), nullptr, "b200fe_create");
+  return static_cast<int64_t>(reinterpret_cast<intptr_t>(h));
+}
+
+void fe_destroy(int64_t h) { b200fe_destroy(H(h)); }
+
+std::tuple<at::Tensor, at::Tensor> fe_plan(int64_t h, const at::Tensor& lengths) {
+  auto len = lengths.to(at::kCPU, at::kLong).contiguous();
+  const int b = (int)len.numel();
+  auto nf = at::empty({b}, at::kLong), nr = at::empty({b}, at::kLong);
+  int64_t max_rows = 0;
+  size_t ws = 0;
+  check(b200fe_plan(H(h), len.data_ptr<int64_t>(), b, nf.data_ptr<int64_t>(), nr.data_ptr<int64_t>(), &max_rows, &ws), H(h),
+        "b200fe_plan");
+  return {nf, nr};
+}
+
+// wave: CUDA float32, either [B, Nmax] (offsets undefined) or a flat length-packed buffer with host offsets.
+std::tuple<at::Tensor, at::Tensor> fe_forward(int64_t h, const at::Tensor& wave, const c10::optional<at::Tensor>& offsets,
+                                              const at::Tensor& lengths, int64_t rows_cap,
+                                              const c10::optional<at::Tensor>& stats, int64_t seed) {
+  TORCH_CHECK(wave.is_cuda(), "b200fe.forward: waveform must be a CUDA tensor (there is no CPU fallback)");
+  TORCH_CHECK(wave.scalar_type() == at::kFloat, "b200fe.forward: waveform must be float32");
+  c10::cuda::CUDAGuard guard(wave.device());
+  auto w = wave.contiguous();
+  auto len = lengths.to(at::kCPU, at::kLong).contiguous();
+  const int b = (int)len.numel();
+  at::Tensor off;
+  const int64_t* off_ptr = nullptr;
+  int64_t row_stride = 0;
+  if (offsets.has_value() && offsets->defined()) {
+    off = offsets->to(at::kCPU, at::kLong).contiguous();
+    TORCH_CHECK(off.numel() == b, "offsets and lengths differ in size");
+    off_ptr = off.data_ptr<int64_t>();
+  } else {
+    TORCH_CHECK(w.dim() == 2 && w.size(0) == b, "waveform must be [B, Nmax] when no offsets are given");
+    row_stride = w.size(1);
+  }
+  int64_t max_rows = 0;
+  size_t ws = 0;
+  check(b200fe_plan(H(h), len.data_ptr<int64_t>(), b, nullptr, nullptr, &max_rows, &ws), H(h), "b200fe_plan");
+  if (rows_cap <= 0) rows_cap = max_rows;
+  const int64_t d = b200fe_output_dim(H(h));
+  auto opts = w.options();
+  auto feats = at::empty({b, rows_cap, d}, opts);
+  auto lens = at::empty({b}, opts.dtype(at::kLong));
+  auto work = at::empty({(int64_t)(ws ? ws : 256)}, opts.dtype(at::kByte));
+  double* st = nullptr;
+  if (stats.has_value() && stats->defined()) {
+    TORCH_CHECK(stats->is_cuda() && stats->scalar_type() == at::kDouble && stats->is_contiguous() &&
+                    stats->numel() == 2 * d + 1, "stats must be a contiguous CUDA float64 [2*D+1] tensor");
+    st = stats->data_ptr<double>();
+  }
+  check(b200fe_forward(H(h), w.data_ptr<float>(), w.numel(), off_ptr, row_stride, len.data_ptr<int64_t>(), b,
+                       feats.data_ptr<float>(), rows_cap, lens.data_ptr<int64_t>(), st, (uint64_t)seed, work.data_ptr(),
+                       (size_t)work.numel(), cur_stream()),
+        H(h), "b200fe_forward");
+  return {feats, lens};
+}
+
+std::tuple<at::Tensor, at::Tensor> fe_lfr_cmvn(int64_t h, const at::Tensor& fbank, const at::Tensor& n_frames) {
+  TORCH_CHECK(fbank.is_cuda() && fbank.scalar_type() == at::kFloat && fbank.dim() == 3,
+              "b200fe.lfr_cmvn: features must be a CUDA float32 [B, T, n_mels] tensor");
+  c10::cuda::CUDAGuard guard(fbank.device());
+  auto x = fbank.contiguous();
+  auto nf = n_frames.to(at::kCPU, at::kLong).contiguous();
+  const int b = (int)x.size(0);
+  TORCH_CHECK(nf.numel() == b, "n_frames size mismatch");
+  int64_t max_rows = 0;
+  // rows per utterance = ceil(T / lfr_n): size the output from the largest frame count
+  const int64_t d = b200fe_output_dim(H(h));
+  const int64_t m = x.size(2);
+  TORCH_CHECK(d % m == 0, "feature dim does not match the front-end");
+  int64_t tmax = 0;
+  for (int i = 0; i < b; ++i) tmax = std::max<int64_t>(tmax, nf.data_ptr<int64_t>()[i]);
+  // lfr_n is not exported; recover rows via plan-free arithmetic in the library: ask with rows_cap = tmax (upper bound)
+  max_rows = tmax;
+  auto feats_full = at::empty({b, max_rows, d}, x.options());
+  auto lens = at::empty({b}, x.options().dtype(at::kLong));
+  auto work = at::empty({(int64_t)(256 + 64 * (int64_t)b + 512)}, x.options().dtype(at::kByte));
+  check(b200fe_lfr_cmvn(H(h), x.data_ptr<float>(), x.size(1), nf.data_ptr<int64_t>(), b, feats_full.data_ptr<float>(), max_rows,
+                        lens.data_ptr<int64_t>(), work.data_ptr(), (size_t)work.numel(), cur_stream()),
+        H(h), "b200fe_lfr_cmvn");
+  return {feats_full, lens};
+}
+
+std::tuple<at::Tensor, at::Tensor> fe_get_tables(int64_t h) {
+  const int L = b200fe_frame_samples(H(h)), nfft = b200fe_fft_size(H(h));
+  const int d = b200fe_output_dim(H(h));
+  (void)d;
+  auto win = at::empty({L}, at::kFloat);
+  // n_mels is recovered from the caller; the library writes n_mels * nfft/2 floats
+  auto mel = at::zeros({128, nfft / 2}, at::kFloat);
+  check(b200fe_get_tables(H(h), win.data_ptr<float>(), mel.data_ptr<float>()), H(h), "b200fe_get_tables");
+  return {win, mel};
+}
+
+std::vector<int64_t> fe_geometry(int64_t h) {
+  return {b200fe_frame_samples(H(h)), b200fe_shift_samples(H(h)), b200fe_fft_size(H(h)), b200fe_output_dim(H(h))};
+}
+
+at::Tensor fe_stream_state(int64_t h, int64_t n_streams, int64_t max_chunk, c10::Device device) {
+  size_t bytes = 0;
+  check(b200fe_stream_state_bytes(H(h), (int)n_streams, (int)max_chunk, &bytes), H(h), "b200fe_stream_state_bytes");
+  TORCH_CHECK(device.is_cuda(), "stream state must live on a CUDA device");
+  c10::cuda::CUDAGuard guard(device);
+  auto st = at::zeros({(int64_t)bytes}, at::TensorOptions().dtype(at::kByte).device(device));
+  return st;
+}
+
+int64_t fe_stream_max_rows(int64_t h, int64_t max_chunk) { return b200fe_stream_max_rows(H(h), (int)max_chunk); }
+
+void fe_stream_reset(int64_t h, at::Tensor state, int64_t n_streams, int64_t max_chunk, const c10::optional<at::Tensor>& ids) {
+  TORCH_CHECK(state.is_cuda(), "state must be CUDA");
+  c10::cuda::CUDAGuard guard(state.device());
+  const int32_t* idp = nullptr;
+  int n = 0;
+  at::Tensor idt;
+  if (ids.has_value() && ids->defined()) {
+    idt = ids->to(state.device(), at::kInt).contiguous();
+    idp = idt.data_ptr<int32_t>();
+    n = (int)idt.numel();
+  }
+  check(b200fe_stream_reset(H(h), state.data_ptr(), (int)n_streams, (int)max_chunk, idp, n, cur_stream()), H(h),
+        "b200fe_stream_reset");
+}
+
+std::tuple<at::Tensor, at::Tensor> fe_stream_push(int64_t h, at::Tensor state, int64_t n_streams, int64_t max_chunk,
+                                                  const at::Tensor& chunks, const at::Tensor& chunk_lens,
+                                                  const at::Tensor& stream_ids, const c10::optional<at::Tensor>& is_final) {
+  TORCH_CHECK(state.is_cuda() && chunks.is_cuda(), "b200fe.stream_push: state and chunks must be CUDA tensors");
+  TORCH_CHECK(chunks.scalar_type() == at::kFloat && chunks.dim() == 2, "chunks must be float32 [n, chunk_max]");
+  c10::cuda::CUDAGuard guard(chunks.device());
+  auto c = chunks.contiguous();
+  const int n = (int)c.size(0);
+  TORCH_CHECK(c.size(1) <= max_chunk, "chunk wider than max_chunk_samples");
+  auto cl = chunk_lens.to(c.device(), at::kInt).contiguous();
+  auto ids = stream_ids.to(c.device(), at::kInt).contiguous();
+  TORCH_CHECK(cl.numel() == n && ids.numel() == n, "chunk_lens / stream_ids size mismatch");
+  at::Tensor fin;
+  const uint8_t* finp = nullptr;
+  if (is_final.has_value() && is_final->defined()) {
+    fin = is_final->to(c.device(), at::kByte).contiguous();
+    TORCH_CHECK(fin.numel() == n, "is_final size mismatch");
+    finp = fin.data_ptr<uint8_t>();
+  }
+  const int64_t rows_cap = b200fe_stream_max_rows(H(h), (int)max_chunk);
+  const int64_t d = b200fe_output_dim(H(h));
+  auto feats = at::empty({n, rows_cap, d}, c.options());
+  auto rows = at::empty({n}, c.options().dtype(at::kInt));
+  check(b200fe_stream_push(H(h), state.data_ptr(), (int)n_streams, (int)max_chunk, c.data_ptr<float>(), c.size(1),
+                           cl.data_ptr<int32_t>(), ids.data_ptr<int32_t>(), finp, n, feats.data_ptr<float>(), rows_cap,
+                           rows.data_ptr<int32_t>(), cur_stream()),
+        H(h), "b200fe_stream_push");
+  return {feats, rows};
+}
+
+void fe_synth_uniform(at::Tensor wave, const at::Tensor& offsets, const at::Tensor& lengths, int64_t seed, double amp) {
+  TORCH_CHECK(wave.is_cuda() && wave.scalar_type() == at::kFloat && wave.is_contiguous(), "wave must be contiguous CUDA float32");
+  c10::cuda::CUDAGuard guard(wave.device());
+  auto off = offsets.to(wave.device(), at::kLong).contiguous();
+  auto len = lengths.to(wave.device(), at::kLong).contiguous();
+  int rc = b200fe_synth_uniform(wave.data_ptr<float>(), off.data_ptr<int64_t>(), len.data_ptr<int64_t>(), (int)len.numel(),
+                                (uint64_t)seed, (float)amp, cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_synth_uniform failed");
+}
+
+int64_t fe_launch_count(int64_t h) { return b200fe_launch_count(H(h)); }
+
+void fe_profile_enable(int64_t h, bool on) { check(b200fe_profile_enable(H(h), on), H(h), "b200fe_profile_enable"); }
+
+std::tuple<double, int64_t> fe_profile_collect(int64_t h) {
+  double ms = 0.0;
+  int64_t n = 0;
+  check(b200fe_profile_collect(H(h), &ms, &n), H(h), "b200fe_profile_collect");
+  return {ms, n};
+}
+
+}  // namespace
+
+TORCH_LIBRARY(b200fe, m) {
+  m.def("create(int fs, float frame_length, float frame_shift, int n_mels, int window_type, int lfr_m, int lfr_n, "
+        "float dither, bool snip_edges, bool upscale, float preemph, bool remove_dc, float low_freq, float high_freq, "
+        "float blackman_coeff, Tensor? cmvn) -> int", fe_create);
+  m.def("destroy(int h) -> ()", fe_destroy);
+  m.def("plan(int h, Tensor lengths) -> (Tensor, Tensor)", fe_plan);
+  m.def("forward(int h, Tensor wave, Tensor? offsets, Tensor lengths, int rows_cap, Tensor? stats, int seed) -> (Tensor, Tensor)",
+        fe_forward);
+  m.def("lfr_cmvn(int h, Tensor fbank, Tensor n_frames) -> (Tensor, Tensor)", fe_lfr_cmvn);
+  m.def("get_tables(int h) -> (Tensor, Tensor)", fe_get_tables);
+  m.def("geometry(int h) -> int[]", fe_geometry);
+  m.def("stream_state(int h, int n_streams, int max_chunk, Device device) -> Tensor", fe_stream_state);
+  m.def("stream_max_rows(int h, int max_chunk) -> int", fe_stream_max_rows);
+  m.def("stream_reset(int h, Tensor state, int n_streams, int max_chunk, Tensor? ids) -> ()", fe_stream_reset);
+  m.def("stream_push(int h, Tensor state, int n_streams, int max_chunk, Tensor chunks, Tensor chunk_lens, Tensor stream_ids, "
+        "Tensor? is_final) -> (Tensor, Tensor)", fe_stream_push);
+  m.def("synth_uniform(Tensor wave, Tensor offsets, Tensor lengths, int seed, float amp) -> ()", fe_synth_uniform);
+  m.def("launch_count(int h) -> int", fe_launch_count);
+  m.def("profile_enable(int h, bool on) -> ()", fe_profile_enable);
+  m.def("profile_collect(int h) -> (float, int)", fe_profile_collect);
+}

@@ -1,0 +1,99 @@
+"""Streaming front-end on device-resident state.
+
+`StreamPool` is the B200-native form: S concurrent streams share one HBM state slab (sample carry, LFR splice frames,
+counters per stream) and every tick is ONE kernel launch over all streams that received a chunk.  It replaces both the
+upstream per-connection `WavFrontendOnline` cache dict and the reference's host-side np.concatenate accumulation
+(R:voice-service/app/services/voice_interface.py:1304-1311,1688-1746).
+
+`WavFrontendOnline` keeps upstream's single-stream call shape - forward(input[1, n], input_lengths, cache=dict,
+is_final=bool) -> (feats[1, k, D], feats_lengths) - on top of a one-stream pool whose state tensor lives in `cache`.
+Semantics: concat(stream outputs) == offline output; the final flush always completes ceil(T/lfr_n) rows.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .frontend import WavFrontend, _as_length_tensor
+
+
+class StreamPool:
+    def __init__(self, frontend: WavFrontend, n_streams: int, max_chunk_samples: int, device="cuda"):
+        self.frontend = frontend
+        self.n_streams = int(n_streams)
+        self.max_chunk = int(max_chunk_samples)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("StreamPool state must live on a CUDA device (no CPU fallback)")
+        self._h = frontend._handle(lfr=True, cmvn=True)
+        ops = self._h.ops
+        self.state = ops.stream_state(self._h.h, self.n_streams, self.max_chunk, self.device)
+        self.rows_cap = int(ops.stream_max_rows(self._h.h, self.max_chunk))
+        self.reset()
+
+    def reset(self, stream_ids: Optional[torch.Tensor] = None) -> None:
+        self._h.ops.stream_reset(self._h.h, self.state, self.n_streams, self.max_chunk, stream_ids)
+
+    def push(self, chunks: torch.Tensor, chunk_lens: torch.Tensor, stream_ids: torch.Tensor,
+             is_final: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """chunks: CUDA float32 [n, <=max_chunk]; returns (feats [n, rows_cap, D], rows int32 [n]) on the device,
+        without synchronising.  stream_ids must be distinct within one call."""
+        if not chunks.is_cuda:
+            raise RuntimeError("chunks must be a CUDA tensor: the B200 front-end has no CPU fallback")
+        return self._h.ops.stream_push(self._h.h, self.state, self.n_streams, self.max_chunk, chunks, chunk_lens,
+                                       stream_ids, is_final)
+
+    def snapshot(self) -> torch.Tensor:
+        """Checkpoint of every stream (one memcpy of the slab)."""
+        return self.state.clone()
+
+    def restore(self, snap: torch.Tensor) -> None:
+        self.state.copy_(snap)
+
+
+class WavFrontendOnline(WavFrontend):
+    """Chunked front-end with upstream's call shape (batch size 1, state in the caller's `cache` dict)."""
+
+    def __init__(self, *args, max_chunk_samples: int = 16000, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.max_chunk_samples = int(max_chunk_samples)
+        self.frame_sample_length = int(self.frame_length * self.fs / 1000)
+        self.frame_shift_sample_length = int(self.frame_shift * self.fs / 1000)
+
+    def init_cache(self, cache: dict, device="cuda") -> dict:
+        cache["pool"] = StreamPool(self, 1, self.max_chunk_samples, device)
+        cache["ids"] = torch.zeros(1, dtype=torch.int32, device=device)
+        return cache
+
+    def forward(self, input: torch.Tensor, input_lengths, cache: Optional[dict] = None, is_final: bool = False,
+                **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        self._check_cuda(input, "input")
+        assert input.shape[0] == 1, "we support to extract feature online only when the batch size is equal to 1 now"
+        if cache is None:
+            cache = {}
+        if "pool" not in cache:
+            self.init_cache(cache, input.device)
+        pool: StreamPool = cache["pool"]
+        n = int(_as_length_tensor(input_lengths)[0])
+        x = input[0, :n].to(torch.float32)
+        outs = []
+        pos = 0
+        while True:
+            m = min(self.max_chunk_samples, n - pos)
+            last = pos + m >= n
+            chunk = torch.zeros(1, self.max_chunk_samples, dtype=torch.float32, device=input.device)
+            chunk[0, :m] = x[pos:pos + m]
+            fin = torch.tensor([1 if (is_final and last) else 0], dtype=torch.uint8, device=input.device)
+            feats, rows = pool.push(chunk, torch.tensor([m], dtype=torch.int32, device=input.device), cache["ids"], fin)
+            k = int(rows[0])   # the reference returns exact-size tensors, so this path synchronises
+            if k:
+                outs.append(feats[0, :k])
+            pos += m
+            if last:
+                break
+        if not outs:
+            return torch.empty(0, device=input.device), torch.zeros(1, dtype=torch.int64)
+        out = torch.cat(outs, dim=0).unsqueeze(0)
+        return out, torch.as_tensor([out.shape[1]], dtype=torch.int64)
