@@ -139,6 +139,30 @@ short_utt_kernel(const float* wave, const ShortDesc* descs, const float* short_m
 
 __global__ void add_count_kernel(double* dst, double v) { *dst += v; }
 
+// Expands the per-utterance descriptors into the launch-wide tile list (one thread per tile).
+__global__ void build_tiles_kernel(const UttDesc* utts, int batch, int n_tiles, int rows_per_tile, int lfr_m, int lfr_n,
+                                   int S, TileDesc* tiles) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  int lo = 0, hi = batch - 1;   // last utterance whose tile_begin <= t (utterances without tiles share the next begin)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (utts[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+  }
+  const UttDesc ud = utts[lo];
+  const int left = (lfr_m - 1) / 2;
+  TileDesc d;
+  d.utt = lo;
+  d.T = ud.n_frames;
+  d.row0 = (t - ud.tile_begin) * rows_per_tile;
+  d.nrow = min(rows_per_tile, ud.n_rows - d.row0);
+  d.f_lo = min(max(lfr_n * d.row0 - left, 0), d.T - 1);
+  const int f_hi = min(max(lfr_n * (d.row0 + d.nrow - 1) - left + lfr_m - 1, 0), d.T - 1);
+  d.F = f_hi - d.f_lo + 1;
+  d.g0 = ud.wave_off + (long long)d.f_lo * S;
+  tiles[t] = d;
+}
+
 // Counter-based synthetic PCM, bit-identical to toolbox_for_asr_and_tts_b200/synth.py::uniform_pcm.
 __device__ __forceinline__ unsigned long long synth_mix(unsigned long long seed, unsigned long long u,
                                                         unsigned long long n) {

@@ -42,7 +42,7 @@ struct b200fe_handle {
   std::vector<float> window_host;   // [L], without upscale
   std::vector<float> mel_host;      // [n_mels, nfft/2]
   float* d_window = nullptr;        // [512]
-  float2* d_twiddle = nullptr;      // [17*16]
+  float2* d_twiddle = nullptr;      // [17*kXRow]
   float* d_mel_w = nullptr;         // [kMaxNnz]
   int* d_mel_desc = nullptr;        // [kMaxMels]
   float* d_cmvn = nullptr;          // [2*D]
@@ -176,7 +176,10 @@ int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, 
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-size_t workspace_need(int batch) { return align256((size_t)batch * sizeof(UttDesc)) + align256((size_t)batch * sizeof(ShortDesc)); }
+size_t workspace_need(int batch, int n_tiles = 0) {
+  return align256((size_t)batch * sizeof(UttDesc)) + align256((size_t)batch * sizeof(ShortDesc)) +
+         align256((size_t)n_tiles * sizeof(TileDesc));
+}
 
 // stream-ordered upload through a small ring of pinned buffers
 int upload(b200fe_handle* h, const void* src, size_t bytes, void* dst, cudaStream_t st) {
@@ -337,11 +340,11 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
     md[m] = (lo < 0 ? 1 : lo) | (cnt << 9) | (off << 18);
     off += cnt;
   }
-  std::vector<float2> tw(17 * 16);
+  std::vector<float2> tw(17 * kXRow, make_float2(0.f, 0.f));
   for (int r = 0; r < 17; ++r)
     for (int n2 = 0; n2 < 16; ++n2) {
       const int ph = (n2 * r) & 511;
-      tw[r * 16 + n2] = make_float2((float)cos(2.0 * M_PI * ph / 512.0), (float)(-sin(2.0 * M_PI * ph / 512.0)));
+      tw[r * kXRow + n2] = make_float2((float)cos(2.0 * M_PI * ph / 512.0), (float)(-sin(2.0 * M_PI * ph / 512.0)));
     }
   CK(cudaMalloc(&h->d_window, 512 * sizeof(float)));
   CK(cudaMalloc(&h->d_twiddle, tw.size() * sizeof(float2)));
@@ -425,7 +428,7 @@ int b200fe_plan(b200fe_handle* h, const int64_t* lengths_host, int batch, int64_
     if (n_rows_out) n_rows_out[u] = pl.utts[u].n_rows;
   }
   if (max_rows_out) *max_rows_out = pl.max_rows;
-  if (workspace_bytes) *workspace_bytes = workspace_need(batch);
+  if (workspace_bytes) *workspace_bytes = workspace_need(batch, pl.n_tiles);
   return B200FE_OK;
 }
 
@@ -437,12 +440,12 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
   if (batch == 0) return B200FE_OK;
   if (!wave_dev || !lengths_host || !feats_dev || !workspace_dev || batch < 0)
     return fail(h, B200FE_E_INVALID, "null argument");
-  if (workspace_bytes < workspace_need(batch)) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lock(h->mu);
   Plan pl;
   int rc = make_plan(h, lengths_host, offsets_host, row_stride, batch, pl);
   if (rc) return rc;
+  if (workspace_bytes < workspace_need(batch, pl.n_tiles)) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
   if (pl.max_rows > rows_cap) return fail(h, B200FE_E_INVALID, "rows_cap smaller than the longest utterance's row count");
   for (int u = 0; u < batch; ++u) {
     const long long end = pl.utts[u].wave_off + lengths_host[u];
@@ -450,7 +453,14 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
   }
   UttDesc* d_utts = reinterpret_cast<UttDesc*>(workspace_dev);
   ShortDesc* d_shorts = reinterpret_cast<ShortDesc*>((char*)workspace_dev + align256((size_t)batch * sizeof(UttDesc)));
+  TileDesc* d_tiles = reinterpret_cast<TileDesc*>((char*)d_shorts + align256((size_t)batch * sizeof(ShortDesc)));
   if ((rc = upload(h, pl.utts.data(), (size_t)batch * sizeof(UttDesc), d_utts, st))) return rc;
+  if (pl.n_tiles > 0) {
+    build_tiles_kernel<<<(pl.n_tiles + 255) / 256, 256, 0, st>>>(d_utts, batch, pl.n_tiles, h->rows_per_tile, h->cfg.lfr_m,
+                                                                 h->cfg.lfr_n, h->S, d_tiles);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
 
   // 1. padding rows + feat_lens
   {
@@ -464,7 +474,7 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
   // 2. the fused tile kernel over all regular utterances
   if (pl.n_tiles > 0) {
     TileParams p;
-    p.wave = wave_dev; p.wave_total = wave_total; p.utts = d_utts; p.batch = batch; p.n_tiles = pl.n_tiles;
+    p.wave = wave_dev; p.wave_total = wave_total; p.utts = d_utts; p.tiles = d_tiles; p.batch = batch; p.n_tiles = pl.n_tiles;
     p.feats = feats_dev; p.rows_cap = rows_cap; p.stats = stats_dev;
     p.frame_len = h->L; p.frame_shift = h->S; p.n_mels = h->cfg.n_mels;
     p.lfr_m = h->cfg.lfr_m; p.lfr_n = h->cfg.lfr_n; p.rows_per_tile = h->rows_per_tile; p.e_cap = h->e_cap;

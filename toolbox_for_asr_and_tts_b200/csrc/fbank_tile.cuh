@@ -43,10 +43,23 @@ struct UttDesc {          // built on the host by b200fe_plan/forward
   int tile_begin;         // index of the utterance's first tile in the launch-wide tile list
 };
 
+// One tile of the launch-wide work list, fully resolved by build_tiles_kernel so that the fused kernel never chases a
+// dependent global load: 32 bytes, read one tile ahead.
+struct __align__(16) TileDesc {
+  long long g0;   // absolute index (in the wave buffer) of the first sample of the tile's first frame
+  int utt;
+  int row0;       // first LFR row of the tile
+  int f_lo;       // first frame of the tile
+  int F;          // frames in the tile (<= kFMax)
+  int nrow;       // LFR rows in the tile
+  int T;          // frames of the utterance
+};
+
 struct TileParams {
   const float* wave;
   long long wave_total;
   const UttDesc* utts;
+  const TileDesc* tiles;  // [n_tiles], built on the device from utts
   int batch;
   int n_tiles;
   float* feats;           // [batch, rows_cap, out_dim]
@@ -63,7 +76,7 @@ struct TileParams {
   float dither;
   unsigned long long seed;
   const float* window;    // [512] window * (2^15 if upscale), zero beyond L
-  const float2* twiddle;  // [17][16]  exp(-2*pi*i*n2*r/512)
+  const float2* twiddle;  // [17][kXRow]  exp(-2*pi*i*n2*r/512), rows padded like the transpose buffer (bank conflicts)
   const float* mel_w;     // [kMaxNnz] packed non-zero weights (x 0.25: the spectra below are 4*|X|^2)
   const int* mel_desc;    // [n_mels]  lo | cnt << 9 | off << 18
   const float* cmvn;      // nullptr or [2][out_dim]
@@ -75,7 +88,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int e_cap, int n_mels) {
   b += 2 * kFMax * 4;                               // raw first / last sample of each frame
   b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;      // transpose buffers (aliased by the power spectra)
   b += (size_t)kFMax * n_mels * 4;                  // log-mel of the tile
-  b += 17 * 16 * 8;                                 // twiddles
+  b += 17 * kXRow * 8;                                 // twiddles
   b += kMaxNnz * 4 + kMaxMels * 4;                  // sparse filterbank
   return b;
 }
@@ -108,7 +121,8 @@ __device__ __forceinline__ float dither_normal(unsigned long long seed, unsigned
 //   e_base   staged pre-emphasised samples, e_base[f*S + n] = x[n] - preemph*x[n-1] of tile-local frame f
 //   x0_s/xl_s raw first / last sample of every tile-local frame
 //   win      this thread's window taps (n = 16*i + j), already scaled by 2^15 when upscaling
-//   xg       this 16-thread group's transpose buffer; pbuf4 = the warp's [bin][4] spectra (aliases the warp's xg's)
+//   xg       this 16-thread group's transpose buffer; pbuf4 = the warp's spectra, [2 groups][256 bins] x (frame A, frame B),
+//            aliasing the warp's two xg's
 //   logmel   shared [F][M] destination
 // NROWS = ceil(frame_len / 16): rows of 16 samples that can be non-zero (25 for 400-sample frames, else 32).
 // EXACT: frame_len == 16*NROWS, so no per-sample bounds predicate is needed in the stage-1 load.
@@ -195,8 +209,8 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
   {
     const float4* rowA4 = reinterpret_cast<const float4*>(xg + j * kXRow);
     const float4* rowB4 = reinterpret_cast<const float4*>(xg + (32 - rowB) * kXRow);
-    const float4* twA4 = reinterpret_cast<const float4*>(tw_s + j * 16);
-    const float4* twB4 = reinterpret_cast<const float4*>(tw_s + rowB * 16);
+    const float4* twA4 = reinterpret_cast<const float4*>(tw_s + j * kXRow);
+    const float4* twB4 = reinterpret_cast<const float4*>(tw_s + rowB * kXRow);
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
       const float4 ya = rowA4[h], yb = rowB4[h], ta = twA4[h], tb = twB4[h];
@@ -235,7 +249,7 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
     A_RE(15) = t0 ? B_RE(15) : A_RE(15);
     A_IM(15) = t0 ? B_IM(15) : A_IM(15);
     const int binA = j, binB = 32 - rowB;
-    float2* pb2 = reinterpret_cast<float2*>(pbuf4) + grp_in_warp;   // [bin][2 groups] of (frame A, frame B)
+    float2* pb2 = reinterpret_cast<float2*>(pbuf4) + grp_in_warp * 256;   // [2 groups][256 bins] of (frame A, frame B)
     static_for<0, 16>([&](auto ic) {
       constexpr int i = decltype(ic)::value;
       const float ur = A_RE(i), ui = A_IM(i);
@@ -244,7 +258,7 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
       const float pA = fmaf(s1, s1, d1 * d1);   // 4 * |X_A[k]|^2
       const float pB = fmaf(s2, s2, d2 * d2);   // 4 * |X_B[k]|^2
       const int bin = i < 8 ? binA + 32 * i : binB + 32 * (15 - i);
-      if (!(t0 && i == 0)) pb2[2 * bin] = make_float2(pA, pB);
+      if (!(t0 && i == 0)) pb2[bin] = make_float2(pA, pB);
     });
 #undef A_RE
 #undef A_IM
@@ -258,13 +272,14 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
     const int d = meld_s[m];
     const int lo = d & 511, cnt = (d >> 9) & 511, off = d >> 18;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float2* pg0 = reinterpret_cast<const float2*>(pbuf4) + lo;
     for (int q = 0; q < cnt; ++q) {
       const float w = melw_s[off + q];
-      const float4 s = pbuf4[lo + q];
-      acc.x = fmaf(w, s.x, acc.x);
-      acc.y = fmaf(w, s.y, acc.y);
-      acc.z = fmaf(w, s.z, acc.z);
-      acc.w = fmaf(w, s.w, acc.w);
+      const float2 s0 = pg0[q], s1 = pg0[256 + q];
+      acc.x = fmaf(w, s0.x, acc.x);
+      acc.y = fmaf(w, s0.y, acc.y);
+      acc.z = fmaf(w, s1.x, acc.z);
+      acc.w = fmaf(w, s1.y, acc.w);
     }
     const int fr = 4 * quad;
     if (fr < F) logmel[fr * M + m] = __logf(fmaxf(acc.x, log_floor));
@@ -291,7 +306,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   float2* xbuf = reinterpret_cast<float2*>(xl_s + kFMax);
   float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + kFMax * p.n_mels);
-  float* melw_s = reinterpret_cast<float*>(tw_s + 17 * 16);
+  float* melw_s = reinterpret_cast<float*>(tw_s + 17 * kXRow);
   int* meld_s = reinterpret_cast<int*>(melw_s + kMaxNnz);
 
   const int tid = threadIdx.x;
@@ -304,7 +319,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   const int lfr_left = (p.lfr_m - 1) / 2;
 
   // ---- per-CTA constants: tables to shared memory, this thread's window taps to registers
-  for (int i = tid; i < 17 * 16; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  for (int i = tid; i < 17 * kXRow; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   for (int i = tid; i < kMaxNnz; i += kCtaThreads) melw_s[i] = p.mel_w[i];
   for (int i = tid; i < kMaxMels; i += kCtaThreads) meld_s[i] = i < M ? p.mel_desc[i] : 0;
   float win[NROWS];
@@ -344,55 +359,58 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   float2* xg = xbuf + (warp * 2 + grp_in_warp) * kXGroupFloat2;                 // this group's transpose buffer
   float4* pbuf4 = reinterpret_cast<float4*>(xbuf + warp * 2 * kXGroupFloat2);   // this warp's [bin][4 frames] spectra
 
+  // tile descriptors are read one tile ahead so that no dependent global load sits in front of a tile
+  TileDesc cur;
+  if (blockIdx.x < p.n_tiles) cur = p.tiles[blockIdx.x];
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    // ---- locate the tile: last utterance whose tile_begin <= tile (utterances without tiles share the next begin)
-    int utt;
-    {
-      int lo = 0, hi = p.batch - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (p.utts[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
-      }
-      utt = lo;
-    }
-    const UttDesc ud = p.utts[utt];
-    const int T = ud.n_frames;
-    const int row0 = (tile - ud.tile_begin) * p.rows_per_tile;
-    const int nrow = min(p.rows_per_tile, ud.n_rows - row0);
-    const int f_lo = min(max(p.lfr_n * row0 - lfr_left, 0), T - 1);
-    const int f_hi = min(max(p.lfr_n * (row0 + nrow - 1) - lfr_left + p.lfr_m - 1, 0), T - 1);
-    const int F = f_hi - f_lo + 1;                            // <= kFMax by construction of rows_per_tile
-    const long long g0 = ud.wave_off + (long long)f_lo * S;   // absolute index of the tile's first sample
+    const int tile_next = tile + gridDim.x;
+    TileDesc nxt = cur;
+    if (tile_next < p.n_tiles) nxt = p.tiles[tile_next];
+    const int utt = cur.utt, row0 = cur.row0, nrow = cur.nrow, T = cur.T, f_lo = cur.f_lo, F = cur.F;
+    const long long g0 = cur.g0;
     const int a_off = (int)((wave_mis + (unsigned)(g0 & 3)) & 3);
     const long long ga = g0 - a_off;                          // 16-byte aligned load grid
     const int n_s = (F - 1) * S + L;
 
-    // ---- stage: HBM -> (pre-emphasis) -> shared, 128-bit both ways
+    // ---- stage: HBM -> (pre-emphasis) -> shared, 128-bit both ways.  All loads of a batch are issued before the
+    //      first use, so a tile pays one memory latency instead of one per iteration.
     {
       const int nv = (a_off + n_s + 3) >> 2;
-      for (int v0 = warp * 32; v0 < nv; v0 += kCtaThreads) {
-        const int v = v0 + lane;
-        const long long ab = ga + 4ll * v;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v < nv) {
-          if (ab >= 0 && ab + 3 < p.wave_total) {
-            x = ldg_stream4(p.wave + ab);
-          } else {
-            if (ab >= 0 && ab < p.wave_total) x.x = p.wave[ab];
-            if (ab + 1 >= 0 && ab + 1 < p.wave_total) x.y = p.wave[ab + 1];
-            if (ab + 2 >= 0 && ab + 2 < p.wave_total) x.z = p.wave[ab + 2];
-            if (ab + 3 >= 0 && ab + 3 < p.wave_total) x.w = p.wave[ab + 3];
+      constexpr int kBatch = 6;
+      for (int vb = 0; vb < nv; vb += kBatch * kCtaThreads) {
+        float4 x[kBatch];
+        float pv[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int v = vb + u * kCtaThreads + tid;
+          const long long ab = ga + 4ll * v;
+          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          pv[u] = 0.f;
+          if (v < nv) {
+            if (ab >= 0 && ab + 3 < p.wave_total) {
+              x[u] = ldg_stream4(p.wave + ab);
+            } else {
+              if (ab >= 0 && ab < p.wave_total) x[u].x = p.wave[ab];
+              if (ab + 1 >= 0 && ab + 1 < p.wave_total) x[u].y = p.wave[ab + 1];
+              if (ab + 2 >= 0 && ab + 2 < p.wave_total) x[u].z = p.wave[ab + 2];
+              if (ab + 3 >= 0 && ab + 3 < p.wave_total) x[u].w = p.wave[ab + 3];
+            }
+            if (lane == 0 && ab >= 1 && ab - 1 < p.wave_total) pv[u] = p.wave[ab - 1];
           }
         }
-        float prev = __shfl_up_sync(0xffffffffu, x.w, 1);
-        if (lane == 0) prev = (v < nv && ab >= 1 && ab - 1 < p.wave_total) ? p.wave[ab - 1] : 0.f;
-        if (v < nv) {
-          float4 e;
-          e.x = fmaf(-p.preemph, prev, x.x);
-          e.y = fmaf(-p.preemph, x.x, x.y);
-          e.z = fmaf(-p.preemph, x.y, x.z);
-          e.w = fmaf(-p.preemph, x.z, x.w);
-          *reinterpret_cast<float4*>(e_s + 4 * v) = e;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int v = vb + u * kCtaThreads + tid;
+          float prev = __shfl_up_sync(0xffffffffu, x[u].w, 1);
+          if (lane == 0) prev = pv[u];
+          if (v < nv) {
+            float4 e;
+            e.x = fmaf(-p.preemph, prev, x[u].x);
+            e.y = fmaf(-p.preemph, x[u].x, x[u].y);
+            e.z = fmaf(-p.preemph, x[u].y, x[u].z);
+            e.w = fmaf(-p.preemph, x[u].z, x[u].w);
+            *reinterpret_cast<float4*>(e_s + 4 * v) = e;
+          }
         }
       }
       if (tid < F) {
@@ -401,6 +419,16 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
       }
     }
     __syncthreads();
+
+    // ---- pull the next tile's samples into L2 while this tile computes (one prefetch per 128-byte line)
+    if (tile_next < p.n_tiles) {
+      const long long nb = nxt.g0 & ~31ll;
+      const int lines = (((nxt.F - 1) * S + L + 32 + 31) >> 5);
+      for (int ln = tid; ln < lines; ln += kCtaThreads) {
+        const long long idx = nb + 32ll * ln;
+        if (idx >= 0 && idx < p.wave_total) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wave + idx));
+      }
+    }
 
     // ---- per warp: quads of 4 frames (2 groups x 2 frames), no CTA-wide sync inside
     for (int quad = warp; 4 * quad < F; quad += kWarps)
@@ -435,6 +463,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
         }
       }
     }
+    cur = nxt;
     __syncthreads();   // the tile's shared buffers are free again
   }
 
