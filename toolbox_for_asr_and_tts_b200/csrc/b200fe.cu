@@ -42,9 +42,9 @@ struct b200fe_handle {
   std::vector<float> window_host;   // [L], without upscale
   std::vector<float> mel_host;      // [n_mels, nfft/2]
   float* d_window = nullptr;        // [512]
-  float2* d_twiddle = nullptr;      // [17*kXRow]
-  float* d_mel_w = nullptr;         // [kMaxNnz]
-  int* d_mel_desc = nullptr;        // [kMaxMels]
+  float2* d_twiddle = nullptr;      // [2*kTwTable]
+  float2* d_mel_w = nullptr;        // [kMaxNnz] (up, down) per bin
+  int* d_mel_desc = nullptr;        // [kMaxInt] per interval
   float* d_cmvn = nullptr;          // [2*D]
   // dense mel banks for shrunken frames (VF:147), keyed by fft size
   std::map<int, int> short_mel_off;
@@ -325,35 +325,67 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
   if (build_mel(cfg->n_mels, nfft, cfg->sample_rate, cfg->low_freq, cfg->high_freq, h->mel_host) != 0)
     return bail(B200FE_E_INVALID, "Bad values in options: low-freq / high-freq vs. nyquist");
 
-  // sparse filterbank: per filter a contiguous run of non-zero bins
-  std::vector<float> mw(kMaxNnz, 0.f);
-  std::vector<int> md(kMaxMels, 0);
-  int off = 0;
-  const int nb = nfft / 2;
-  for (int m = 0; m < cfg->n_mels; ++m) {
-    int lo = -1, hi = -1;
-    for (int k = 0; k < nb; ++k)
-      if (h->mel_host[(size_t)m * nb + k] > 0.f) { if (lo < 0) lo = k; hi = k; }
-    const int cnt = lo < 0 ? 0 : hi - lo + 1;
-    if (lo == 0 || off + cnt > kMaxNnz) return bail(B200FE_E_UNSUPPORTED, "mel filterbank does not fit the sparse layout");
-    for (int q = 0; q < cnt; ++q) mw[off + q] = 0.25f * h->mel_host[(size_t)m * nb + lo + q];
-    md[m] = (lo < 0 ? 1 : lo) | (cnt << 9) | (off << 18);
-    off += cnt;
-  }
-  std::vector<float2> tw(17 * kXRow, make_float2(0.f, 0.f));
-  for (int r = 0; r < 17; ++r)
-    for (int n2 = 0; n2 < 16; ++n2) {
-      const int ph = (n2 * r) & 511;
-      tw[r * kXRow + n2] = make_float2((float)cos(2.0 * M_PI * ph / 512.0), (float)(-sin(2.0 * M_PI * ph / 512.0)));
+  // sparse filterbank by interval: interval iv = bins whose mel lies in [centre(iv-1), centre(iv)); such a bin feeds
+  // the up-slope of filter iv and the down-slope of filter iv-1 and nothing else (TA:494-499, triangles in mel domain)
+  std::vector<float2> mw(kMaxNnz, make_float2(0.f, 0.f));
+  std::vector<int> md(kMaxInt, 0);
+  {
+    const int nb = nfft / 2, nm = cfg->n_mels;
+    std::vector<int> iv_of(nb, -1);
+    int prev = 0;
+    for (int k = 0; k < nb; ++k) {
+      int first = -1, last = -1, nz = 0;
+      for (int m = 0; m < nm; ++m)
+        if (h->mel_host[(size_t)m * nb + k] > 0.f) { if (first < 0) first = m; last = m; ++nz; }
+      if (nz == 0) continue;
+      if (nz > 2 || last - first > 1) return bail(B200FE_E_UNSUPPORTED, "mel filterbank is not a 2-banded triangle bank");
+      // two weights: up-slope of `last`, down-slope of `first` -> interval `last`.  One weight (interval 0, the last
+      // interval, or a bin exactly on a centre): either neighbour interval yields the same sum; keep the run monotone.
+      const int iv = nz == 2 ? last : (prev <= first ? first : first + 1);
+      if (iv < prev) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not monotone");
+      iv_of[k] = iv;
+      prev = iv;
     }
+    // intervals must be contiguous, increasing runs of bins
+    int off = 0, k = 0;
+    for (int iv = 0; iv <= nm; ++iv) {
+      while (k < nb && iv_of[k] < iv) {
+        if (iv_of[k] >= 0) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not monotone");
+        ++k;
+      }
+      const int lo = k;
+      int cnt = 0;
+      while (k < nb && iv_of[k] == iv) {
+        const float up = iv < nm ? h->mel_host[(size_t)iv * nb + k] : 0.f;
+        const float dn = iv >= 1 ? h->mel_host[(size_t)(iv - 1) * nb + k] : 0.f;
+        if (off + cnt >= kMaxNnz) return bail(B200FE_E_UNSUPPORTED, "mel filterbank does not fit the sparse layout");
+        mw[off + cnt] = make_float2(0.25f * up, 0.25f * dn);
+        ++cnt;
+        ++k;
+      }
+      if (cnt > 0 && lo == 0) return bail(B200FE_E_UNSUPPORTED, "FFT bin 0 must not carry mel weight");
+      md[iv] = (cnt ? lo : 1) | (cnt << 9) | (off << 18);
+      off += cnt;
+    }
+    for (; k < nb; ++k)
+      if (iv_of[k] >= 0) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not monotone");
+  }
+  std::vector<float2> tw(2 * kTwTable, make_float2(0.f, 0.f));
+  for (int g = 0; g < 2; ++g)
+    for (int r = 0; r < kTwRows; ++r)
+      for (int n2 = 0; n2 < 16; ++n2) {
+        const int ph = (((n2 - 16 * g) * r) % 512 + 512) % 512;
+        tw[g * kTwTable + r * kXRow + n2] =
+            make_float2((float)cos(2.0 * M_PI * ph / 512.0), (float)(-sin(2.0 * M_PI * ph / 512.0)));
+      }
   CK(cudaMalloc(&h->d_window, 512 * sizeof(float)));
   CK(cudaMalloc(&h->d_twiddle, tw.size() * sizeof(float2)));
-  CK(cudaMalloc(&h->d_mel_w, kMaxNnz * sizeof(float)));
-  CK(cudaMalloc(&h->d_mel_desc, kMaxMels * sizeof(int)));
+  CK(cudaMalloc(&h->d_mel_w, kMaxNnz * sizeof(float2)));
+  CK(cudaMalloc(&h->d_mel_desc, kMaxInt * sizeof(int)));
   CK(cudaMemcpy(h->d_window, win512.data(), 512 * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(h->d_mel_w, mw.data(), kMaxNnz * sizeof(float), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(h->d_mel_desc, md.data(), kMaxMels * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_mel_w, mw.data(), kMaxNnz * sizeof(float2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_mel_desc, md.data(), kMaxInt * sizeof(int), cudaMemcpyHostToDevice));
   if (cmvn_host) {
     CK(cudaMalloc(&h->d_cmvn, 2 * h->D * sizeof(float)));
     CK(cudaMemcpy(h->d_cmvn, cmvn_host, 2 * h->D * sizeof(float), cudaMemcpyHostToDevice));

@@ -32,7 +32,10 @@ constexpr int kFMax = 32;           // frames per tile (upper bound)
 constexpr int kXRow = 18;           // float2 per transpose row: 16 + 2 pad -> 144 B, conflict-free 128-bit reads
 constexpr int kXGroupFloat2 = 32 * kXRow;
 constexpr int kMaxMels = 128;
-constexpr int kMaxNnz = 512;        // every FFT bin feeds at most 2 triangular filters
+constexpr int kMaxNnz = 256;        // one (up, down) weight pair per FFT bin: a bin feeds at most 2 triangular filters
+constexpr int kMaxInt = kMaxMels + 1;  // intervals between consecutive filter centres
+constexpr int kTwRows = 17;         // twiddle rows 0..16 (row 16 serves thread 0's second column)
+constexpr int kTwTable = kTwRows * kXRow;
 constexpr int kNfft = 512;
 
 struct UttDesc {          // built on the host by b200fe_plan/forward
@@ -76,9 +79,10 @@ struct TileParams {
   float dither;
   unsigned long long seed;
   const float* window;    // [512] window * (2^15 if upscale), zero beyond L
-  const float2* twiddle;  // [17][kXRow]  exp(-2*pi*i*n2*r/512), rows padded like the transpose buffer (bank conflicts)
-  const float* mel_w;     // [kMaxNnz] packed non-zero weights (x 0.25: the spectra below are 4*|X|^2)
-  const int* mel_desc;    // [n_mels]  lo | cnt << 9 | off << 18
+  const float2* twiddle;  // [2][17][kXRow]: table g is exp(-2*pi*i*(n2 - 16*g)*r/512); rows padded like the transpose
+                          // buffer.  Table 1 undoes the one-row rotation group 1 applies to its sample loads.
+  const float2* mel_w;    // [kMaxNnz] (up, down) weight of every FFT bin inside its interval, x 0.25 (spectra are 4|X|^2)
+  const int* mel_desc;    // [n_mels + 1] per interval between filter centres: lo | cnt << 9 | off << 18
   const float* cmvn;      // nullptr or [2][out_dim]
 };
 
@@ -88,8 +92,8 @@ __host__ __device__ inline size_t tile_smem_bytes(int e_cap, int n_mels) {
   b += 2 * kFMax * 4;                               // raw first / last sample of each frame
   b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;      // transpose buffers (aliased by the power spectra)
   b += (size_t)kFMax * n_mels * 4;                  // log-mel of the tile
-  b += 17 * kXRow * 8;                                 // twiddles
-  b += kMaxNnz * 4 + kMaxMels * 4;                  // sparse filterbank
+  b += 2 * kTwTable * 8;                            // twiddles (one table per group of a warp)
+  b += kMaxNnz * 8 + ((kMaxInt + 3) & ~3) * 4;      // sparse filterbank
   return b;
 }
 
@@ -126,23 +130,43 @@ __device__ __forceinline__ float dither_normal(unsigned long long seed, unsigned
 //   logmel   shared [F][M] destination
 // NROWS = ceil(frame_len / 16): rows of 16 samples that can be non-zero (25 for 400-sample frames, else 32).
 // EXACT: frame_len == 16*NROWS, so no per-sample bounds predicate is needed in the stage-1 load.
+// This thread's window taps: register i multiplies sample row i - g (g = 1 for the rotated second group of a warp).
+template <int NROWS>
+__device__ __forceinline__ void load_window_taps(float (&win)[NROWS + 1], const float* window512, int j, int grp_in_warp) {
+  const int g = NROWS < 32 ? grp_in_warp : 0;
+#pragma unroll
+  for (int i = 0; i <= NROWS; ++i) {
+    const int row = i - g;
+    win[i] = (row >= 0 && row < NROWS) ? window512[16 * row + j] : 0.f;
+  }
+}
+
+// ROT: the second 16-thread group of a warp loads its samples one 16-sample row late (register i holds row i-1).
+// Frames start 160 samples = 5*32 banks apart, so without this both groups of a warp would hit the same 16 banks on
+// every sample load (2-way conflict).  The rotation multiplies FFT32 output k1 by W32^k1, which twiddle table 1
+// undoes for free.
 template <int NROWS, bool EXACT, bool DITHER>
 __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_s, const float* xl_s, int F, int quad,
-                                           int S, int L, const float (&win)[NROWS], float2* xg, float4* pbuf4,
-                                           const float2* tw_s, const float* melw_s, const int* meld_s, int M,
+                                           int S, int L, const float (&win)[NROWS + 1], float2* xg, float4* pbuf4,
+                                           const float2* tw_s, const float2* melw_s, const int* meld_s, int M,
                                            float preemph, int remove_dc, float log_floor, float dither,
                                            unsigned long long seed, unsigned utt, unsigned frame_abs0, float* logmel,
                                            int j, int grp_in_warp, int lane) {
+  constexpr bool ROT = NROWS < 32;
+  constexpr int NR = ROT ? NROWS + 1 : NROWS;      // register rows in use
+  const int g = ROT ? grp_in_warp : 0;
   const int fA = 4 * quad + 2 * grp_in_warp;   // tile-local frame of the real lane; fA + 1 is the imaginary lane
   const bool vA = fA < F, vB = fA + 1 < F;
   float re[32], im[32];
   {
-    // stage 1 load: thread j owns samples n = 16*i + j of both frames
-    const float* eA = e_base + fA * S + j;
+    // stage 1 load: thread j owns samples n = 16*row + j of both frames; register i holds row i - g
+    const float* eA = e_base + fA * S + j - 16 * g;
     const float* eB = eA + S;
 #pragma unroll
-    for (int i = 0; i < NROWS; ++i) {
-      const bool in = EXACT || (16 * i + j < L);
+    for (int i = 0; i < NR; ++i) {
+      bool in;
+      if constexpr (EXACT) in = ROT ? (i == 0 ? g == 0 : (i == NROWS ? g == 1 : true)) : true;
+      else in = (i - g >= 0) && (16 * (i - g) + j < L);
       re[i] = (vA && in) ? eA[16 * i] : 0.f;
       im[i] = (vB && in) ? eB[16 * i] : 0.f;
     }
@@ -154,9 +178,9 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
       // the pre-emphasised value picks up dither*(g(n) - preemph*g(n-1))
       const unsigned fa = frame_abs0 + (unsigned)fA;
 #pragma unroll
-      for (int i = 0; i < NROWS; ++i) {
-        const int n = 16 * i + j;
-        if (n < L) {
+      for (int i = 0; i < NR; ++i) {
+        const int n = 16 * (i - g) + j;
+        if (n >= 0 && n < L) {
           const int nm = n > 0 ? n - 1 : 0;
           if (vA) re[i] += dither * (dither_normal(seed, utt, fa, n) - preemph * dither_normal(seed, utt, fa, nm));
           if (vB) im[i] += dither * (dither_normal(seed, utt, fa + 1, n) - preemph * dither_normal(seed, utt, fa + 1, nm));
@@ -166,12 +190,15 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
       if (vB) { x0B += dither * dither_normal(seed, utt, fa + 1, 0); xlB += dither * dither_normal(seed, utt, fa + 1, L - 1); }
     }
     if (j == 0) {  // replicate rule at the frame start: y[0] = x[0] - preemph * x[0]  (TA:193-198)
-      re[0] = fmaf(-preemph, x0A, x0A);
-      im[0] = fmaf(-preemph, x0B, x0B);
+      const float yA = fmaf(-preemph, x0A, x0A), yB = fmaf(-preemph, x0B, x0B);
+      if (g == 0) { re[0] = yA; im[0] = yB; }
+      if constexpr (ROT) { if (g == 1) { re[1] = yA; im[1] = yB; } }
     }
-    float sA = 0.f, sB = 0.f;
+    // frame sums as 4 independent chains (a serial chain of 25 adds would expose the FADD latency)
+    float sA4[4] = {0.f, 0.f, 0.f, 0.f}, sB4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < NROWS; ++i) { sA += re[i]; sB += im[i]; }
+    for (int i = 0; i < NR; ++i) { sA4[i & 3] += re[i]; sB4[i & 3] += im[i]; }
+    float sA = (sA4[0] + sA4[1]) + (sA4[2] + sA4[3]), sB = (sB4[0] + sB4[1]) + (sB4[2] + sB4[3]);
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) {
       sA += __shfl_xor_sync(0xffffffffu, sA, o);
@@ -185,14 +212,14 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
       mB = (sB - preemph * (xlB - x0B)) * invL;
     }
 #pragma unroll
-    for (int i = 0; i < NROWS; ++i) {
+    for (int i = 0; i < NR; ++i) {
       re[i] = (re[i] - mA) * win[i];
       im[i] = (im[i] - mB) * win[i];
     }
 #pragma unroll
-    for (int i = NROWS; i < 32; ++i) { re[i] = 0.f; im[i] = 0.f; }
+    for (int i = NR; i < 32; ++i) { re[i] = 0.f; im[i] = 0.f; }
   }
-  fft_dif<32, NROWS>(re, im);
+  fft_dif<32, NR>(re, im);
 
   // ---- the one transpose: row k1 of the group's buffer <- Y[n2 = j][k1]
   __syncwarp();   // the previous quad's mel reads of the aliased spectra are done
@@ -207,13 +234,18 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
   const int rowB = j == 0 ? 16 : j;
   float ar[16], ai[16], br[16], bi[16];
   {
+    const float2* tw_g = tw_s + g * kTwTable;
     const float4* rowA4 = reinterpret_cast<const float4*>(xg + j * kXRow);
     const float4* rowB4 = reinterpret_cast<const float4*>(xg + (32 - rowB) * kXRow);
-    const float4* twA4 = reinterpret_cast<const float4*>(tw_s + j * kXRow);
-    const float4* twB4 = reinterpret_cast<const float4*>(tw_s + rowB * kXRow);
+    const float4* twA4 = reinterpret_cast<const float4*>(tw_g + j * kXRow);
+    const float4* tw16 = reinterpret_cast<const float4*>(tw_g + 16 * kXRow);   // same address for the whole group
+    const bool t0 = (j == 0);
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
-      const float4 ya = rowA4[h], yb = rowB4[h], ta = twA4[h], tb = twB4[h];
+      const float4 ya = rowA4[h], yb = rowB4[h], ta = twA4[h], t16 = tw16[h];
+      // columns j and 32-j share one twiddle row (conjugated); only thread 0 (columns 0 and 16) needs row 16
+      float4 tb;
+      tb.x = t0 ? t16.x : ta.x; tb.y = t0 ? t16.y : ta.y; tb.z = t0 ? t16.z : ta.z; tb.w = t0 ? t16.w : ta.w;
       // column A: Y * W512^(n2*cA);  column B: Y * conj(W512^(n2*rowB)), whose FFT comes out rotated by one bin
       ar[2 * h] = fmaf(ya.x, ta.x, -(ya.y * ta.y));
       ai[2 * h] = fmaf(ya.x, ta.y, ya.y * ta.x);
@@ -267,25 +299,40 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
   }
   __syncwarp();
 
-  // ---- sparse mel + log for the warp's 4 frames: lane <-> filter
-  for (int m = lane; m < M; m += 32) {
-    const int d = meld_s[m];
-    const int lo = d & 511, cnt = (d >> 9) & 511, off = d >> 18;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float2* pg0 = reinterpret_cast<const float2*>(pbuf4) + lo;
-    for (int q = 0; q < cnt; ++q) {
-      const float w = melw_s[off + q];
-      const float2 s0 = pg0[q], s1 = pg0[256 + q];
-      acc.x = fmaf(w, s0.x, acc.x);
-      acc.y = fmaf(w, s0.y, acc.y);
-      acc.z = fmaf(w, s1.x, acc.z);
-      acc.w = fmaf(w, s1.y, acc.w);
+  // ---- sparse mel + log for the warp's 4 frames.  lane <-> interval between two filter centres: every FFT bin lies in
+  //      exactly one interval and feeds the up-slope of filter j and the down-slope of filter j-1, so each bin is read
+  //      once.  energy[m] = up[m] + down[m+1]; rounds run from the top so that down[32(r+1)] is already known.
+  {
+    const float2* pg = reinterpret_cast<const float2*>(pbuf4);
+    const int n_int = M + 1;
+    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = (n_int - 1) >> 5; r >= 0; --r) {
+      const int iv = lane + 32 * r;
+      const int d = iv < n_int ? meld_s[iv] : 0;
+      const int lo = d & 511, cnt = (d >> 9) & 511, off = d >> 18;
+      float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < cnt; ++q) {
+        const float2 w = melw_s[off + q];
+        const float2 s0 = pg[lo + q], s1 = pg[256 + lo + q];
+        up.x = fmaf(w.x, s0.x, up.x); up.y = fmaf(w.x, s0.y, up.y);
+        up.z = fmaf(w.x, s1.x, up.z); up.w = fmaf(w.x, s1.y, up.w);
+        dn.x = fmaf(w.y, s0.x, dn.x); dn.y = fmaf(w.y, s0.y, dn.y);
+        dn.z = fmaf(w.y, s1.x, dn.z); dn.w = fmaf(w.y, s1.y, dn.w);
+      }
+      float4 nb;   // down-slope sums of the next interval
+      nb.x = __shfl_down_sync(0xffffffffu, dn.x, 1); nb.y = __shfl_down_sync(0xffffffffu, dn.y, 1);
+      nb.z = __shfl_down_sync(0xffffffffu, dn.z, 1); nb.w = __shfl_down_sync(0xffffffffu, dn.w, 1);
+      if (lane == 31) nb = carry;
+      carry.x = __shfl_sync(0xffffffffu, dn.x, 0); carry.y = __shfl_sync(0xffffffffu, dn.y, 0);
+      carry.z = __shfl_sync(0xffffffffu, dn.z, 0); carry.w = __shfl_sync(0xffffffffu, dn.w, 0);
+      if (iv < M) {
+        const int fr = 4 * quad;
+        if (fr < F) logmel[fr * M + iv] = __logf(fmaxf(up.x + nb.x, log_floor));
+        if (fr + 1 < F) logmel[(fr + 1) * M + iv] = __logf(fmaxf(up.y + nb.y, log_floor));
+        if (fr + 2 < F) logmel[(fr + 2) * M + iv] = __logf(fmaxf(up.z + nb.z, log_floor));
+        if (fr + 3 < F) logmel[(fr + 3) * M + iv] = __logf(fmaxf(up.w + nb.w, log_floor));
+      }
     }
-    const int fr = 4 * quad;
-    if (fr < F) logmel[fr * M + m] = __logf(fmaxf(acc.x, log_floor));
-    if (fr + 1 < F) logmel[(fr + 1) * M + m] = __logf(fmaxf(acc.y, log_floor));
-    if (fr + 2 < F) logmel[(fr + 2) * M + m] = __logf(fmaxf(acc.z, log_floor));
-    if (fr + 3 < F) logmel[(fr + 3) * M + m] = __logf(fmaxf(acc.w, log_floor));
   }
 }
 
@@ -306,7 +353,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   float2* xbuf = reinterpret_cast<float2*>(xl_s + kFMax);
   float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + kFMax * p.n_mels);
-  float* melw_s = reinterpret_cast<float*>(tw_s + 17 * kXRow);
+  float2* melw_s = tw_s + 2 * kTwTable;
   int* meld_s = reinterpret_cast<int*>(melw_s + kMaxNnz);
 
   const int tid = threadIdx.x;
@@ -319,12 +366,11 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   const int lfr_left = (p.lfr_m - 1) / 2;
 
   // ---- per-CTA constants: tables to shared memory, this thread's window taps to registers
-  for (int i = tid; i < 17 * kXRow; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  for (int i = tid; i < 2 * kTwTable; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   for (int i = tid; i < kMaxNnz; i += kCtaThreads) melw_s[i] = p.mel_w[i];
-  for (int i = tid; i < kMaxMels; i += kCtaThreads) meld_s[i] = i < M ? p.mel_desc[i] : 0;
-  float win[NROWS];
-#pragma unroll
-  for (int i = 0; i < NROWS; ++i) win[i] = p.window[16 * i + j];
+  for (int i = tid; i < kMaxInt; i += kCtaThreads) meld_s[i] = i <= M ? p.mel_desc[i] : 0;
+  float win[NROWS + 1];
+  load_window_taps<NROWS>(win, p.window, j, grp_in_warp);
 
   // output columns handled by this thread in the LFR/CMVN phase (float4 granularity), fixed for the CTA's lifetime
   const int D4 = D >> 2, M4 = M >> 2;
@@ -376,26 +422,37 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
     //      first use, so a tile pays one memory latency instead of one per iteration.
     {
       const int nv = (a_off + n_s + 3) >> 2;
+      const bool interior = ga >= 1 && ga + 4ll * nv <= p.wave_total;   // no per-element bounds checks needed
+      const float* src = p.wave + ga;
       constexpr int kBatch = 6;
       for (int vb = 0; vb < nv; vb += kBatch * kCtaThreads) {
         float4 x[kBatch];
         float pv[kBatch];
+        if (interior) {
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          const int v = vb + u * kCtaThreads + tid;
-          const long long ab = ga + 4ll * v;
-          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          pv[u] = 0.f;
-          if (v < nv) {
-            if (ab >= 0 && ab + 3 < p.wave_total) {
-              x[u] = ldg_stream4(p.wave + ab);
-            } else {
+          for (int u = 0; u < kBatch; ++u) {
+            const int v = vb + u * kCtaThreads + tid;
+            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pv[u] = 0.f;
+            if (v < nv) {
+              x[u] = ldg_stream4(src + 4 * v);
+              if (lane == 0) pv[u] = src[4 * v - 1];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int v = vb + u * kCtaThreads + tid;
+            const long long ab = ga + 4ll * v;
+            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pv[u] = 0.f;
+            if (v < nv) {
               if (ab >= 0 && ab < p.wave_total) x[u].x = p.wave[ab];
               if (ab + 1 >= 0 && ab + 1 < p.wave_total) x[u].y = p.wave[ab + 1];
               if (ab + 2 >= 0 && ab + 2 < p.wave_total) x[u].z = p.wave[ab + 2];
               if (ab + 3 >= 0 && ab + 3 < p.wave_total) x[u].w = p.wave[ab + 3];
+              if (lane == 0 && ab >= 1 && ab - 1 < p.wave_total) pv[u] = p.wave[ab - 1];
             }
-            if (lane == 0 && ab >= 1 && ab - 1 < p.wave_total) pv[u] = p.wave[ab - 1];
           }
         }
 #pragma unroll

@@ -51,7 +51,7 @@ struct StreamParams {
   unsigned long long seed;
   const float* window;
   const float2* twiddle;
-  const float* mel_w;
+  const float2* mel_w;
   const int* mel_desc;
   const float* cmvn;
 };
@@ -62,8 +62,8 @@ __host__ __device__ inline size_t stream_smem_bytes(int e_cap, int nf_max, int c
   b += (size_t)2 * ((nf_max + 3) & ~3) * 4;
   b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;
   b += (size_t)(cache_cap + nf_max) * n_mels * 4;
-  b += 17 * kXRow * 8;
-  b += kMaxNnz * 4 + kMaxMels * 4;
+  b += 2 * kTwTable * 8;
+  b += kMaxNnz * 8 + ((kMaxInt + 3) & ~3) * 4;
   return b;
 }
 
@@ -90,7 +90,7 @@ stream_push_kernel(const StreamParams p) {
   float2* xbuf = reinterpret_cast<float2*>(xl_s + nfp);
   float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + (p.lay.cache_cap + p.nf_max) * p.n_mels);
-  float* melw_s = reinterpret_cast<float*>(tw_s + 17 * kXRow);
+  float2* melw_s = tw_s + 2 * kTwTable;
   int* meld_s = reinterpret_cast<int*>(melw_s + kMaxNnz);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -112,12 +112,11 @@ stream_push_kernel(const StreamParams p) {
   const int n_new = min(max(p.chunk_lens[b], 0), p.max_chunk);
   const bool fin = p.is_final && p.is_final[b];
 
-  for (int i = tid; i < 17 * kXRow; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  for (int i = tid; i < 2 * kTwTable; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   for (int i = tid; i < kMaxNnz; i += kCtaThreads) melw_s[i] = p.mel_w[i];
-  for (int i = tid; i < kMaxMels; i += kCtaThreads) meld_s[i] = i < M ? p.mel_desc[i] : 0;
-  float win[NROWS];
-#pragma unroll
-  for (int i = 0; i < NROWS; ++i) win[i] = p.window[16 * i + j];
+  for (int i = tid; i < kMaxInt; i += kCtaThreads) meld_s[i] = i <= M ? p.mel_desc[i] : 0;
+  float win[NROWS + 1];
+  load_window_taps<NROWS>(win, p.window, j, grp_in_warp);
 
   // splice frames of earlier ticks come first in the tile's log-mel buffer
   for (int i = tid; i < cache_len * M; i += kCtaThreads) logmel_s[i] = cache[i];
