@@ -43,8 +43,9 @@ struct b200fe_handle {
   std::vector<float> mel_host;      // [n_mels, nfft/2]
   float* d_window = nullptr;        // [512]
   float2* d_twiddle = nullptr;      // [2*kTwTable]
-  float2* d_mel_w = nullptr;        // [kMaxNnz] (up, down) per bin
-  int* d_mel_desc = nullptr;        // [kMaxInt] per interval
+  float2* d_mel_w = nullptr;        // [kMelSlots * 32] lane-transposed (up, down) weights
+  int* d_mel_lo = nullptr;          // [32 * kMelRounds] first bin of every interval's padded run
+  int mel_rounds = 0, mel_cnt[kMelRounds] = {0}, mel_base[kMelRounds] = {0};
   float* d_cmvn = nullptr;          // [2*D]
   // dense mel banks for shrunken frames (VF:147), keyed by fft size
   std::map<int, int> short_mel_off;
@@ -327,8 +328,8 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
 
   // sparse filterbank by interval: interval iv = bins whose mel lies in [centre(iv-1), centre(iv)); such a bin feeds
   // the up-slope of filter iv and the down-slope of filter iv-1 and nothing else (TA:494-499, triangles in mel domain)
-  std::vector<float2> mw(kMaxNnz, make_float2(0.f, 0.f));
-  std::vector<int> md(kMaxInt, 0);
+  std::vector<float2> mw((size_t)kMelSlots * 32, make_float2(0.f, 0.f));
+  std::vector<int> mlo(32 * kMelRounds, 1);
   {
     const int nb = nfft / 2, nm = cfg->n_mels;
     std::vector<int> iv_of(nb, -1);
@@ -338,37 +339,54 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
       for (int m = 0; m < nm; ++m)
         if (h->mel_host[(size_t)m * nb + k] > 0.f) { if (first < 0) first = m; last = m; ++nz; }
       if (nz == 0) continue;
+      if (k == 0) return bail(B200FE_E_UNSUPPORTED, "FFT bin 0 must not carry mel weight");
       if (nz > 2 || last - first > 1) return bail(B200FE_E_UNSUPPORTED, "mel filterbank is not a 2-banded triangle bank");
       // two weights: up-slope of `last`, down-slope of `first` -> interval `last`.  One weight (interval 0, the last
-      // interval, or a bin exactly on a centre): either neighbour interval yields the same sum; keep the run monotone.
-      const int iv = nz == 2 ? last : (prev <= first ? first : first + 1);
+      // interval, or a bin exactly on a centre): it is an up-slope weight up to the filter's peak, a down-slope weight
+      // after it; on the peak either neighbour interval yields the same sum, so keep the run monotone.
+      int iv;
+      if (nz == 2) iv = last;
+      else {
+        int peak = 0;
+        for (int kk = 1; kk < nb; ++kk)
+          if (h->mel_host[(size_t)first * nb + kk] > h->mel_host[(size_t)first * nb + peak]) peak = kk;
+        iv = k > peak ? first + 1 : first;
+        if (iv < prev && prev <= first + 1) iv = prev;
+      }
       if (iv < prev) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not monotone");
       iv_of[k] = iv;
       prev = iv;
     }
-    // intervals must be contiguous, increasing runs of bins
-    int off = 0, k = 0;
-    for (int iv = 0; iv <= nm; ++iv) {
-      while (k < nb && iv_of[k] < iv) {
-        if (iv_of[k] >= 0) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not monotone");
-        ++k;
-      }
-      const int lo = k;
-      int cnt = 0;
-      while (k < nb && iv_of[k] == iv) {
-        const float up = iv < nm ? h->mel_host[(size_t)iv * nb + k] : 0.f;
-        const float dn = iv >= 1 ? h->mel_host[(size_t)(iv - 1) * nb + k] : 0.f;
-        if (off + cnt >= kMaxNnz) return bail(B200FE_E_UNSUPPORTED, "mel filterbank does not fit the sparse layout");
-        mw[off + cnt] = make_float2(0.25f * up, 0.25f * dn);
-        ++cnt;
-        ++k;
-      }
-      if (cnt > 0 && lo == 0) return bail(B200FE_E_UNSUPPORTED, "FFT bin 0 must not carry mel weight");
-      md[iv] = (cnt ? lo : 1) | (cnt << 9) | (off << 18);
-      off += cnt;
+    std::vector<int> ilo(nm + 1, -1), icnt(nm + 1, 0);
+    for (int k = 0; k < nb; ++k) {
+      if (iv_of[k] < 0) continue;
+      const int iv = iv_of[k];
+      if (ilo[iv] < 0) ilo[iv] = k;
+      if (k != ilo[iv] + icnt[iv]) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not contiguous");
+      icnt[iv]++;
     }
-    for (; k < nb; ++k)
-      if (iv_of[k] >= 0) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not monotone");
+    h->mel_rounds = (nm + 1 + 31) / 32;
+    int base = 0;
+    for (int r = 0; r < h->mel_rounds; ++r) {
+      int c = 0;
+      for (int iv = 32 * r; iv < 32 * r + 32 && iv <= nm; ++iv) c = icnt[iv] > c ? icnt[iv] : c;
+      h->mel_cnt[r] = c;
+      h->mel_base[r] = base;
+      if (base + c > kMelSlots) return bail(B200FE_E_UNSUPPORTED, "mel filterbank does not fit the sparse layout");
+      for (int iv = 32 * r; iv < 32 * r + 32 && iv <= nm; ++iv) {
+        int lo = icnt[iv] ? ilo[iv] : 1;
+        if (lo + c > nb) lo = nb - c;                 // keep the padded run inside the spectrum
+        mlo[iv] = lo;
+        for (int q = 0; q < c; ++q) {
+          const int k = lo + q;
+          if (iv_of[k] != iv) continue;               // padding slot: weight 0
+          const float up = iv < nm ? h->mel_host[(size_t)iv * nb + k] : 0.f;
+          const float dn = iv >= 1 ? h->mel_host[(size_t)(iv - 1) * nb + k] : 0.f;
+          mw[(size_t)(base + q) * 32 + (iv & 31)] = make_float2(0.25f * up, 0.25f * dn);
+        }
+      }
+      base += c;
+    }
   }
   std::vector<float2> tw(2 * kTwTable, make_float2(0.f, 0.f));
   for (int g = 0; g < 2; ++g)
@@ -380,12 +398,12 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
       }
   CK(cudaMalloc(&h->d_window, 512 * sizeof(float)));
   CK(cudaMalloc(&h->d_twiddle, tw.size() * sizeof(float2)));
-  CK(cudaMalloc(&h->d_mel_w, kMaxNnz * sizeof(float2)));
-  CK(cudaMalloc(&h->d_mel_desc, kMaxInt * sizeof(int)));
+  CK(cudaMalloc(&h->d_mel_w, mw.size() * sizeof(float2)));
+  CK(cudaMalloc(&h->d_mel_lo, mlo.size() * sizeof(int)));
   CK(cudaMemcpy(h->d_window, win512.data(), 512 * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(h->d_mel_w, mw.data(), kMaxNnz * sizeof(float2), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(h->d_mel_desc, md.data(), kMaxInt * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_mel_w, mw.data(), mw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_mel_lo, mlo.data(), mlo.size() * sizeof(int), cudaMemcpyHostToDevice));
   if (cmvn_host) {
     CK(cudaMalloc(&h->d_cmvn, 2 * h->D * sizeof(float)));
     CK(cudaMemcpy(h->d_cmvn, cmvn_host, 2 * h->D * sizeof(float), cudaMemcpyHostToDevice));
@@ -398,7 +416,7 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
 
 void b200fe_destroy(b200fe_handle* h) {
   if (!h) return;
-  cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_mel_w); cudaFree(h->d_mel_desc);
+  cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo);
   cudaFree(h->d_cmvn); cudaFree(h->d_short_mel);
   for (auto& s : h->slots) {
     if (s.ev) { cudaEventSynchronize(s.ev); cudaEventDestroy(s.ev); }
@@ -513,7 +531,8 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
     p.preemph = h->cfg.preemphasis; p.remove_dc = h->cfg.remove_dc_offset; p.log_floor = h->cfg.log_floor;
     p.dither = h->cfg.dither / (h->cfg.upscale_samples ? 32768.f : 1.f);   // TA:179 adds it after the 2^15 upscale
     p.seed = dither_seed;
-    p.window = h->d_window; p.twiddle = h->d_twiddle; p.mel_w = h->d_mel_w; p.mel_desc = h->d_mel_desc;
+    p.window = h->d_window; p.twiddle = h->d_twiddle; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_rounds = h->mel_rounds;
+    for (int r = 0; r < kMelRounds; ++r) { p.mel_cnt[r] = h->mel_cnt[r]; p.mel_base[r] = h->mel_base[r]; }
     p.cmvn = h->d_cmvn;
     const int grid = pl.n_tiles < 3 * h->n_sms ? pl.n_tiles : 3 * h->n_sms;
     const bool dither = h->cfg.dither != 0.f, stats = stats_dev != nullptr;

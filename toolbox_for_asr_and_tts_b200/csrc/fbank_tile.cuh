@@ -32,8 +32,9 @@ constexpr int kFMax = 32;           // frames per tile (upper bound)
 constexpr int kXRow = 18;           // float2 per transpose row: 16 + 2 pad -> 144 B, conflict-free 128-bit reads
 constexpr int kXGroupFloat2 = 32 * kXRow;
 constexpr int kMaxMels = 128;
-constexpr int kMaxNnz = 256;        // one (up, down) weight pair per FFT bin: a bin feeds at most 2 triangular filters
 constexpr int kMaxInt = kMaxMels + 1;  // intervals between consecutive filter centres
+constexpr int kMelRounds = (kMaxInt + 31) / 32;   // rounds of 32 intervals (lane <-> interval)
+constexpr int kMelSlots = 64;       // sum over rounds of the round's widest interval (bins), upper bound
 constexpr int kTwRows = 17;         // twiddle rows 0..16 (row 16 serves thread 0's second column)
 constexpr int kTwTable = kTwRows * kXRow;
 constexpr int kNfft = 512;
@@ -81,8 +82,14 @@ struct TileParams {
   const float* window;    // [512] window * (2^15 if upscale), zero beyond L
   const float2* twiddle;  // [2][17][kXRow]: table g is exp(-2*pi*i*(n2 - 16*g)*r/512); rows padded like the transpose
                           // buffer.  Table 1 undoes the one-row rotation group 1 applies to its sample loads.
-  const float2* mel_w;    // [kMaxNnz] (up, down) weight of every FFT bin inside its interval, x 0.25 (spectra are 4|X|^2)
-  const int* mel_desc;    // [n_mels + 1] per interval between filter centres: lo | cnt << 9 | off << 18
+  // sparse mel bank by interval between filter centres (lane <-> interval, rounds of 32 intervals).  Every round has a
+  // warp-uniform trip count mel_cnt[r] = its widest interval; weights are zero-padded to it and stored lane-transposed:
+  // mel_w[(mel_base[r] + q) * 32 + lane] = (up, down) weight x 0.25 of bin mel_lo[32 r + lane] + q.  Read through L1.
+  const float2* mel_w;
+  const int* mel_lo;      // [32 * mel_rounds]
+  int mel_rounds;
+  int mel_cnt[kMelRounds];
+  int mel_base[kMelRounds];
   const float* cmvn;      // nullptr or [2][out_dim]
 };
 
@@ -93,7 +100,6 @@ __host__ __device__ inline size_t tile_smem_bytes(int e_cap, int n_mels) {
   b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;      // transpose buffers (aliased by the power spectra)
   b += (size_t)kFMax * n_mels * 4;                  // log-mel of the tile
   b += 2 * kTwTable * 8;                            // twiddles (one table per group of a warp)
-  b += kMaxNnz * 8 + ((kMaxInt + 3) & ~3) * 4;      // sparse filterbank
   return b;
 }
 
@@ -130,6 +136,20 @@ __device__ __forceinline__ float dither_normal(unsigned long long seed, unsigned
 //   logmel   shared [F][M] destination
 // NROWS = ceil(frame_len / 16): rows of 16 samples that can be non-zero (25 for 400-sample frames, else 32).
 // EXACT: frame_len == 16*NROWS, so no per-sample bounds predicate is needed in the stage-1 load.
+struct MelTab {
+  const float2* w;
+  const int* lo;
+  int rounds;
+  int cnt[kMelRounds];
+  int base[kMelRounds];
+};
+
+__device__ __forceinline__ float fast_ln(float x) {   // x is a normal positive number (>= the log floor)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * 0.69314718055994530942f;
+}
+
 // This thread's window taps: register i multiplies sample row i - g (g = 1 for the rotated second group of a warp).
 template <int NROWS>
 __device__ __forceinline__ void load_window_taps(float (&win)[NROWS + 1], const float* window512, int j, int grp_in_warp) {
@@ -148,7 +168,7 @@ __device__ __forceinline__ void load_window_taps(float (&win)[NROWS + 1], const 
 template <int NROWS, bool EXACT, bool DITHER>
 __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_s, const float* xl_s, int F, int quad,
                                            int S, int L, const float (&win)[NROWS + 1], float2* xg, float4* pbuf4,
-                                           const float2* tw_s, const float2* melw_s, const int* meld_s, int M,
+                                           const float2* tw_s, const MelTab& mel, int M,
                                            float preemph, int remove_dc, float log_floor, float dither,
                                            unsigned long long seed, unsigned utt, unsigned frame_abs0, float* logmel,
                                            int j, int grp_in_warp, int lane) {
@@ -290,7 +310,7 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
       const float pA = fmaf(s1, s1, d1 * d1);   // 4 * |X_A[k]|^2
       const float pB = fmaf(s2, s2, d2 * d2);   // 4 * |X_B[k]|^2
       const int bin = i < 8 ? binA + 32 * i : binB + 32 * (15 - i);
-      if (!(t0 && i == 0)) pb2[bin] = make_float2(pA, pB);
+      pb2[bin] = (t0 && i == 0) ? make_float2(0.f, 0.f) : make_float2(pA, pB);   // bin 0 carries no mel weight
     });
 #undef A_RE
 #undef A_IM
@@ -302,35 +322,46 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
   // ---- sparse mel + log for the warp's 4 frames.  lane <-> interval between two filter centres: every FFT bin lies in
   //      exactly one interval and feeds the up-slope of filter j and the down-slope of filter j-1, so each bin is read
   //      once.  energy[m] = up[m] + down[m+1]; rounds run from the top so that down[32(r+1)] is already known.
+  //      Trip counts are warp-uniform (zero-padded weights), so there is no divergence inside the loop.
   {
     const float2* pg = reinterpret_cast<const float2*>(pbuf4);
-    const int n_int = M + 1;
     float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = (n_int - 1) >> 5; r >= 0; --r) {
-      const int iv = lane + 32 * r;
-      const int d = iv < n_int ? meld_s[iv] : 0;
-      const int lo = d & 511, cnt = (d >> 9) & 511, off = d >> 18;
-      float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = 0; q < cnt; ++q) {
-        const float2 w = melw_s[off + q];
-        const float2 s0 = pg[lo + q], s1 = pg[256 + lo + q];
-        up.x = fmaf(w.x, s0.x, up.x); up.y = fmaf(w.x, s0.y, up.y);
-        up.z = fmaf(w.x, s1.x, up.z); up.w = fmaf(w.x, s1.y, up.w);
-        dn.x = fmaf(w.y, s0.x, dn.x); dn.y = fmaf(w.y, s0.y, dn.y);
-        dn.z = fmaf(w.y, s1.x, dn.z); dn.w = fmaf(w.y, s1.y, dn.w);
-      }
-      float4 nb;   // down-slope sums of the next interval
-      nb.x = __shfl_down_sync(0xffffffffu, dn.x, 1); nb.y = __shfl_down_sync(0xffffffffu, dn.y, 1);
-      nb.z = __shfl_down_sync(0xffffffffu, dn.z, 1); nb.w = __shfl_down_sync(0xffffffffu, dn.w, 1);
-      if (lane == 31) nb = carry;
-      carry.x = __shfl_sync(0xffffffffu, dn.x, 0); carry.y = __shfl_sync(0xffffffffu, dn.y, 0);
-      carry.z = __shfl_sync(0xffffffffu, dn.z, 0); carry.w = __shfl_sync(0xffffffffu, dn.w, 0);
-      if (iv < M) {
-        const int fr = 4 * quad;
-        if (fr < F) logmel[fr * M + iv] = __logf(fmaxf(up.x + nb.x, log_floor));
-        if (fr + 1 < F) logmel[(fr + 1) * M + iv] = __logf(fmaxf(up.y + nb.y, log_floor));
-        if (fr + 2 < F) logmel[(fr + 2) * M + iv] = __logf(fmaxf(up.z + nb.z, log_floor));
-        if (fr + 3 < F) logmel[(fr + 3) * M + iv] = __logf(fmaxf(up.w + nb.w, log_floor));
+#pragma unroll 1
+    for (int r = mel.rounds - 1; r >= 0; --r) {
+      {
+        // warp-uniform trip count / table base of this round (selected with static indices so they stay uniform)
+        int cnt = mel.cnt[0], base = mel.base[0];
+#pragma unroll
+        for (int t = 1; t < kMelRounds; ++t)
+          if (r == t) { cnt = mel.cnt[t]; base = mel.base[t]; }
+        const int iv = lane + 32 * r;
+        const int lo = __ldg(mel.lo + iv);
+        const float2* wt = mel.w + (base * 32 + lane);
+        const float2* p0 = pg + lo;
+        float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int q = 0; q < cnt; ++q) {
+          const float2 w = __ldg(wt + 32 * q);
+          const float2 s0 = p0[q], s1 = p0[256 + q];
+          up.x = fmaf(w.x, s0.x, up.x); up.y = fmaf(w.x, s0.y, up.y);
+          up.z = fmaf(w.x, s1.x, up.z); up.w = fmaf(w.x, s1.y, up.w);
+          dn.x = fmaf(w.y, s0.x, dn.x); dn.y = fmaf(w.y, s0.y, dn.y);
+          dn.z = fmaf(w.y, s1.x, dn.z); dn.w = fmaf(w.y, s1.y, dn.w);
+        }
+        float4 nb;   // down-slope sums of the next interval
+        nb.x = __shfl_down_sync(0xffffffffu, dn.x, 1); nb.y = __shfl_down_sync(0xffffffffu, dn.y, 1);
+        nb.z = __shfl_down_sync(0xffffffffu, dn.z, 1); nb.w = __shfl_down_sync(0xffffffffu, dn.w, 1);
+        if (lane == 31) nb = carry;
+        carry.x = __shfl_sync(0xffffffffu, dn.x, 0); carry.y = __shfl_sync(0xffffffffu, dn.y, 0);
+        carry.z = __shfl_sync(0xffffffffu, dn.z, 0); carry.w = __shfl_sync(0xffffffffu, dn.w, 0);
+        if (iv < M) {
+          const int fr = 4 * quad;
+          float* dst = logmel + fr * M + iv;
+          if (fr < F) dst[0] = fast_ln(fmaxf(up.x + nb.x, log_floor));
+          if (fr + 1 < F) dst[M] = fast_ln(fmaxf(up.y + nb.y, log_floor));
+          if (fr + 2 < F) dst[2 * M] = fast_ln(fmaxf(up.z + nb.z, log_floor));
+          if (fr + 3 < F) dst[3 * M] = fast_ln(fmaxf(up.w + nb.w, log_floor));
+        }
       }
     }
   }
@@ -353,8 +384,6 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   float2* xbuf = reinterpret_cast<float2*>(xl_s + kFMax);
   float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + kFMax * p.n_mels);
-  float2* melw_s = tw_s + 2 * kTwTable;
-  int* meld_s = reinterpret_cast<int*>(melw_s + kMaxNnz);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -367,8 +396,10 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
 
   // ---- per-CTA constants: tables to shared memory, this thread's window taps to registers
   for (int i = tid; i < 2 * kTwTable; i += kCtaThreads) tw_s[i] = p.twiddle[i];
-  for (int i = tid; i < kMaxNnz; i += kCtaThreads) melw_s[i] = p.mel_w[i];
-  for (int i = tid; i < kMaxInt; i += kCtaThreads) meld_s[i] = i <= M ? p.mel_desc[i] : 0;
+  MelTab mel;
+  mel.w = p.mel_w; mel.lo = p.mel_lo; mel.rounds = p.mel_rounds;
+#pragma unroll
+  for (int r = 0; r < kMelRounds; ++r) { mel.cnt[r] = p.mel_cnt[r]; mel.base[r] = p.mel_base[r]; }
   float win[NROWS + 1];
   load_window_taps<NROWS>(win, p.window, j, grp_in_warp);
 
@@ -489,7 +520,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
 
     // ---- per warp: quads of 4 frames (2 groups x 2 frames), no CTA-wide sync inside
     for (int quad = warp; 4 * quad < F; quad += kWarps)
-      fbank_quad<NROWS, EXACT, DITHER>(e_s + a_off, x0_s, xl_s, F, quad, S, L, win, xg, pbuf4, tw_s, melw_s, meld_s, M,
+      fbank_quad<NROWS, EXACT, DITHER>(e_s + a_off, x0_s, xl_s, F, quad, S, L, win, xg, pbuf4, tw_s, mel, M,
                                        p.preemph, p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)utt,
                                        (unsigned)f_lo, logmel_s, j, grp_in_warp, lane);
     __syncthreads();
@@ -521,7 +552,8 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
       }
     }
     cur = nxt;
-    __syncthreads();   // the tile's shared buffers are free again
+    // no barrier here: the next tile's staging only writes e_s / x0_s / xl_s, whose last readers finished before the
+    // barrier above, and logmel_s is not written again before the barrier that follows the next staging.
   }
 
   if constexpr (STATS) {

@@ -52,7 +52,10 @@ struct StreamParams {
   const float* window;
   const float2* twiddle;
   const float2* mel_w;
-  const int* mel_desc;
+  const int* mel_lo;
+  int mel_rounds;
+  int mel_cnt[kMelRounds];
+  int mel_base[kMelRounds];
   const float* cmvn;
 };
 
@@ -63,7 +66,6 @@ __host__ __device__ inline size_t stream_smem_bytes(int e_cap, int nf_max, int c
   b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;
   b += (size_t)(cache_cap + nf_max) * n_mels * 4;
   b += 2 * kTwTable * 8;
-  b += kMaxNnz * 8 + ((kMaxInt + 3) & ~3) * 4;
   return b;
 }
 
@@ -90,8 +92,6 @@ stream_push_kernel(const StreamParams p) {
   float2* xbuf = reinterpret_cast<float2*>(xl_s + nfp);
   float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + (p.lay.cache_cap + p.nf_max) * p.n_mels);
-  float2* melw_s = tw_s + 2 * kTwTable;
-  int* meld_s = reinterpret_cast<int*>(melw_s + kMaxNnz);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = tid & (kGroup - 1), grp_in_warp = lane >> 4;
@@ -113,8 +113,10 @@ stream_push_kernel(const StreamParams p) {
   const bool fin = p.is_final && p.is_final[b];
 
   for (int i = tid; i < 2 * kTwTable; i += kCtaThreads) tw_s[i] = p.twiddle[i];
-  for (int i = tid; i < kMaxNnz; i += kCtaThreads) melw_s[i] = p.mel_w[i];
-  for (int i = tid; i < kMaxInt; i += kCtaThreads) meld_s[i] = i <= M ? p.mel_desc[i] : 0;
+  MelTab mel;
+  mel.w = p.mel_w; mel.lo = p.mel_lo; mel.rounds = p.mel_rounds;
+#pragma unroll
+  for (int r = 0; r < kMelRounds; ++r) { mel.cnt[r] = p.mel_cnt[r]; mel.base[r] = p.mel_base[r]; }
   float win[NROWS + 1];
   load_window_taps<NROWS>(win, p.window, j, grp_in_warp);
 
@@ -151,7 +153,7 @@ stream_push_kernel(const StreamParams p) {
   float2* xg = xbuf + (warp * 2 + grp_in_warp) * kXGroupFloat2;
   float4* pbuf4 = reinterpret_cast<float4*>(xbuf + warp * 2 * kXGroupFloat2);
   for (int quad = warp; 4 * quad < nf; quad += kWarps)
-    fbank_quad<NROWS, EXACT, DITHER>(e_s, x0_s, xl_s, nf, quad, S, L, win, xg, pbuf4, tw_s, melw_s, meld_s, M, p.preemph,
+    fbank_quad<NROWS, EXACT, DITHER>(e_s, x0_s, xl_s, nf, quad, S, L, win, xg, pbuf4, tw_s, mel, M, p.preemph,
                                      p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)sid, (unsigned)t_seen,
                                      logmel_s + cache_len * M, j, grp_in_warp, lane);
   __syncthreads();
