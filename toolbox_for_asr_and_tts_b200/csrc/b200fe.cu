@@ -46,6 +46,7 @@ struct b200fe_handle {
   float2* d_mel_w = nullptr;        // [kMelSlots * 32] lane-transposed (up, down) weights
   int* d_mel_lo = nullptr;          // [32 * kMelRounds] first bin of every interval's padded run
   int mel_rounds = 0, mel_cnt[kMelRounds] = {0}, mel_base[kMelRounds] = {0};
+  bool mel_paraformer = false;      // table shape == MelShapeParaformer: fully unrolled mel stage
   float* d_cmvn = nullptr;          // [2*D]
   // dense mel banks for shrunken frames (VF:147), keyed by fft size
   std::map<int, int> short_mel_off;
@@ -207,11 +208,11 @@ int upload(b200fe_handle* h, const void* src, size_t bytes, void* dst, cudaStrea
   return 0;
 }
 
-template <int NROWS, bool EXACT>
+template <int NROWS, bool EXACT, class MELS>
 int launch_tile(b200fe_handle* h, const TileParams& p, int grid, bool dither, bool stats, cudaStream_t st) {
 #define LAUNCH(DI, STT)                                                                                         \
   do {                                                                                                          \
-    auto k = fbank_lfr_cmvn_tile_kernel<NROWS, EXACT, DI, STT>;                                                 \
+    auto k = fbank_lfr_cmvn_tile_kernel<NROWS, EXACT, DI, STT, MELS>;                                                 \
     CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));      \
     k<<<grid, kCtaThreads, h->smem_bytes, st>>>(p);                                                             \
   } while (0)
@@ -365,28 +366,36 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
       if (k != ilo[iv] + icnt[iv]) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not contiguous");
       icnt[iv]++;
     }
-    h->mel_rounds = (nm + 1 + 31) / 32;
+    h->mel_rounds = (nm + 30) / 31;
     int base = 0;
     for (int r = 0; r < h->mel_rounds; ++r) {
       int c = 0;
-      for (int iv = 32 * r; iv < 32 * r + 32 && iv <= nm; ++iv) c = icnt[iv] > c ? icnt[iv] : c;
+      for (int l = 0; l < 32; ++l) {
+        const int iv = 31 * r + l;
+        if (iv <= nm && icnt[iv] > c) c = icnt[iv];
+      }
       h->mel_cnt[r] = c;
       h->mel_base[r] = base;
       if (base + c > kMelSlots) return bail(B200FE_E_UNSUPPORTED, "mel filterbank does not fit the sparse layout");
-      for (int iv = 32 * r; iv < 32 * r + 32 && iv <= nm; ++iv) {
-        int lo = icnt[iv] ? ilo[iv] : 1;
+      for (int l = 0; l < 32; ++l) {
+        const int iv = 31 * r + l;
+        int lo = (iv <= nm && icnt[iv]) ? ilo[iv] : 1;
         if (lo + c > nb) lo = nb - c;                 // keep the padded run inside the spectrum
-        mlo[iv] = lo;
+        mlo[32 * r + l] = lo;
+        if (iv > nm) continue;
         for (int q = 0; q < c; ++q) {
           const int k = lo + q;
           if (iv_of[k] != iv) continue;               // padding slot: weight 0
           const float up = iv < nm ? h->mel_host[(size_t)iv * nb + k] : 0.f;
           const float dn = iv >= 1 ? h->mel_host[(size_t)(iv - 1) * nb + k] : 0.f;
-          mw[(size_t)(base + q) * 32 + (iv & 31)] = make_float2(0.25f * up, 0.25f * dn);
+          mw[(size_t)(base + q) * 32 + l] = make_float2(0.25f * up, 0.25f * dn);
         }
       }
       base += c;
     }
+    h->mel_paraformer = h->mel_rounds == MelShapeParaformer::kRounds;
+    for (int r = 0; r < MelShapeParaformer::kRounds && h->mel_paraformer; ++r)
+      h->mel_paraformer = h->mel_cnt[r] == MelShapeParaformer::cnt(r);
   }
   std::vector<float2> tw(2 * kTwTable, make_float2(0.f, 0.f));
   for (int g = 0; g < 2; ++g)
@@ -536,8 +545,9 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
     p.cmvn = h->d_cmvn;
     const int grid = pl.n_tiles < 3 * h->n_sms ? pl.n_tiles : 3 * h->n_sms;
     const bool dither = h->cfg.dither != 0.f, stats = stats_dev != nullptr;
-    if (h->L == 400) rc = launch_tile<25, true>(h, p, grid, dither, stats, st);
-    else rc = launch_tile<32, false>(h, p, grid, dither, stats, st);
+    if (h->L == 400 && h->mel_paraformer) rc = launch_tile<25, true, MelShapeParaformer>(h, p, grid, dither, stats, st);
+    else if (h->L == 400) rc = launch_tile<25, true, MelShapeRuntime>(h, p, grid, dither, stats, st);
+    else rc = launch_tile<32, false, MelShapeRuntime>(h, p, grid, dither, stats, st);
     if (rc) return rc;
   }
   // 3. utterances shorter than one frame (VF:147)

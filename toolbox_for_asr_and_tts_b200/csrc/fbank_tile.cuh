@@ -33,7 +33,7 @@ constexpr int kXRow = 18;           // float2 per transpose row: 16 + 2 pad -> 1
 constexpr int kXGroupFloat2 = 32 * kXRow;
 constexpr int kMaxMels = 128;
 constexpr int kMaxInt = kMaxMels + 1;  // intervals between consecutive filter centres
-constexpr int kMelRounds = (kMaxInt + 31) / 32;   // rounds of 32 intervals (lane <-> interval)
+constexpr int kMelRounds = (kMaxMels + 30) / 31;  // rounds of 31 filters: lane <-> interval, lane 31 only feeds lane 30
 constexpr int kMelSlots = 64;       // sum over rounds of the round's widest interval (bins), upper bound
 constexpr int kTwRows = 17;         // twiddle rows 0..16 (row 16 serves thread 0's second column)
 constexpr int kTwTable = kTwRows * kXRow;
@@ -82,7 +82,8 @@ struct TileParams {
   const float* window;    // [512] window * (2^15 if upscale), zero beyond L
   const float2* twiddle;  // [2][17][kXRow]: table g is exp(-2*pi*i*(n2 - 16*g)*r/512); rows padded like the transpose
                           // buffer.  Table 1 undoes the one-row rotation group 1 applies to its sample loads.
-  // sparse mel bank by interval between filter centres (lane <-> interval, rounds of 32 intervals).  Every round has a
+  // sparse mel bank by interval between filter centres.  Round r: lane l <-> interval 31 r + l (the last lane's interval
+  // is the first of the next round: it only supplies the down-slope sum of filter 31 r + 30).  Every round has a
   // warp-uniform trip count mel_cnt[r] = its widest interval; weights are zero-padded to it and stored lane-transposed:
   // mel_w[(mel_base[r] + q) * 32 + lane] = (up, down) weight x 0.25 of bin mel_lo[32 r + lane] + q.  Read through L1.
   const float2* mel_w;
@@ -150,6 +151,59 @@ __device__ __forceinline__ float fast_ln(float x) {   // x is a normal positive 
   return y * 0.69314718055994530942f;
 }
 
+// Compile-time shape of the interval table (rounds and per-round trip counts).  MelShapeRuntime reads them from MelTab;
+// MelShapeFixed lets the compiler unroll the whole mel stage and hoist its loads (the 80-mel / 512-point / 16 kHz bank
+// of the Paraformer front-end is MelShapeFixed<3, 2, 5, 9>).
+struct MelShapeRuntime { static constexpr bool kFixed = false; };
+template <int R, int C0, int C1 = 0, int C2 = 0>
+struct MelShapeFixed {
+  static constexpr bool kFixed = true;
+  static constexpr int kRounds = R;
+  __host__ __device__ static constexpr int cnt(int r) { return r == 0 ? C0 : (r == 1 ? C1 : C2); }
+  __host__ __device__ static constexpr int base(int r) { return r == 0 ? 0 : (r == 1 ? C0 : C0 + C1); }
+};
+using MelShapeParaformer = MelShapeFixed<3, 2, 5, 9>;
+
+// One round of the interval mel: lane <-> interval 31 r + lane.  CNT >= 0: compile-time trip count (fully unrolled).
+template <int CNT>
+__device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, int base, const float2* pg, int lane, int M,
+                                          int F, int quad, float log_floor, float* logmel) {
+  const int cnt = CNT >= 0 ? CNT : cnt_rt;
+  const int iv = lane + 31 * r;
+  const int lo = __ldg(mel.lo + 32 * r + lane);
+  const float2* wt = mel.w + (base * 32 + lane);
+  const float2* p0 = pg + lo;
+  float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto body = [&](int q) {
+    const float2 w = __ldg(wt + 32 * q);
+    const float2 s0 = p0[q], s1 = p0[256 + q];
+    up.x = fmaf(w.x, s0.x, up.x); up.y = fmaf(w.x, s0.y, up.y);
+    up.z = fmaf(w.x, s1.x, up.z); up.w = fmaf(w.x, s1.y, up.w);
+    dn.x = fmaf(w.y, s0.x, dn.x); dn.y = fmaf(w.y, s0.y, dn.y);
+    dn.z = fmaf(w.y, s1.x, dn.z); dn.w = fmaf(w.y, s1.y, dn.w);
+  };
+  if constexpr (CNT >= 0) {
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) body(q);
+  } else {
+#pragma unroll 4
+    for (int q = 0; q < cnt; ++q) body(q);
+  }
+  // energy[filter iv] = up-slope sum of interval iv + down-slope sum of interval iv + 1 (the next lane)
+  const float ex = up.x + __shfl_down_sync(0xffffffffu, dn.x, 1);
+  const float ey = up.y + __shfl_down_sync(0xffffffffu, dn.y, 1);
+  const float ez = up.z + __shfl_down_sync(0xffffffffu, dn.z, 1);
+  const float ew = up.w + __shfl_down_sync(0xffffffffu, dn.w, 1);
+  if (lane < 31 && iv < M) {
+    const int fr = 4 * quad;
+    float* dst = logmel + fr * M + iv;
+    if (fr < F) dst[0] = fast_ln(fmaxf(ex, log_floor));
+    if (fr + 1 < F) dst[M] = fast_ln(fmaxf(ey, log_floor));
+    if (fr + 2 < F) dst[2 * M] = fast_ln(fmaxf(ez, log_floor));
+    if (fr + 3 < F) dst[3 * M] = fast_ln(fmaxf(ew, log_floor));
+  }
+}
+
 // This thread's window taps: register i multiplies sample row i - g (g = 1 for the rotated second group of a warp).
 template <int NROWS>
 __device__ __forceinline__ void load_window_taps(float (&win)[NROWS + 1], const float* window512, int j, int grp_in_warp) {
@@ -165,7 +219,7 @@ __device__ __forceinline__ void load_window_taps(float (&win)[NROWS + 1], const 
 // Frames start 160 samples = 5*32 banks apart, so without this both groups of a warp would hit the same 16 banks on
 // every sample load (2-way conflict).  The rotation multiplies FFT32 output k1 by W32^k1, which twiddle table 1
 // undoes for free.
-template <int NROWS, bool EXACT, bool DITHER>
+template <int NROWS, bool EXACT, bool DITHER, class MELS>
 __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_s, const float* xl_s, int F, int quad,
                                            int S, int L, const float (&win)[NROWS + 1], float2* xg, float4* pbuf4,
                                            const float2* tw_s, const MelTab& mel, int M,
@@ -321,47 +375,22 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
 
   // ---- sparse mel + log for the warp's 4 frames.  lane <-> interval between two filter centres: every FFT bin lies in
   //      exactly one interval and feeds the up-slope of filter j and the down-slope of filter j-1, so each bin is read
-  //      once.  energy[m] = up[m] + down[m+1]; rounds run from the top so that down[32(r+1)] is already known.
-  //      Trip counts are warp-uniform (zero-padded weights), so there is no divergence inside the loop.
+  //      once: energy[m] = up[m] + down[m+1].  Trip counts are warp-uniform (zero-padded weights): no divergence.
   {
     const float2* pg = reinterpret_cast<const float2*>(pbuf4);
-    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (MELS::kFixed) {
+      static_for<0, MELS::kRounds>([&](auto ic) {
+        constexpr int r = decltype(ic)::value;
+        mel_round<MELS::cnt(r)>(mel, r, 0, MELS::base(r), pg, lane, M, F, quad, log_floor, logmel);
+      });
+    } else {
 #pragma unroll 1
-    for (int r = mel.rounds - 1; r >= 0; --r) {
-      {
-        // warp-uniform trip count / table base of this round (selected with static indices so they stay uniform)
-        int cnt = mel.cnt[0], base = mel.base[0];
+      for (int r = 0; r < mel.rounds; ++r) {
+        int cnt = mel.cnt[0], base = mel.base[0];   // selected with static indices so that they stay warp-uniform
 #pragma unroll
         for (int t = 1; t < kMelRounds; ++t)
           if (r == t) { cnt = mel.cnt[t]; base = mel.base[t]; }
-        const int iv = lane + 32 * r;
-        const int lo = __ldg(mel.lo + iv);
-        const float2* wt = mel.w + (base * 32 + lane);
-        const float2* p0 = pg + lo;
-        float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int q = 0; q < cnt; ++q) {
-          const float2 w = __ldg(wt + 32 * q);
-          const float2 s0 = p0[q], s1 = p0[256 + q];
-          up.x = fmaf(w.x, s0.x, up.x); up.y = fmaf(w.x, s0.y, up.y);
-          up.z = fmaf(w.x, s1.x, up.z); up.w = fmaf(w.x, s1.y, up.w);
-          dn.x = fmaf(w.y, s0.x, dn.x); dn.y = fmaf(w.y, s0.y, dn.y);
-          dn.z = fmaf(w.y, s1.x, dn.z); dn.w = fmaf(w.y, s1.y, dn.w);
-        }
-        float4 nb;   // down-slope sums of the next interval
-        nb.x = __shfl_down_sync(0xffffffffu, dn.x, 1); nb.y = __shfl_down_sync(0xffffffffu, dn.y, 1);
-        nb.z = __shfl_down_sync(0xffffffffu, dn.z, 1); nb.w = __shfl_down_sync(0xffffffffu, dn.w, 1);
-        if (lane == 31) nb = carry;
-        carry.x = __shfl_sync(0xffffffffu, dn.x, 0); carry.y = __shfl_sync(0xffffffffu, dn.y, 0);
-        carry.z = __shfl_sync(0xffffffffu, dn.z, 0); carry.w = __shfl_sync(0xffffffffu, dn.w, 0);
-        if (iv < M) {
-          const int fr = 4 * quad;
-          float* dst = logmel + fr * M + iv;
-          if (fr < F) dst[0] = fast_ln(fmaxf(up.x + nb.x, log_floor));
-          if (fr + 1 < F) dst[M] = fast_ln(fmaxf(up.y + nb.y, log_floor));
-          if (fr + 2 < F) dst[2 * M] = fast_ln(fmaxf(up.z + nb.z, log_floor));
-          if (fr + 3 < F) dst[3 * M] = fast_ln(fmaxf(up.w + nb.w, log_floor));
-        }
+        mel_round<-1>(mel, r, cnt, base, pg, lane, M, F, quad, log_floor, logmel);
       }
     }
   }
@@ -374,7 +403,7 @@ struct StatsAcc {
 template <>
 struct StatsAcc<false> {};
 
-template <int NROWS, bool EXACT, bool DITHER, bool STATS>
+template <int NROWS, bool EXACT, bool DITHER, bool STATS, class MELS>
 __global__ void __launch_bounds__(kCtaThreads, 3)
 fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -455,7 +484,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
       const int nv = (a_off + n_s + 3) >> 2;
       const bool interior = ga >= 1 && ga + 4ll * nv <= p.wave_total;   // no per-element bounds checks needed
       const float* src = p.wave + ga;
-      constexpr int kBatch = 6;
+      constexpr int kBatch = 11;   // 11 x 128 float4 cover a 400/160 tile in one batch: one exposed memory latency
       for (int vb = 0; vb < nv; vb += kBatch * kCtaThreads) {
         float4 x[kBatch];
         float pv[kBatch];
@@ -520,7 +549,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
 
     // ---- per warp: quads of 4 frames (2 groups x 2 frames), no CTA-wide sync inside
     for (int quad = warp; 4 * quad < F; quad += kWarps)
-      fbank_quad<NROWS, EXACT, DITHER>(e_s + a_off, x0_s, xl_s, F, quad, S, L, win, xg, pbuf4, tw_s, mel, M,
+      fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s + a_off, x0_s, xl_s, F, quad, S, L, win, xg, pbuf4, tw_s, mel, M,
                                        p.preemph, p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)utt,
                                        (unsigned)f_lo, logmel_s, j, grp_in_warp, lane);
     __syncthreads();

@@ -14,14 +14,14 @@ int stream_layout(const b200fe_handle* h, int n_streams, int max_chunk, StreamLa
   return 0;
 }
 
-template <int NROWS, bool EXACT>
+template <int NROWS, bool EXACT, class MELS>
 int launch_stream(b200fe_handle* h, const StreamParams& p, size_t smem, bool dither, cudaStream_t st) {
   if (dither) {
-    auto k = stream_push_kernel<NROWS, EXACT, true>;
+    auto k = stream_push_kernel<NROWS, EXACT, true, MELS>;
     CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<p.n, kCtaThreads, smem, st>>>(p);
   } else {
-    auto k = stream_push_kernel<NROWS, EXACT, false>;
+    auto k = stream_push_kernel<NROWS, EXACT, false, MELS>;
     CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<p.n, kCtaThreads, smem, st>>>(p);
   }
@@ -85,8 +85,9 @@ int b200fe_stream_push(b200fe_handle* h, void* state_dev, int n_streams, int max
   p.window = h->d_window; p.twiddle = h->d_twiddle; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_rounds = h->mel_rounds;
   for (int r = 0; r < kMelRounds; ++r) { p.mel_cnt[r] = h->mel_cnt[r]; p.mel_base[r] = h->mel_base[r]; } p.cmvn = h->d_cmvn;
   const bool dither = h->cfg.dither != 0.f;
-  if (h->L == 400) return launch_stream<25, true>(h, p, smem, dither, (cudaStream_t)stream);
-  return launch_stream<32, false>(h, p, smem, dither, (cudaStream_t)stream);
+  if (h->L == 400 && h->mel_paraformer) return launch_stream<25, true, MelShapeParaformer>(h, p, smem, dither, (cudaStream_t)stream);
+  if (h->L == 400) return launch_stream<25, true, MelShapeRuntime>(h, p, smem, dither, (cudaStream_t)stream);
+  return launch_stream<32, false, MelShapeRuntime>(h, p, smem, dither, (cudaStream_t)stream);
 }
 
 }  // extern "C"

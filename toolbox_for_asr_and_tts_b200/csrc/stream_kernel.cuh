@@ -81,7 +81,7 @@ __global__ void stream_reset_kernel(void* state, StreamLayout lay, const int* id
   c[3 * lay.n_streams + s] = 0;
 }
 
-template <int NROWS, bool EXACT, bool DITHER>
+template <int NROWS, bool EXACT, bool DITHER, class MELS>
 __global__ void __launch_bounds__(kCtaThreads, 2)
 stream_push_kernel(const StreamParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -153,7 +153,7 @@ stream_push_kernel(const StreamParams p) {
   float2* xg = xbuf + (warp * 2 + grp_in_warp) * kXGroupFloat2;
   float4* pbuf4 = reinterpret_cast<float4*>(xbuf + warp * 2 * kXGroupFloat2);
   for (int quad = warp; 4 * quad < nf; quad += kWarps)
-    fbank_quad<NROWS, EXACT, DITHER>(e_s, x0_s, xl_s, nf, quad, S, L, win, xg, pbuf4, tw_s, mel, M, p.preemph,
+    fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s, x0_s, xl_s, nf, quad, S, L, win, xg, pbuf4, tw_s, mel, M, p.preemph,
                                      p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)sid, (unsigned)t_seen,
                                      logmel_s + cache_len * M, j, grp_in_warp, lane);
   __syncthreads();
