@@ -515,14 +515,18 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
             }
           }
         }
+        // the sample before each float4 comes from the previous lane (all shuffles first: they are independent)
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const float up1 = __shfl_up_sync(0xffffffffu, x[u].w, 1);
+          if (lane != 0) pv[u] = up1;
+        }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
           const int v = vb + u * kCtaThreads + tid;
-          float prev = __shfl_up_sync(0xffffffffu, x[u].w, 1);
-          if (lane == 0) prev = pv[u];
           if (v < nv) {
             float4 e;
-            e.x = fmaf(-p.preemph, prev, x[u].x);
+            e.x = fmaf(-p.preemph, pv[u], x[u].x);
             e.y = fmaf(-p.preemph, x[u].x, x[u].y);
             e.z = fmaf(-p.preemph, x[u].y, x[u].z);
             e.w = fmaf(-p.preemph, x[u].z, x[u].w);
