@@ -333,3 +333,61 @@ def test_raw_c_abi_with_ctypes(cmvn):
         assert int(flen[0]) == 17 and np.abs(feats[0].cpu().numpy() - g).max() <= cmvn_atol(cmvn)
     finally:
         lib.b200fe_destroy(h)
+
+
+def test_streaming_512_streams_per_tick_match_single_stream_bitwise(cmvn):
+    """BASELINE.json configs[2] at one GPU's share: 512 concurrent streams, 600 ms chunks, one launch per tick.
+    Every stream must produce exactly what it produces when it is the only stream in the pool (state isolation), and
+    the row schedule must be 10 rows per tick from the first tick on."""
+    fe = make_fe(cmvn)
+    n_streams, chunk, ticks = 512, 9600, 6
+    pool = StreamPool(fe, n_streams=n_streams, max_chunk_samples=chunk, device=DEV)
+    ids = torch.arange(n_streams, dtype=torch.int32, device=DEV)
+    lens = torch.full((n_streams,), chunk, dtype=torch.int32, device=DEV)
+    offs = torch.arange(n_streams, dtype=torch.int64) * (chunk * ticks)
+    wave = torch.zeros(n_streams * chunk * ticks, device=DEV)
+    _native.ops().synth_uniform(wave, offs, torch.full((n_streams,), chunk * ticks, dtype=torch.int64), 77, 0.3)
+    wave = wave.view(n_streams, ticks, chunk)
+    outs = []
+    for t in range(ticks):
+        fin = torch.full((n_streams,), 1 if t == ticks - 1 else 0, dtype=torch.uint8, device=DEV)
+        feats, rows = pool.push(wave[:, t].contiguous(), lens, ids, fin)
+        expect = 10 if t < ticks - 1 else -(-(1 + (chunk * ticks - 400) // 160) // 6) - 10 * (ticks - 1)
+        assert bool((rows == expect).all()), (t, rows[:4])
+        outs.append(feats[:, :expect].clone())
+    allrows = torch.cat(outs, dim=1)                      # [512, 60, 560]
+    solo = StreamPool(fe, n_streams=1, max_chunk_samples=chunk, device=DEV)
+    one = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for s in (0, 1, 255, 511):
+        got = []
+        for t in range(ticks):
+            fin = torch.tensor([1 if t == ticks - 1 else 0], dtype=torch.uint8, device=DEV)
+            f, r = solo.push(wave[s:s + 1, t].contiguous(), lens[:1], one, fin)
+            got.append(f[0, :int(r[0])])
+        assert torch.equal(torch.cat(got), allrows[s]), s
+    # and against the offline front-end on the concatenated audio
+    off, ol = fe(wave[:4].reshape(4, -1), [chunk * ticks] * 4)
+    assert int(ol[0]) == allrows.shape[1]
+    assert (off - allrows[:4]).abs().max() <= cmvn_atol(cmvn)
+
+
+def test_sharded_bulk_extraction_equals_single_pass(cmvn):
+    """BASELINE.json configs[3] in miniature: utterances sharded over 8 'ranks' (longest-first), each shard processed
+    on its own, CMVN statistics summed.  Features of shard k must equal the single-pass features bit for bit and the
+    reduced statistics must equal the single-pass statistics (float64 sums in a different order)."""
+    from toolbox_for_asr_and_tts_b200 import sharding
+    fe = make_fe(None)
+    lens = synth.utterance_lengths(81, 40, lo=4000, hi=64000)
+    waves = [synth.uniform_pcm(81, i, int(n)) for i, n in enumerate(lens)]
+    stats_all = torch.zeros(1121, dtype=torch.float64, device=DEV)
+    full, fl = fe(dense_batch(waves), lens.tolist(), stats=stats_all)
+    stats_sum = torch.zeros(1121, dtype=torch.float64, device=DEV)
+    for part in sharding.partition_utterances(lens, 8):
+        st = torch.zeros(1121, dtype=torch.float64, device=DEV)
+        f, l = fe(dense_batch([waves[i] for i in part]), [int(lens[i]) for i in part], stats=st)
+        for k, i in enumerate(part):
+            assert int(l[k]) == int(fl[i]) and torch.equal(f[k, :int(l[k])], full[i, :int(fl[i])])
+        stats_sum += st            # what the NCCL all-reduce does across ranks
+    assert float(stats_sum[-1]) == float(stats_all[-1])
+    rel = ((stats_sum - stats_all).abs() / stats_all.abs().clamp(min=1.0)).max()
+    assert float(rel) < 1e-12
