@@ -39,9 +39,7 @@ def utterance_lengths(seed: int, batch: int, lo: int = 16000, hi: int = 480000) 
 
 def packed_offsets(lengths: np.ndarray, align: int = 4) -> tuple[np.ndarray, int]:
     """Start of each utterance in a length-packed buffer, every start aligned to `align` samples (16 bytes)."""
-    offs = np.zeros(len(lengths), dtype=np.int64)
-    pos = 0
-    for i, n in enumerate(lengths):
-        offs[i] = pos
-        pos += (int(n) + align - 1) // align * align
-    return offs, pos
+    padded = (np.asarray(lengths, dtype=np.int64) + align - 1) // align * align
+    ends = np.cumsum(padded)
+    offs = np.concatenate(([0], ends[:-1])).astype(np.int64) if len(padded) else np.zeros(0, dtype=np.int64)
+    return offs, int(ends[-1]) if len(padded) else 0
