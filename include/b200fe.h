@@ -134,6 +134,18 @@ int b200fe_stream_push(b200fe_handle* h, void* state_dev, int n_streams, int max
 /* Upper bound of rows one push can emit for a chunk of max_chunk_samples (sizes rows_cap). */
 int b200fe_stream_max_rows(const b200fe_handle* h, int max_chunk_samples);
 
+/* ---- TTS-side log-mel (BASELINE.json configs[4]; no reference code exists for it, the definition is frozen in
+ * oracle/tts_mel_np.py): n_fft = win = 1024, periodic Hann, reflect padding (n_fft-hop)/2 per side so that
+ * frames = n_samples / hop, magnitude sqrt(re^2+im^2+1e-9), Slaney-scale Slaney-normalised filters, log(clamp 1e-5).
+ * mel_dev: float32 [batch, n_mels, frames_cap] (mel-major); frames beyond an utterance are zero.
+ * offsets_dev / lengths_dev: int64 device arrays; max_frames = max_i lengths[i] / hop sizes the launch. */
+typedef struct b200fe_tts b200fe_tts;
+int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_min, float f_max, b200fe_tts** out);
+void b200fe_tts_destroy(b200fe_tts* t);
+int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total, const int64_t* offsets_dev,
+                       const int64_t* lengths_dev, int batch, int64_t max_frames, float* mel_dev, int64_t frames_cap,
+                       int64_t* mel_lens_dev, void* stream);
+
 /* ---- bench / test support: counter-based synthetic PCM, identical to synth.py on the host.
  * x[u][n] = amp * (2*U01(hash(seed,u,n)) - 1) written at wave_dev[offsets_dev[u] + n], n < lengths_dev[u]. */
 int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int64_t* lengths_dev, int batch,

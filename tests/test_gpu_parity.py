@@ -391,3 +391,23 @@ def test_sharded_bulk_extraction_equals_single_pass(cmvn):
     assert float(stats_sum[-1]) == float(stats_all[-1])
     rel = ((stats_sum - stats_all).abs() / stats_all.abs().clamp(min=1.0)).max()
     assert float(rel) < 1e-12
+
+
+def test_tts_log_mel_against_frozen_definition():
+    """BASELINE.json configs[4]: 24 kHz, n_fft 1024, hop 256, 80 mels.  PARITY UNPINNED by the reference (it has no
+    audio->mel code); the CUDA path is compared with the frozen numpy definition (oracle/tts_mel_np.py)."""
+    from oracle import tts_mel_np as tm
+    from toolbox_for_asr_and_tts_b200 import TtsLogMel
+    fe = TtsLogMel()
+    lens = [24000, 72000, 1280, 512, 1025, 385 + 256, 100003]
+    waves = [synth.uniform_pcm(91, i, n) for i, n in enumerate(lens)]
+    mel, frames = fe(dense_batch(waves), lens)
+    assert mel.dtype == torch.float32 and tuple(mel.shape) == (len(lens), 80, max(lens) // 256)
+    for i, n in enumerate(lens):
+        ref = tm.tts_log_mel(waves[i])
+        assert int(frames[i]) == n // 256 == ref.shape[1]
+        got = mel[i, :, :ref.shape[1]].cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-3, (n, np.abs(got - ref).max())
+        assert not mel[i, :, ref.shape[1]:].any()           # padded frames are zero
+    with pytest.raises(RuntimeError):
+        fe(torch.zeros(1, 24000), [24000])                  # CPU tensors are rejected

@@ -17,6 +17,7 @@
 #include "aux_kernels.cuh"
 #include "fbank_tile.cuh"
 #include "stream_kernel.cuh"
+#include "tts_mel.cuh"
 
 using namespace b200fe;
 
@@ -117,6 +118,77 @@ int build_mel(int n_mels, int nfft, double fs, double low, double high, std::vec
       bank[(size_t)m * nb + k] = (float)v;
     }
   }
+  return 0;
+}
+
+// Sparse mel bank by interval between filter centres (see TileParams::mel_w).  `bank` is dense [nm, ld] (row stride ld),
+// only columns < nb are used.  A bin must feed at most two adjacent filters (triangular banks).
+int build_interval_table(const std::vector<float>& bank, int nm, int nb, int ld, float scale, std::vector<float2>& mw,
+                         std::vector<int>& mlo, int& rounds, int* cnt_out, int* base_out, std::string& why) {
+  mw.assign((size_t)kMelSlots * 32, make_float2(0.f, 0.f));
+  mlo.assign(32 * kMelRounds, 1);
+  auto W = [&](int m, int k) { return bank[(size_t)m * ld + k]; };
+  std::vector<int> iv_of(nb, -1);
+  int prev = 0;
+  for (int k = 0; k < nb; ++k) {
+    int first = -1, last = -1, nz = 0;
+    for (int m = 0; m < nm; ++m)
+      if (W(m, k) > 0.f) { if (first < 0) first = m; last = m; ++nz; }
+    if (nz == 0) continue;
+    if (k == 0) { why = "FFT bin 0 must not carry mel weight"; return -1; }
+    if (nz > 2 || last - first > 1) { why = "mel filterbank is not a 2-banded triangle bank"; return -1; }
+    // two weights: up-slope of `last`, down-slope of `first` -> interval `last`.  One weight (interval 0, the last
+    // interval, or a bin exactly on a centre): it is an up-slope weight up to the filter's peak, a down-slope weight
+    // after it; on the peak either neighbour interval yields the same sum, so keep the run monotone.
+    int iv;
+    if (nz == 2) iv = last;
+    else {
+      int peak = 0;
+      for (int kk = 1; kk < nb; ++kk)
+        if (W(first, kk) > W(first, peak)) peak = kk;
+      iv = k > peak ? first + 1 : first;
+      if (iv < prev && prev <= first + 1) iv = prev;
+    }
+    if (iv < prev) { why = "mel filterbank intervals are not monotone"; return -1; }
+    iv_of[k] = iv;
+    prev = iv;
+  }
+  std::vector<int> ilo(nm + 1, -1), icnt(nm + 1, 0);
+  for (int k = 0; k < nb; ++k) {
+    if (iv_of[k] < 0) continue;
+    const int iv = iv_of[k];
+    if (ilo[iv] < 0) ilo[iv] = k;
+    if (k != ilo[iv] + icnt[iv]) { why = "mel filterbank intervals are not contiguous"; return -1; }
+    icnt[iv]++;
+  }
+  rounds = (nm + 30) / 31;
+  int base = 0;
+  for (int r = 0; r < rounds; ++r) {
+    int c = 0;
+    for (int l = 0; l < 32; ++l) {
+      const int iv = 31 * r + l;
+      if (iv <= nm && icnt[iv] > c) c = icnt[iv];
+    }
+    cnt_out[r] = c;
+    base_out[r] = base;
+    if (base + c > kMelSlots) { why = "mel filterbank does not fit the sparse layout"; return -1; }
+    for (int l = 0; l < 32; ++l) {
+      const int iv = 31 * r + l;
+      int lo = (iv <= nm && icnt[iv]) ? ilo[iv] : 1;
+      if (lo + c > nb) lo = nb - c;                 // keep the padded run inside the spectrum
+      mlo[32 * r + l] = lo;
+      if (iv > nm) continue;
+      for (int q = 0; q < c; ++q) {
+        const int k = lo + q;
+        if (iv_of[k] != iv) continue;               // padding slot: weight 0
+        const float up = iv < nm ? W(iv, k) : 0.f;
+        const float dn = iv >= 1 ? W(iv - 1, k) : 0.f;
+        mw[(size_t)(base + q) * 32 + l] = make_float2(scale * up, scale * dn);
+      }
+    }
+    base += c;
+  }
+  for (int r = rounds; r < kMelRounds; ++r) { cnt_out[r] = 0; base_out[r] = base; }
   return 0;
 }
 
@@ -329,70 +401,13 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
 
   // sparse filterbank by interval: interval iv = bins whose mel lies in [centre(iv-1), centre(iv)); such a bin feeds
   // the up-slope of filter iv and the down-slope of filter iv-1 and nothing else (TA:494-499, triangles in mel domain)
-  std::vector<float2> mw((size_t)kMelSlots * 32, make_float2(0.f, 0.f));
-  std::vector<int> mlo(32 * kMelRounds, 1);
+  std::vector<float2> mw;
+  std::vector<int> mlo;
   {
-    const int nb = nfft / 2, nm = cfg->n_mels;
-    std::vector<int> iv_of(nb, -1);
-    int prev = 0;
-    for (int k = 0; k < nb; ++k) {
-      int first = -1, last = -1, nz = 0;
-      for (int m = 0; m < nm; ++m)
-        if (h->mel_host[(size_t)m * nb + k] > 0.f) { if (first < 0) first = m; last = m; ++nz; }
-      if (nz == 0) continue;
-      if (k == 0) return bail(B200FE_E_UNSUPPORTED, "FFT bin 0 must not carry mel weight");
-      if (nz > 2 || last - first > 1) return bail(B200FE_E_UNSUPPORTED, "mel filterbank is not a 2-banded triangle bank");
-      // two weights: up-slope of `last`, down-slope of `first` -> interval `last`.  One weight (interval 0, the last
-      // interval, or a bin exactly on a centre): it is an up-slope weight up to the filter's peak, a down-slope weight
-      // after it; on the peak either neighbour interval yields the same sum, so keep the run monotone.
-      int iv;
-      if (nz == 2) iv = last;
-      else {
-        int peak = 0;
-        for (int kk = 1; kk < nb; ++kk)
-          if (h->mel_host[(size_t)first * nb + kk] > h->mel_host[(size_t)first * nb + peak]) peak = kk;
-        iv = k > peak ? first + 1 : first;
-        if (iv < prev && prev <= first + 1) iv = prev;
-      }
-      if (iv < prev) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not monotone");
-      iv_of[k] = iv;
-      prev = iv;
-    }
-    std::vector<int> ilo(nm + 1, -1), icnt(nm + 1, 0);
-    for (int k = 0; k < nb; ++k) {
-      if (iv_of[k] < 0) continue;
-      const int iv = iv_of[k];
-      if (ilo[iv] < 0) ilo[iv] = k;
-      if (k != ilo[iv] + icnt[iv]) return bail(B200FE_E_UNSUPPORTED, "mel filterbank intervals are not contiguous");
-      icnt[iv]++;
-    }
-    h->mel_rounds = (nm + 30) / 31;
-    int base = 0;
-    for (int r = 0; r < h->mel_rounds; ++r) {
-      int c = 0;
-      for (int l = 0; l < 32; ++l) {
-        const int iv = 31 * r + l;
-        if (iv <= nm && icnt[iv] > c) c = icnt[iv];
-      }
-      h->mel_cnt[r] = c;
-      h->mel_base[r] = base;
-      if (base + c > kMelSlots) return bail(B200FE_E_UNSUPPORTED, "mel filterbank does not fit the sparse layout");
-      for (int l = 0; l < 32; ++l) {
-        const int iv = 31 * r + l;
-        int lo = (iv <= nm && icnt[iv]) ? ilo[iv] : 1;
-        if (lo + c > nb) lo = nb - c;                 // keep the padded run inside the spectrum
-        mlo[32 * r + l] = lo;
-        if (iv > nm) continue;
-        for (int q = 0; q < c; ++q) {
-          const int k = lo + q;
-          if (iv_of[k] != iv) continue;               // padding slot: weight 0
-          const float up = iv < nm ? h->mel_host[(size_t)iv * nb + k] : 0.f;
-          const float dn = iv >= 1 ? h->mel_host[(size_t)(iv - 1) * nb + k] : 0.f;
-          mw[(size_t)(base + q) * 32 + l] = make_float2(0.25f * up, 0.25f * dn);
-        }
-      }
-      base += c;
-    }
+    std::string why;
+    if (build_interval_table(h->mel_host, cfg->n_mels, nfft / 2, nfft / 2, 0.25f, mw, mlo, h->mel_rounds, h->mel_cnt,
+                             h->mel_base, why) != 0)
+      return bail(B200FE_E_UNSUPPORTED, why);
     h->mel_paraformer = h->mel_rounds == MelShapeParaformer::kRounds;
     for (int r = 0; r < MelShapeParaformer::kRounds && h->mel_paraformer; ++r)
       h->mel_paraformer = h->mel_cnt[r] == MelShapeParaformer::cnt(r);
@@ -613,3 +628,4 @@ int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int6
 }  // extern "C"
 
 #include "stream_api.inl"
+#include "tts_api.inl"

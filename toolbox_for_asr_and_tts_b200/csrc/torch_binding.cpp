@@ -225,6 +225,46 @@ void fe_synth_uniform(at::Tensor wave, const at::Tensor& offsets, const at::Tens
   TORCH_CHECK(rc == B200FE_OK, "b200fe_synth_uniform failed");
 }
 
+int64_t tts_create(int64_t sample_rate, int64_t n_fft, int64_t hop, int64_t n_mels, double f_min, double f_max) {
+  b200fe_tts* t = nullptr;
+  check(b200fe_tts_create((int)sample_rate, (int)n_fft, (int)hop, (int)n_mels, (float)f_min, (float)f_max, &t), nullptr,
+        "b200fe_tts_create");
+  return static_cast<int64_t>(reinterpret_cast<intptr_t>(t));
+}
+
+void tts_destroy(int64_t t) { b200fe_tts_destroy(reinterpret_cast<b200fe_tts*>(static_cast<intptr_t>(t))); }
+
+// wave: CUDA float32 [B, Nmax] (or flat with offsets); returns (mel [B, n_mels, max_frames], frames int64 [B])
+std::tuple<at::Tensor, at::Tensor> tts_forward(int64_t t, const at::Tensor& wave, const c10::optional<at::Tensor>& offsets,
+                                               const at::Tensor& lengths, int64_t hop, int64_t n_mels) {
+  TORCH_CHECK(wave.is_cuda() && wave.scalar_type() == at::kFloat, "b200fe.tts_forward: waveform must be CUDA float32 (no CPU fallback)");
+  c10::cuda::CUDAGuard guard(wave.device());
+  auto w = wave.contiguous();
+  auto len_host = lengths.to(at::kCPU, at::kLong).contiguous();
+  const int b = (int)len_host.numel();
+  at::Tensor off_host;
+  if (offsets.has_value() && offsets->defined()) off_host = offsets->to(at::kCPU, at::kLong).contiguous();
+  else {
+    TORCH_CHECK(w.dim() == 2 && w.size(0) == b, "waveform must be [B, Nmax] when no offsets are given");
+    off_host = at::arange(b, at::kLong) * w.size(1);
+  }
+  int64_t max_frames = 0;
+  for (int i = 0; i < b; ++i) {
+    const int64_t n = len_host.data_ptr<int64_t>()[i];
+    TORCH_CHECK(n > (1024 - hop) / 2, "reflect padding needs more than (n_fft-hop)/2 samples");
+    TORCH_CHECK(off_host.data_ptr<int64_t>()[i] + n <= w.numel(), "utterance outside the wave buffer");
+    max_frames = std::max(max_frames, n / hop);
+  }
+  auto len_dev = len_host.to(w.device(), true), off_dev = off_host.to(w.device(), true);
+  auto mel = at::empty({b, n_mels, max_frames}, w.options());
+  auto lens = at::empty({b}, w.options().dtype(at::kLong));
+  int rc = b200fe_tts_forward(reinterpret_cast<b200fe_tts*>(static_cast<intptr_t>(t)), w.data_ptr<float>(), w.numel(),
+                              off_dev.data_ptr<int64_t>(), len_dev.data_ptr<int64_t>(), b, max_frames, mel.data_ptr<float>(),
+                              max_frames, lens.data_ptr<int64_t>(), cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_tts_forward failed");
+  return {mel, lens};
+}
+
 int64_t fe_launch_count(int64_t h) { return b200fe_launch_count(H(h)); }
 
 void fe_profile_enable(int64_t h, bool on) { check(b200fe_profile_enable(H(h), on), H(h), "b200fe_profile_enable"); }
@@ -255,6 +295,9 @@ TORCH_LIBRARY(b200fe, m) {
   m.def("stream_push(int h, Tensor state, int n_streams, int max_chunk, Tensor chunks, Tensor chunk_lens, Tensor stream_ids, "
         "Tensor? is_final) -> (Tensor, Tensor)", fe_stream_push);
   m.def("synth_uniform(Tensor wave, Tensor offsets, Tensor lengths, int seed, float amp) -> ()", fe_synth_uniform);
+  m.def("tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_min, float f_max) -> int", tts_create);
+  m.def("tts_destroy(int t) -> ()", tts_destroy);
+  m.def("tts_forward(int t, Tensor wave, Tensor? offsets, Tensor lengths, int hop, int n_mels) -> (Tensor, Tensor)", tts_forward);
   m.def("launch_count(int h) -> int", fe_launch_count);
   m.def("profile_enable(int h, bool on) -> ()", fe_profile_enable);
   m.def("profile_collect(int h) -> (float, int)", fe_profile_collect);

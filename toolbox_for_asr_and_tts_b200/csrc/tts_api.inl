@@ -1,0 +1,122 @@
+// TTS log-mel entry points of the C ABI (included at the end of b200fe.cu).
+struct b200fe_tts {
+  int sample_rate = 0, n_fft = 0, hop = 0, n_mels = 0;
+  float* d_window = nullptr;
+  float2* d_twiddle = nullptr;
+  float2* d_w1024 = nullptr;
+  float2* d_mel_w = nullptr;
+  int* d_mel_lo = nullptr;
+  int mel_rounds = 0, mel_cnt[kMelRounds] = {0}, mel_base[kMelRounds] = {0};
+  size_t smem = 0;
+  std::string err;
+};
+
+namespace {
+
+double slaney_hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+double slaney_mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+// Slaney-scale, Slaney-normalised triangular filters in the Hz domain: dense [n_mels, n_freqs]
+void build_slaney_bank(int n_freqs, double f_min, double f_max, int n_mels, int sample_rate, std::vector<float>& bank) {
+  std::vector<double> f_pts(n_mels + 2);
+  const double m_lo = slaney_hz_to_mel(f_min), m_hi = slaney_hz_to_mel(f_max);
+  for (int i = 0; i < n_mels + 2; ++i) f_pts[i] = slaney_mel_to_hz(m_lo + (m_hi - m_lo) * i / (n_mels + 1));
+  bank.assign((size_t)n_mels * n_freqs, 0.f);
+  for (int k = 0; k < n_freqs; ++k) {
+    const double f = (double)(sample_rate / 2) * k / (n_freqs - 1);
+    for (int m = 0; m < n_mels; ++m) {
+      const double down = (f - f_pts[m]) / (f_pts[m + 1] - f_pts[m]);
+      const double up = (f_pts[m + 2] - f) / (f_pts[m + 2] - f_pts[m + 1]);
+      const double v = fmax(0.0, fmin(down, up)) * (2.0 / (f_pts[m + 2] - f_pts[m]));
+      bank[(size_t)m * n_freqs + k] = (float)v;
+    }
+  }
+}
+
+thread_local std::string g_tts_error;
+
+}  // namespace
+
+extern "C" {
+
+int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_min, float f_max, b200fe_tts** out) {
+  if (!out) return B200FE_E_INVALID;
+  *out = nullptr;
+  auto failc = [&](int code, const std::string& m) { g_create_error = m; return code; };
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return failc(B200FE_E_CUDA, "no CUDA device: no CPU fallback");
+  if (n_fft != kTtsNfft) return failc(B200FE_E_UNSUPPORTED, "only n_fft = 1024 is implemented");
+  if (hop <= 0 || (hop & 1) || hop > n_fft || (n_fft - hop) % 2) return failc(B200FE_E_INVALID, "hop must be even and <= n_fft");
+  if (n_mels < 4 || n_mels > kMaxMels) return failc(B200FE_E_UNSUPPORTED, "n_mels must be in [4, 128]");
+  if (!(f_min >= 0 && f_max > f_min && f_max <= sample_rate / 2.0f)) return failc(B200FE_E_INVALID, "bad f_min / f_max");
+  b200fe_tts* t = new b200fe_tts();
+  t->sample_rate = sample_rate; t->n_fft = n_fft; t->hop = hop; t->n_mels = n_mels;
+  t->smem = tts_smem_bytes(hop, n_mels);
+  if (t->smem > 227 * 1024) { delete t; return failc(B200FE_E_UNSUPPORTED, "hop too large for the shared-memory tile"); }
+  std::vector<float> bank;
+  build_slaney_bank(n_fft / 2 + 1, f_min, f_max, n_mels, sample_rate, bank);
+  std::vector<float2> mw;
+  std::vector<int> mlo;
+  std::string why;
+  if (build_interval_table(bank, n_mels, n_fft / 2, n_fft / 2 + 1, 1.0f, mw, mlo, t->mel_rounds, t->mel_cnt, t->mel_base, why) != 0) {
+    delete t;
+    return failc(B200FE_E_UNSUPPORTED, why);
+  }
+  for (int m = 0; m < n_mels; ++m)
+    if (bank[(size_t)m * (n_fft / 2 + 1) + n_fft / 2] != 0.f) { delete t; return failc(B200FE_E_UNSUPPORTED, "the Nyquist bin must not carry mel weight"); }
+  std::vector<float> win(n_fft);
+  for (int n = 0; n < n_fft; ++n) win[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / n_fft));   // periodic Hann
+  std::vector<float2> tw(kTwTable, make_float2(0.f, 0.f)), w1024(16);
+  for (int r = 0; r < kTwRows; ++r)
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const int ph = (n2 * r) & 511;
+      tw[r * kXRow + n2] = make_float2((float)cos(2.0 * M_PI * ph / 512.0), (float)(-sin(2.0 * M_PI * ph / 512.0)));
+    }
+  for (int jj = 0; jj < 16; ++jj) w1024[jj] = make_float2((float)cos(2.0 * M_PI * jj / 1024.0), (float)(-sin(2.0 * M_PI * jj / 1024.0)));
+  bool ok = cudaMalloc(&t->d_window, win.size() * 4) == cudaSuccess && cudaMalloc(&t->d_twiddle, tw.size() * 8) == cudaSuccess &&
+            cudaMalloc(&t->d_w1024, 16 * 8) == cudaSuccess && cudaMalloc(&t->d_mel_w, mw.size() * 8) == cudaSuccess &&
+            cudaMalloc(&t->d_mel_lo, mlo.size() * 4) == cudaSuccess;
+  ok = ok && cudaMemcpy(t->d_window, win.data(), win.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(t->d_twiddle, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(t->d_w1024, w1024.data(), 16 * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(t->d_mel_w, mw.data(), mw.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(t->d_mel_lo, mlo.data(), mlo.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) { b200fe_tts_destroy(t); return failc(B200FE_E_CUDA, "device allocation failed"); }
+  *out = t;
+  return B200FE_OK;
+}
+
+void b200fe_tts_destroy(b200fe_tts* t) {
+  if (!t) return;
+  cudaFree(t->d_window); cudaFree(t->d_twiddle); cudaFree(t->d_w1024); cudaFree(t->d_mel_w); cudaFree(t->d_mel_lo);
+  delete t;
+}
+
+int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total, const int64_t* offsets_dev,
+                       const int64_t* lengths_dev, int batch, int64_t max_frames, float* mel_dev, int64_t frames_cap,
+                       int64_t* mel_lens_dev, void* stream) {
+  if (!t) return B200FE_E_INVALID;
+  if (batch == 0) return B200FE_OK;
+  if (!wave_dev || !offsets_dev || !lengths_dev || !mel_dev || batch < 0 || max_frames > frames_cap) return B200FE_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TtsParams p;
+  p.wave = wave_dev; p.wave_total = wave_total; p.offsets = (const long long*)offsets_dev; p.lengths = (const long long*)lengths_dev;
+  p.batch = batch; p.hop = t->hop; p.n_mels = t->n_mels; p.mel = mel_dev; p.frames_cap = frames_cap;
+  p.mel_lens = (long long*)mel_lens_dev; p.mag_eps = 1e-9f; p.log_floor = 1e-5f;
+  p.window = t->d_window; p.twiddle = t->d_twiddle; p.w1024 = t->d_w1024;
+  p.mel_tab.w = t->d_mel_w; p.mel_tab.lo = t->d_mel_lo; p.mel_tab.rounds = t->mel_rounds;
+  for (int r = 0; r < kMelRounds; ++r) { p.mel_tab.cnt[r] = t->mel_cnt[r]; p.mel_tab.base[r] = t->mel_base[r]; }
+  if (cudaFuncSetAttribute(tts_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem) != cudaSuccess) return B200FE_E_CUDA;
+  tts_pad_kernel<<<dim3(8, batch), 256, 0, st>>>((const long long*)lengths_dev, t->hop, t->n_mels, mel_dev, frames_cap);
+  const int tiles = (int)((max_frames + kTtsFrames - 1) / kTtsFrames);
+  if (tiles > 0) tts_mel_kernel<<<dim3(tiles, batch), kCtaThreads, t->smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
+}
+
+}  // extern "C"
