@@ -6,7 +6,7 @@ import ctypes
 import numpy as np
 import pytest
 import torch
-from conftest import LOGMEL_ATOL, PARAFORMER
+from conftest import LOGMEL_ATOL, PARAFORMER, assert_logmel_close
 
 from oracle import kaldi_fbank_np as kf
 from oracle import wav_frontend_np as wf
@@ -19,6 +19,20 @@ DEV = "cuda:0"
 
 def cmvn_atol(cmvn):
     return LOGMEL_ATOL * float(np.abs(cmvn[1]).max())
+
+
+def assert_feats_close(got, ref, cmvn):
+    """LFR+CMVN features [..., 560]: undo the CMVN and compare in the log-mel domain (conftest.assert_logmel_close)."""
+    got = got.cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    ref = ref.cpu().numpy() if isinstance(ref, torch.Tensor) else np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if got.size == 0:
+        return
+    sh, sc = cmvn[0].astype(np.float64), cmvn[1].astype(np.float64)
+    m = cmvn.shape[1] // 80
+    lg = (got.astype(np.float64) / sc - sh).reshape(got.shape[:-1] + (m, 80))
+    lr = (ref.astype(np.float64) / sc - sh).reshape(ref.shape[:-1] + (m, 80))
+    assert_logmel_close(lg, lr)
 
 
 def make_fe(cmvn=None, **over):
@@ -67,8 +81,7 @@ def test_paraformer_against_golden(golden, cmvn, n):
     g = golden[f"paraformer_{n}"]
     assert feats.dtype == torch.float32 and lens.dtype == torch.int64
     assert tuple(feats.shape) == (1,) + g.shape and int(lens[0]) == g.shape[0]
-    err = np.abs(feats[0].cpu().numpy() - g).max()
-    assert err <= cmvn_atol(cmvn), err
+    assert_feats_close(feats[0], g, cmvn)
 
 
 @pytest.mark.parametrize("n", [400, 16000])
@@ -76,7 +89,7 @@ def test_povey_against_golden(golden, cmvn, n):
     fe = make_fe(cmvn, window="povey")
     x = torch.from_numpy(synth.uniform_pcm(SEED, n, n))[None].to(DEV)
     feats, _ = fe(x, [n])
-    assert np.abs(feats[0].cpu().numpy() - golden[f"povey_{n}"]).max() <= cmvn_atol(cmvn)
+    assert_feats_close(feats[0], golden[f"povey_{n}"], cmvn)
 
 
 def test_forward_fbank_against_golden(golden):
@@ -84,7 +97,7 @@ def test_forward_fbank_against_golden(golden):
     x = torch.from_numpy(synth.uniform_pcm(SEED, 16000, 16000))[None].to(DEV)
     feats, lens = fe.forward_fbank(x, [16000])
     assert tuple(feats.shape) == (1, 98, 80) and int(lens[0]) == 98
-    assert np.abs(feats[0].cpu().numpy() - golden["fbank_16000"]).max() <= LOGMEL_ATOL
+    assert_logmel_close(feats[0].cpu().numpy(), golden["fbank_16000"])
 
 
 def test_ragged_batch_against_golden(golden, cmvn):
@@ -95,7 +108,7 @@ def test_ragged_batch_against_golden(golden, cmvn):
     assert np.array_equal(flens.cpu().numpy(), golden["batch_lens"])
     f = feats.cpu().numpy()
     assert f.shape == golden["batch_feats"].shape
-    assert np.abs(f - golden["batch_feats"]).max() <= cmvn_atol(cmvn)
+    assert_feats_close(f, golden["batch_feats"], cmvn)
     for i, k in enumerate(golden["batch_lens"]):
         assert not f[i, k:].any()          # pad_sequence zeros, bit-exact
 
@@ -103,7 +116,7 @@ def test_ragged_batch_against_golden(golden, cmvn):
 def test_gaussian_with_dc_against_golden(golden, cmvn):
     fe = make_fe(cmvn)
     feats, _ = fe(torch.from_numpy(golden["gauss_input"])[None].to(DEV), [24000])
-    assert np.abs(feats[0].cpu().numpy() - golden["gauss_feats"]).max() <= cmvn_atol(cmvn)
+    assert_feats_close(feats[0], golden["gauss_feats"], cmvn)
 
 
 def test_counts_are_bit_exact_for_many_lengths():
@@ -124,7 +137,7 @@ def test_random_ragged_batch_against_oracle(cmvn):
     ref, rlens = wf.frontend_forward(waves, lens, cmvn=cmvn, **PARAFORMER)
     assert np.array_equal(flens.cpu().numpy(), rlens)
     d = np.abs(feats.cpu().numpy() - ref)
-    assert d.max() <= cmvn_atol(cmvn), d.max()
+    assert_feats_close(feats, ref, cmvn)
     print("ragged batch: max-abs", d.max(), "mean-abs", d.mean())
 
 
@@ -220,7 +233,7 @@ def test_streaming_concat_equals_offline(cmvn, chunk):
         cat = torch.cat(got[s], dim=0) if got[s] else torch.zeros(0, 560)
         assert cat.shape[0] == int(off_lens[s]), (s, chunk)
         # same kernels, but frames pair up differently inside the packed FFT: fp32 rounding noise only
-        assert (cat - off[s, :cat.shape[0]].cpu()).abs().max() <= cmvn_atol(cmvn), (s, chunk)
+        assert_feats_close(cat, off[s, :cat.shape[0]], cmvn)
 
 
 def test_streaming_600ms_row_schedule_and_reference_shaped_api(cmvn):
@@ -238,7 +251,7 @@ def test_streaming_600ms_row_schedule_and_reference_shaped_api(cmvn):
         if f.numel():
             outs.append(f[0])
     assert per[:3] == [10, 10, 10] and per[-1] == 7 and sum(per) == 167 == int(fl[0])
-    assert (torch.cat(outs) - full[0]).abs().max() <= cmvn_atol(cmvn)
+    assert_feats_close(torch.cat(outs), full[0], cmvn)
 
 
 def test_global_cmvn_statistics():
@@ -330,7 +343,8 @@ def test_raw_c_abi_with_ctypes(cmvn):
         assert rc == 0, lib.b200fe_last_error(h)
         torch.cuda.synchronize()
         g = dict(np.load(__import__("conftest").GOLDEN))["paraformer_16000"]
-        assert int(flen[0]) == 17 and np.abs(feats[0].cpu().numpy() - g).max() <= cmvn_atol(cmvn)
+        assert int(flen[0]) == 17
+        assert_feats_close(feats[0], g, cmvn)
     finally:
         lib.b200fe_destroy(h)
 
@@ -368,7 +382,7 @@ def test_streaming_512_streams_per_tick_match_single_stream_bitwise(cmvn):
     # and against the offline front-end on the concatenated audio
     off, ol = fe(wave[:4].reshape(4, -1), [chunk * ticks] * 4)
     assert int(ol[0]) == allrows.shape[1]
-    assert (off - allrows[:4]).abs().max() <= cmvn_atol(cmvn)
+    assert_feats_close(off, allrows[:4], cmvn)
 
 
 def test_sharded_bulk_extraction_equals_single_pass(cmvn):

@@ -43,7 +43,7 @@ struct b200fe_handle {
   std::vector<float> window_host;   // [L], without upscale
   std::vector<float> mel_host;      // [n_mels, nfft/2]
   float* d_window = nullptr;        // [512]
-  float2* d_twiddle = nullptr;      // [2*kTwTable]
+  float2* d_twiddle = nullptr;      // [kTw2Total]
   float2* d_mel_w = nullptr;        // [kMelSlots * 32] lane-transposed (up, down) weights
   int* d_mel_lo = nullptr;          // [32 * kMelRounds] first bin of every interval's padded run
   int mel_rounds = 0, mel_cnt[kMelRounds] = {0}, mel_base[kMelRounds] = {0};
@@ -412,14 +412,22 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
     for (int r = 0; r < MelShapeParaformer::kRounds && h->mel_paraformer; ++r)
       h->mel_paraformer = h->mel_cnt[r] == MelShapeParaformer::cnt(r);
   }
-  std::vector<float2> tw(2 * kTwTable, make_float2(0.f, 0.f));
+  // stage-2 twiddles of the packed real FFT (TileParams::twiddle) and the column-0 table, evaluated in double
+  std::vector<float2> tw(kTw2Total, make_float2(0.f, 0.f));
   for (int g = 0; g < 2; ++g)
-    for (int r = 0; r < kTwRows; ++r)
-      for (int n2 = 0; n2 < 16; ++n2) {
-        const int ph = (((n2 - 16 * g) * r) % 512 + 512) % 512;
-        tw[g * kTwTable + r * kXRow + n2] =
-            make_float2((float)cos(2.0 * M_PI * ph / 512.0), (float)(-sin(2.0 * M_PI * ph / 512.0)));
+    for (int k1 = 1; k1 <= 16; ++k1)
+      for (int c = 0; c < 16; ++c) {
+        const int ph = (((c - 16 * g) * k1) % 512 + 512) % 512;
+        const double sc = (k1 == 8 || k1 == 16) ? 2.0 : 1.0;
+        tw[g * kTw2Table + (k1 - 1) * kXRow + c] =
+            make_float2((float)(sc * cos(2.0 * M_PI * ph / 512.0)), (float)(-sc * sin(2.0 * M_PI * ph / 512.0)));
       }
+  for (int t = 0; t < 8; ++t)
+    for (int c = 0; c < 8; ++c) {
+      const int ph = (c * t) % 16;
+      tw[2 * kTw2Table + t * kC0Pitch + c] =
+          make_float2((float)(2.0 * cos(2.0 * M_PI * ph / 16.0)), (float)(-2.0 * sin(2.0 * M_PI * ph / 16.0)));
+    }
   CK(cudaMalloc(&h->d_window, 512 * sizeof(float)));
   CK(cudaMalloc(&h->d_twiddle, tw.size() * sizeof(float2)));
   CK(cudaMalloc(&h->d_mel_w, mw.size() * sizeof(float2)));

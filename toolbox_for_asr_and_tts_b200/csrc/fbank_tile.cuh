@@ -10,11 +10,13 @@
 //             between neighbouring tiles);  persistent CTAs stride over the tile list.
 //   * stage = the tile's samples are read ONCE from HBM with 128-bit loads, pre-emphasised and kept in shared memory
 //             (each sample feeds 2.5 frames).
-//   * FFT   = two real frames are packed into one 512-point complex FFT (frame A real, frame B imaginary) done by a
-//             group of 16 threads: a 32-point register FFT per thread, ONE shared-memory transpose, then two 16-point
-//             register FFTs per thread (columns k1 and 32-k1, so the conjugate pairs needed to separate the two
-//             frames are thread-local).  No shuffles on the FFT path; a warp (2 groups = 4 frames) never waits for
-//             another warp inside a tile.
+//   * FFT   = a group of 16 threads transforms two real frames at once, one frame per lane of packed f32x2 registers
+//             (FFMA2/FADD2/FMUL2: half the issue slots per flop).  Thread j owns samples n = 16 i + j: a REAL 32-point
+//             register FFT per thread (16-point complex FFT of even/odd samples + split), ONE shared-memory
+//             transpose of the 17 non-redundant columns, then one complex 16-point register FFT per thread on column
+//             j (column 16 for thread 0), whose 16 bins cover columns j and 32-j of the real spectrum.  Column 0
+//             (bins 0, 32, .., 224) is a direct 16-term sum by threads 0..7.  No shuffles on the FFT path; a warp
+//             (2 groups = 4 frames) never waits for another warp inside a tile.
 //   * mel   = power spectra of the warp's 4 frames are interleaved [bin][4] so one 128-bit shared load feeds 4 FMAs;
 //             the filterbank is stored sparse (<= 2 non-zeros per FFT bin).
 #pragma once
@@ -29,8 +31,17 @@ constexpr int kGroup = 16;          // threads per frame pair
 constexpr int kCtaThreads = 128;    // 4 warps, 8 groups
 constexpr int kWarps = kCtaThreads / 32;
 constexpr int kFMax = 32;           // frames per tile (upper bound)
-constexpr int kXRow = 18;           // float2 per transpose row: 16 + 2 pad -> 144 B, conflict-free 128-bit reads
+constexpr int kXRow = 18;           // float2 per row of the complex-FFT transpose (tts_mel.cuh): 16 + 2 pad -> 144 B
 constexpr int kXGroupFloat2 = 32 * kXRow;
+// Transpose buffer of the packed real FFT, per 16-thread group: rows k1 = 1..16 of 16 float4 (re A, re B, im A, im B),
+// pitch 17 float4 (272 B: 128-bit row reads by 16 threads are conflict-free), then row 0 as 16 float2 (real bins).
+constexpr int kYPitch = 17;
+constexpr int kYGroupF4 = 16 * kYPitch + 8;       // 280 float4 = 4480 B
+constexpr int kYWarpF4 = 2 * kYGroupF4;           // 8960 B per warp, aliased by the warp's 4 KB of power spectra
+// Twiddles of the packed FFT: [2 groups][16 rows k1 = 1..16][kXRow float2] then the column-0 table [8][kC0Pitch].
+constexpr int kTw2Table = 16 * kXRow;
+constexpr int kC0Pitch = 10;                      // float2; 80 B rows: conflict-free 128-bit reads by 8 threads
+constexpr int kTw2Total = 2 * kTw2Table + 8 * kC0Pitch;   // float2
 constexpr int kMaxMels = 128;
 constexpr int kMaxInt = kMaxMels + 1;  // intervals between consecutive filter centres
 constexpr int kMelRounds = (kMaxMels + 30) / 31;  // rounds of 31 filters: lane <-> interval, lane 31 only feeds lane 30
@@ -80,8 +91,9 @@ struct TileParams {
   float dither;
   unsigned long long seed;
   const float* window;    // [512] window * (2^15 if upscale), zero beyond L
-  const float2* twiddle;  // [2][17][kXRow]: table g is exp(-2*pi*i*(n2 - 16*g)*r/512); rows padded like the transpose
-                          // buffer.  Table 1 undoes the one-row rotation group 1 applies to its sample loads.
+  const float2* twiddle;  // [kTw2Total]: table g, row k1-1, entry c = s(k1) * exp(-2*pi*i*(c - 16*g)*k1/512), s = 2 for
+                          // k1 in {8, 16} else 1.  Table 1 undoes the one-row rotation group 1 applies to its sample
+                          // loads.  Then the column-0 table: row t, entry c = 2 * exp(-2*pi*i*c*t/16), c < 8.
   // sparse mel bank by interval between filter centres.  Round r: lane l <-> interval 31 r + l (the last lane's interval
   // is the first of the next round: it only supplies the down-slope sum of filter 31 r + 30).  Every round has a
   // warp-uniform trip count mel_cnt[r] = its widest interval; weights are zero-padded to it and stored lane-transposed:
@@ -98,9 +110,9 @@ __host__ __device__ inline size_t tile_smem_bytes(int e_cap, int n_mels) {
   size_t b = 0;
   b += (size_t)e_cap * 4;                           // staged, pre-emphasised samples
   b += 2 * kFMax * 4;                               // raw first / last sample of each frame
-  b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;      // transpose buffers (aliased by the power spectra)
+  b += (size_t)kWarps * kYWarpF4 * 16;              // transpose buffers (aliased by the power spectra)
   b += (size_t)kFMax * n_mels * 4;                  // log-mel of the tile
-  b += 2 * kTwTable * 8;                            // twiddles (one table per group of a warp)
+  b += kTw2Total * 8;                               // twiddles (one table per group of a warp + column 0)
   return b;
 }
 
@@ -287,38 +299,60 @@ __device__ __forceinline__ void load_window_taps(float (&win)[NROWS + 1], const 
   }
 }
 
+// This thread's row of the stage-2 twiddle table: column j (16 for thread 0) of table g (the rotated group's table
+// when the frame leaves room for the rotation).
+template <int NROWS>
+__device__ __forceinline__ const float2* fft_twiddle_row(const float2* tw_s, int j, int grp_in_warp) {
+  const int g = NROWS < 32 ? grp_in_warp : 0;
+  const int col = j == 0 ? 16 : j;
+  return tw_s + g * kTw2Table + (col - 1) * kXRow;
+}
+
 // ROT: the second 16-thread group of a warp loads its samples one 16-sample row late (register i holds row i-1).
 // Frames start 160 samples = 5*32 banks apart, so without this both groups of a warp would hit the same 16 banks on
 // every sample load (2-way conflict).  The rotation multiplies FFT32 output k1 by W32^k1, which twiddle table 1
 // undoes for free.
+//
+// Packed real FFT (tools/model_s2.py is the numpy model of this dataflow): lane .x of every f2 is frame A, .y frame B.
+//   stage 1  y[i] = windowed sample 16(i-g)+j;  z[m] = y[2m] + i y[2m+1];  Z = FFT16(z);  split -> Y[k1], k1 = 0..16
+//            (2 Y[k1] for k1 not in {0, 8, 16}; the twiddle rows of 8 and 16 and the column-0 table carry the 2).
+//   transpose rows k1 = 1..16 as float4 (re A, re B, im A, im B), row 0 (real) as float2.
+//   stage 2  thread j: column col = j (16 for thread 0):  X[col + 32 k2] = FFT16_c( Y_c[col] * tw[col][c] ), k2 = 0..15;
+//            bins beyond 256 are the conjugates of bins (32 - col) + 32 (15 - k2) and have the same power.
+//   column 0 thread t < 8: X[32 t] = sum_c Y_c[0] W16^(c t)  (real input: 8 folded terms).
+// All stored powers are 4 |X[k]|^2 (the mel weights carry the 0.25).
 template <int NROWS, bool EXACT, bool DITHER, class MELS>
 __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_s, const float* xl_s, int F, int quad,
-                                           int S, int L, const float (&win)[NROWS + 1], float2* xg, float4* pbuf4,
-                                           const float2* tw_s, const MelTab& mel, int M,
+                                           int S, int L, const float (&win)[NROWS + 1], float4* yg, float4* pbuf4,
+                                           const float2* tw_row, const float2* c0_row, const MelTab& mel, int M,
                                            float preemph, int remove_dc, float log_floor, float dither,
                                            unsigned long long seed, unsigned utt, unsigned frame_abs0, float* logmel,
                                            int j, int grp_in_warp, int lane) {
   constexpr bool ROT = NROWS < 32;
   constexpr int NR = ROT ? NROWS + 1 : NROWS;      // register rows in use
+  constexpr int LIVE = (NR + 1) / 2;               // complex points z[m] that can be non-zero
+  static_assert(LIVE == 16 || LIVE > 8, "frame rows must cover more than half of the FFT");
   const int g = ROT ? grp_in_warp : 0;
-  const int fA = 4 * quad + 2 * grp_in_warp;   // tile-local frame of the real lane; fA + 1 is the imaginary lane
+  const int fA = 4 * quad + 2 * grp_in_warp;   // tile-local frame of lane .x; fA + 1 is lane .y
   const bool vA = fA < F, vB = fA + 1 < F;
-  float re[32], im[32];
+  f2 zr[16], zi[16];
+  f2 y0, y16;
   {
+    f2 y[2 * LIVE];
     // stage 1 load: thread j owns samples n = 16*row + j of both frames; register i holds row i - g
     const float* eA = e_base + fA * S + j - 16 * g;
     const float* eB = eA + S;
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
+    for (int i = 0; i < 2 * LIVE; ++i) {
       bool in;
-      if constexpr (EXACT) in = ROT ? (i == 0 ? g == 0 : (i == NROWS ? g == 1 : true)) : true;
-      else in = (i - g >= 0) && (16 * (i - g) + j < L);
-      re[i] = (vA && in) ? eA[16 * i] : 0.f;
-      im[i] = (vB && in) ? eB[16 * i] : 0.f;
+      if constexpr (EXACT) in = ROT ? (i == 0 ? g == 0 : (i == NROWS ? g == 1 : i < NROWS)) : true;
+      else in = (i - g >= 0) && (i < NR) && (16 * (i - g) + j < L);
+      y[i].x = (vA && in) ? eA[16 * i] : 0.f;
+      y[i].y = (vB && in) ? eB[16 * i] : 0.f;
     }
-    float x0A = 0.f, xlA = 0.f, x0B = 0.f, xlB = 0.f;
-    if (vA) { x0A = x0_s[fA]; xlA = xl_s[fA]; }
-    if (vB) { x0B = x0_s[fA + 1]; xlB = xl_s[fA + 1]; }
+    f2 x0 = make_float2(0.f, 0.f), xl = make_float2(0.f, 0.f);
+    if (vA) { x0.x = x0_s[fA]; xl.x = xl_s[fA]; }
+    if (vB) { x0.y = x0_s[fA + 1]; xl.y = xl_s[fA + 1]; }
     if constexpr (DITHER) {
       // x'[n] = x[n] + dither*g(frame, n)  (TA:179-181: independent noise per (frame, sample));
       // the pre-emphasised value picks up dither*(g(n) - preemph*g(n-1))
@@ -328,71 +362,127 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
         const int n = 16 * (i - g) + j;
         if (n >= 0 && n < L) {
           const int nm = n > 0 ? n - 1 : 0;
-          if (vA) re[i] += dither * (dither_normal(seed, utt, fa, n) - preemph * dither_normal(seed, utt, fa, nm));
-          if (vB) im[i] += dither * (dither_normal(seed, utt, fa + 1, n) - preemph * dither_normal(seed, utt, fa + 1, nm));
+          if (vA) y[i].x += dither * (dither_normal(seed, utt, fa, n) - preemph * dither_normal(seed, utt, fa, nm));
+          if (vB) y[i].y += dither * (dither_normal(seed, utt, fa + 1, n) - preemph * dither_normal(seed, utt, fa + 1, nm));
         }
       }
-      if (vA) { x0A += dither * dither_normal(seed, utt, fa, 0); xlA += dither * dither_normal(seed, utt, fa, L - 1); }
-      if (vB) { x0B += dither * dither_normal(seed, utt, fa + 1, 0); xlB += dither * dither_normal(seed, utt, fa + 1, L - 1); }
+      if (vA) { x0.x += dither * dither_normal(seed, utt, fa, 0); xl.x += dither * dither_normal(seed, utt, fa, L - 1); }
+      if (vB) { x0.y += dither * dither_normal(seed, utt, fa + 1, 0); xl.y += dither * dither_normal(seed, utt, fa + 1, L - 1); }
     }
     if (j == 0) {  // replicate rule at the frame start: y[0] = x[0] - preemph * x[0]  (TA:193-198)
-      const float yA = fmaf(-preemph, x0A, x0A), yB = fmaf(-preemph, x0B, x0B);
-      if (g == 0) { re[0] = yA; im[0] = yB; }
-      if constexpr (ROT) { if (g == 1) { re[1] = yA; im[1] = yB; } }
+      const f2 yf = fma2s(x0, -preemph, x0);
+      if (g == 0) y[0] = yf;
+      if constexpr (ROT) { if (g == 1) y[1] = yf; }
     }
     // frame sums as 4 independent chains (a serial chain of 25 adds would expose the FADD latency)
-    float sA4[4] = {0.f, 0.f, 0.f, 0.f}, sB4[4] = {0.f, 0.f, 0.f, 0.f};
+    f2 s4[4];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) { sA4[i & 3] += re[i]; sB4[i & 3] += im[i]; }
-    float sA = (sA4[0] + sA4[1]) + (sA4[2] + sA4[3]), sB = (sB4[0] + sB4[1]) + (sB4[2] + sB4[3]);
+    for (int i = 0; i < 4; ++i) s4[i] = y[i];
+#pragma unroll
+    for (int i = 4; i < NR; ++i) s4[i & 3] = add2(s4[i & 3], y[i]);
+    f2 s = add2(add2(s4[0], s4[1]), add2(s4[2], s4[3]));
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) {
-      sA += __shfl_xor_sync(0xffffffffu, sA, o);
-      sB += __shfl_xor_sync(0xffffffffu, sB, o);
+      f2 t;
+      t.x = __shfl_xor_sync(0xffffffffu, s.x, o);
+      t.y = __shfl_xor_sync(0xffffffffu, s.y, o);
+      s = add2(s, t);
     }
     // (1-preemph) * mean(frame), recovered from the sum of the pre-emphasised samples
-    float mA = 0.f, mB = 0.f;
-    if (remove_dc) {
-      const float invL = 1.0f / (float)L;
-      mA = (sA - preemph * (xlA - x0A)) * invL;
-      mB = (sB - preemph * (xlB - x0B)) * invL;
-    }
+    f2 mean = make_float2(0.f, 0.f);
+    if (remove_dc) mean = mul2s(fma2s(sub2(xl, x0), -preemph, s), 1.0f / (float)L);
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
-      re[i] = (re[i] - mA) * win[i];
-      im[i] = (im[i] - mB) * win[i];
-    }
-#pragma unroll
-    for (int i = NR; i < 32; ++i) { re[i] = 0.f; im[i] = 0.f; }
-  }
-  // ---- 512-point complex FFT of the packed pair: columns k1 = j (A) and 32 - rowB (B) end up in this thread
-  const int rowB = j == 0 ? 16 : j;
-  float ar[16], ai[16], br[16], bi[16];
-  fft512_columns<NR>(re, im, xg, tw_s + g * kTwTable, j, ar, ai, br, bi);
-
-  // ---- separate the two real frames: slot i pairs Z[k] (first) with Z[512-k] (second).
-  {
-    const bool t0 = (j == 0);
-#define A_RE(k) ar[bitrev<16>(k)]
-#define A_IM(k) ai[bitrev<16>(k)]
-#define B_RE(k) br[bitrev<16>(((k) + 1) & 15)]
-#define B_IM(k) bi[bitrev<16>(((k) + 1) & 15)]
-    const int binA = j, binB = 32 - rowB;
-    float2* pb2 = reinterpret_cast<float2*>(pbuf4) + grp_in_warp * 256;   // [2 groups][256 bins] of (frame A, frame B)
+    for (int i = 0; i < NR; ++i) y[i] = mul2s(sub2(y[i], mean), win[i]);
+    // z[m] = y[2m] + i y[2m+1] at bit-reversed positions (decimation in time)
     static_for<0, 16>([&](auto ic) {
-      constexpr int i = decltype(ic)::value;
-      const float ur = A_RE(i), ui = A_IM(i);
-      const float vr = B_RE(15 - i), vi = B_IM(15 - i);
-      const float s1 = ur + vr, d1 = ui - vi, s2 = ui + vi, d2 = ur - vr;
-      const float pA = fmaf(s1, s1, d1 * d1);   // 4 * |X_A[k]|^2
-      const float pB = fmaf(s2, s2, d2 * d2);   // 4 * |X_B[k]|^2
-      const int bin = i < 8 ? binA + 32 * i : binB + 32 * (15 - i);
-      pb2[bin] = (t0 && i == 0) ? make_float2(0.f, 0.f) : make_float2(pA, pB);   // bin 0 carries no mel weight
+      constexpr int m = decltype(ic)::value;
+      if constexpr (m < LIVE) {
+        zr[bitrev<16>(m)] = y[2 * m];
+        zi[bitrev<16>(m)] = (2 * m + 1 < NR) ? y[2 * m + 1] : make_float2(0.f, 0.f);
+      } else {
+        zr[bitrev<16>(m)] = make_float2(0.f, 0.f);
+        zi[bitrev<16>(m)] = make_float2(0.f, 0.f);
+      }
     });
-#undef A_RE
-#undef A_IM
-#undef B_RE
-#undef B_IM
+  }
+  fft_dit2<16, LIVE>(zr, zi);
+  real32_split2(zr, zi, y0, y16);
+
+  // ---- transpose: row k1 of the group's buffer <- Y_j[k1]
+  __syncwarp();   // earlier readers of the (aliased) buffer are done
+  // 64-bit stores (the register allocator does not form the aligned quads a 128-bit store needs).  Slots 8..15 hold
+  // (im, re) instead of (re, im), so the 16 lanes of a group always write 32 distinct banks.
+  {
+    float2* yg2 = reinterpret_cast<float2*>(yg) + 2 * j;
+    const int hr = j >> 3, hi = hr ^ 1;
+    static_for<1, 16>([&](auto ic) {
+      constexpr int k1 = decltype(ic)::value;
+      yg2[(k1 - 1) * 2 * kYPitch + hr] = zr[k1];
+      yg2[(k1 - 1) * 2 * kYPitch + hi] = zi[k1];
+    });
+    yg2[15 * 2 * kYPitch + hr] = y16;
+    yg2[15 * 2 * kYPitch + hi] = make_float2(0.f, 0.f);
+  }
+  reinterpret_cast<float2*>(yg + 16 * kYPitch)[j] = y0;
+  __syncwarp();
+
+  // ---- stage 2: twiddle and 16-point complex FFT of this thread's column
+  const int col = j == 0 ? 16 : j;
+  f2 ar[16], ai[16];
+  {
+    const float4* rowp = yg + (col - 1) * kYPitch;
+    const float4* tw4 = reinterpret_cast<const float4*>(tw_row);
+    static_for<0, 8>([&](auto ic) {
+      constexpr int h = decltype(ic)::value;
+      const float4 t = tw4[h];
+      const float4 v0 = rowp[2 * h], v1 = rowp[2 * h + 1];
+      constexpr bool sw = 2 * h >= 8;   // slots 8..15 are stored (im, re)
+      {
+        const f2 yr = sw ? make_float2(v0.z, v0.w) : make_float2(v0.x, v0.y);
+        const f2 yi = sw ? make_float2(v0.x, v0.y) : make_float2(v0.z, v0.w);
+        ar[bitrev<16>(2 * h)] = fma2s(yr, t.x, neg2(mul2s(yi, t.y)));
+        ai[bitrev<16>(2 * h)] = fma2s(yr, t.y, mul2s(yi, t.x));
+      }
+      {
+        const f2 yr = sw ? make_float2(v1.z, v1.w) : make_float2(v1.x, v1.y);
+        const f2 yi = sw ? make_float2(v1.x, v1.y) : make_float2(v1.z, v1.w);
+        ar[bitrev<16>(2 * h + 1)] = fma2s(yr, t.z, neg2(mul2s(yi, t.w)));
+        ai[bitrev<16>(2 * h + 1)] = fma2s(yr, t.w, mul2s(yi, t.z));
+      }
+    });
+  }
+  // ---- column 0: thread t = j & 7 sums the 16 real bins Y_c[0] against W16^(c t), folded to 8 terms
+  f2 p0;
+  {
+    const float4* u4 = reinterpret_cast<const float4*>(yg + 16 * kYPitch);   // 16 x (A, B)
+    const float4* w4 = reinterpret_cast<const float4*>(c0_row);
+    const float sgn = (j & 1) ? -1.f : 1.f;
+    f2 cr, ci;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float4 ua = u4[h], ub = u4[h + 4], w = w4[h];
+      const f2 v0 = fma2s(make_float2(ub.x, ub.y), sgn, make_float2(ua.x, ua.y));
+      const f2 v1 = fma2s(make_float2(ub.z, ub.w), sgn, make_float2(ua.z, ua.w));
+      if (h == 0) { cr = mul2s(v0, w.x); ci = mul2s(v0, w.y); }
+      else { cr = fma2s(v0, w.x, cr); ci = fma2s(v0, w.y, ci); }
+      cr = fma2s(v1, w.z, cr);
+      ci = fma2s(v1, w.w, ci);
+    }
+    p0 = fma2(cr, cr, mul2(ci, ci));
+  }
+  fft_dit2<16>(ar, ai);
+  __syncwarp();   // every lane has consumed the transpose buffer: the spectra may overwrite it
+
+  // ---- power spectra of the group's two frames: [2 groups][256 bins] x (frame A, frame B)
+  {
+    float2* pb2 = reinterpret_cast<float2*>(pbuf4) + grp_in_warp * 256;
+    static_for<0, 16>([&](auto ic) {
+      constexpr int k2 = decltype(ic)::value;
+      const f2 pw = fma2(ar[k2], ar[k2], mul2(ai[k2], ai[k2]));
+      if constexpr (k2 < 8) pb2[col + 32 * k2] = pw;
+      else if (j != 0) pb2[(32 - col) + 32 * (15 - k2)] = pw;
+    });
+    if (j < 8) pb2[32 * j] = p0;   // bin 0 carries no mel weight
   }
   __syncwarp();
 
@@ -433,8 +523,8 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   float* e_s = reinterpret_cast<float*>(smem_raw);
   float* x0_s = e_s + p.e_cap;
   float* xl_s = x0_s + kFMax;
-  float2* xbuf = reinterpret_cast<float2*>(xl_s + kFMax);
-  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
+  float4* xbuf = reinterpret_cast<float4*>(xl_s + kFMax);
+  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * kYWarpF4);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + kFMax * p.n_mels);
 
   const int tid = threadIdx.x;
@@ -447,7 +537,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   const int lfr_left = (p.lfr_m - 1) / 2;
 
   // ---- per-CTA constants: tables to shared memory, this thread's window taps to registers
-  for (int i = tid; i < 2 * kTwTable; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   MelTab mel;
   mel.w = p.mel_w; mel.lo = p.mel_lo; mel.rounds = p.mel_rounds;
 #pragma unroll
@@ -485,8 +575,10 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   __syncthreads();
 
   const unsigned wave_mis = (unsigned)((reinterpret_cast<uintptr_t>(p.wave) >> 2) & 3);
-  float2* xg = xbuf + (warp * 2 + grp_in_warp) * kXGroupFloat2;                 // this group's transpose buffer
-  float4* pbuf4 = reinterpret_cast<float4*>(xbuf + warp * 2 * kXGroupFloat2);   // this warp's [bin][4 frames] spectra
+  float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;   // this group's transpose buffer
+  float4* pbuf4 = xbuf + warp * kYWarpF4;                          // this warp's power spectra (aliases both groups)
+  const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
+  const float2* c0_row = tw_s + 2 * kTw2Table + (j & 7) * kC0Pitch;
 
   // tile descriptors are read one tile ahead so that no dependent global load sits in front of a tile
   TileDesc cur;
@@ -576,7 +668,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
 
     // ---- per warp: quads of 4 frames (2 groups x 2 frames), no CTA-wide sync inside
     for (int quad = warp; 4 * quad < F; quad += kWarps)
-      fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s + a_off, x0_s, xl_s, F, quad, S, L, win, xg, pbuf4, tw_s, mel, M,
+      fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s + a_off, x0_s, xl_s, F, quad, S, L, win, yg, pbuf4, tw_row, c0_row, mel, M,
                                        p.preemph, p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)utt,
                                        (unsigned)f_lo, logmel_s, j, grp_in_warp, lane);
     __syncthreads();

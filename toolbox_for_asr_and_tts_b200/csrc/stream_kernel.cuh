@@ -63,9 +63,9 @@ __host__ __device__ inline size_t stream_smem_bytes(int e_cap, int nf_max, int c
   size_t b = 0;
   b += (size_t)e_cap * 4;
   b += (size_t)2 * ((nf_max + 3) & ~3) * 4;
-  b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;
+  b += (size_t)kWarps * kYWarpF4 * 16;
   b += (size_t)(cache_cap + nf_max) * n_mels * 4;
-  b += 2 * kTwTable * 8;
+  b += kTw2Total * 8;
   return b;
 }
 
@@ -89,8 +89,8 @@ stream_push_kernel(const StreamParams p) {
   float* e_s = reinterpret_cast<float*>(smem_raw);
   float* x0_s = e_s + p.e_cap;
   float* xl_s = x0_s + nfp;
-  float2* xbuf = reinterpret_cast<float2*>(xl_s + nfp);
-  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
+  float4* xbuf = reinterpret_cast<float4*>(xl_s + nfp);
+  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * kYWarpF4);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + (p.lay.cache_cap + p.nf_max) * p.n_mels);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -112,7 +112,7 @@ stream_push_kernel(const StreamParams p) {
   const int n_new = min(max(p.chunk_lens[b], 0), p.max_chunk);
   const bool fin = p.is_final && p.is_final[b];
 
-  for (int i = tid; i < 2 * kTwTable; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   MelTab mel;
   mel.w = p.mel_w; mel.lo = p.mel_lo; mel.rounds = p.mel_rounds;
 #pragma unroll
@@ -150,10 +150,12 @@ stream_push_kernel(const StreamParams p) {
   }
   __syncthreads();
 
-  float2* xg = xbuf + (warp * 2 + grp_in_warp) * kXGroupFloat2;
-  float4* pbuf4 = reinterpret_cast<float4*>(xbuf + warp * 2 * kXGroupFloat2);
+  float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;
+  float4* pbuf4 = xbuf + warp * kYWarpF4;
+  const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
+  const float2* c0_row = tw_s + 2 * kTw2Table + (j & 7) * kC0Pitch;
   for (int quad = warp; 4 * quad < nf; quad += kWarps)
-    fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s, x0_s, xl_s, nf, quad, S, L, win, xg, pbuf4, tw_s, mel, M, p.preemph,
+    fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s, x0_s, xl_s, nf, quad, S, L, win, yg, pbuf4, tw_row, c0_row, mel, M, p.preemph,
                                      p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)sid, (unsigned)t_seen,
                                      logmel_s + cache_len * M, j, grp_in_warp, lane);
   __syncthreads();
