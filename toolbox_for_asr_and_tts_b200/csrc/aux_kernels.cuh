@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "fbank_tile.cuh"
+#include "fbank_warp.cuh"
 
 namespace b200fe {
 
@@ -161,6 +162,36 @@ __global__ void build_tiles_kernel(const UttDesc* utts, int batch, int n_tiles, 
   d.F = f_hi - d.f_lo + 1;
   d.g0 = ud.wave_off + (long long)d.f_lo * S;
   tiles[t] = d;
+}
+
+// Expands the per-utterance descriptors into the launch-wide quad list of the warp kernel: quad q of utterance u covers
+// frames 4 (q - quad_begin[u]) .. +3.  One thread per quad; utterances without frames own no quads.
+__global__ void build_quads_kernel(const UttDesc* utts, int batch, int n_quads, int S, int lfr_m, int lfr_n, int M,
+                                   QuadDesc* quads) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_quads) return;
+  int lo = 0, hi = batch - 1;
+  while (lo < hi) {   // last utterance whose quad_begin <= q (empty utterances share the next one's quad_begin)
+    const int mid = (lo + hi + 1) >> 1;
+    if (utts[mid].quad_begin <= q) lo = mid; else hi = mid - 1;
+  }
+  const UttDesc ud = utts[lo];
+  QuadDesc d;
+  d.utt = lo;
+  d.T = ud.n_frames;
+  d.rows = ud.n_rows;
+  d.f0 = 4 * (q - ud.quad_begin);
+  const int nF = min(4, ud.n_frames - d.f0);
+  d.g0 = ud.wave_off + (long long)d.f0 * S;
+  d.pad = 0;
+  int slow = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    d.tgt[2 * t] = d.tgt[2 * t + 1] = kNoTarget;
+    if (t < nF && quad_targets(d.f0 + t, d.T, d.rows, lfr_m, lfr_n, M, d.tgt + 2 * t)) slow |= 1 << t;
+  }
+  d.nF = nF | (slow << 8);
+  quads[q] = d;
 }
 
 // Counter-based synthetic PCM, bit-identical to toolbox_for_asr_and_tts_b200/synth.py::uniform_pcm.

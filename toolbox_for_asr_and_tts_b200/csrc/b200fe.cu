@@ -7,8 +7,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -16,6 +18,7 @@
 
 #include "aux_kernels.cuh"
 #include "fbank_tile.cuh"
+#include "fbank_warp.cuh"
 #include "stream_kernel.cuh"
 #include "tts_mel.cuh"
 
@@ -58,6 +61,7 @@ struct b200fe_handle {
   int next_slot = 0;
   long long launches = 0;
   bool profile = false;
+  bool force_tile = false;           // B200FE_FORCE_TILE=1: keep the tile kernel (A/B measurements)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   mutable std::string err;
 };
@@ -205,6 +209,7 @@ struct Plan {
   std::vector<UttDesc> utts;
   std::vector<ShortDesc> shorts;
   int n_tiles = 0;
+  int n_quads = 0;
   long long max_rows = 0;
   long long total_rows = 0;
 };
@@ -213,17 +218,20 @@ int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, 
               Plan& pl) {
   pl.utts.resize(batch);
   pl.shorts.clear();
-  int tile = 0;
+  int tile = 0, quad = 0;
   for (int u = 0; u < batch; ++u) {
     const long long n = lengths[u];
     UttDesc d;
     d.wave_off = offsets ? offsets[u] : (long long)u * row_stride;
     d.n_samples = (int)n;
     d.tile_begin = tile;
+    d.quad_begin = quad;
+    d.reserved = 0;
     if (n >= h->L) {
       d.n_frames = frame_count(n, h->L, h->S);
       d.n_rows = ceil_div(d.n_frames, h->cfg.lfr_n);
       tile += ceil_div(d.n_rows, h->rows_per_tile);
+      quad += ceil_div(d.n_frames, 4);
     } else {
       const int win = short_window(h->cfg, n);
       if (win < 2 || win > n) return fail(h, B200FE_E_SHORT, "choose a window size " + std::to_string(win) +
@@ -246,13 +254,15 @@ int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, 
     pl.utts[u] = d;
   }
   pl.n_tiles = tile;
+  pl.n_quads = quad;
   return 0;
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-size_t workspace_need(int batch, int n_tiles = 0) {
-  return align256((size_t)batch * sizeof(UttDesc)) + align256((size_t)batch * sizeof(ShortDesc)) +
-         align256((size_t)n_tiles * sizeof(TileDesc));
+// the tile list (statistics pass) and the quad list (warp kernel) share one region: a launch uses one of them
+size_t workspace_need(int batch, int n_tiles = 0, int n_quads = 0) {
+  const size_t lists = std::max((size_t)n_tiles * sizeof(TileDesc), (size_t)n_quads * sizeof(QuadDesc));
+  return align256((size_t)batch * sizeof(UttDesc)) + align256((size_t)batch * sizeof(ShortDesc)) + align256(lists);
 }
 
 // stream-ordered upload through a small ring of pinned buffers
@@ -297,6 +307,32 @@ int launch_tile(b200fe_handle* h, const TileParams& p, int grid, bool dither, bo
   if (dither) { if (stats) LAUNCH(true, true); else LAUNCH(true, false); }
   else        { if (stats) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
+  if (h->profile) {
+    CUDA_TRY(h, cudaEventRecord(e1, st));
+    h->prof_events.emplace_back(e0, e1);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+template <int NROWS, bool EXACT, class MELS, int SR>
+int launch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cudaStream_t st) {
+  const size_t smem = warp_smem_bytes();
+#define LAUNCHW(DI)                                                                                   \
+  do {                                                                                                \
+    auto k = fbank_warp_kernel<NROWS, EXACT, DI, MELS, SR>;                                             \
+    CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k<<<grid, kCtaThreads, smem, st>>>(p);                                                            \
+  } while (0)
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profile) {
+    CUDA_TRY(h, cudaEventCreate(&e0));
+    CUDA_TRY(h, cudaEventCreate(&e1));
+    CUDA_TRY(h, cudaEventRecord(e0, st));
+  }
+  if (dither) LAUNCHW(true); else LAUNCHW(false);
+#undef LAUNCHW
   if (h->profile) {
     CUDA_TRY(h, cudaEventRecord(e1, st));
     h->prof_events.emplace_back(e0, e1);
@@ -375,6 +411,7 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
 
   b200fe_handle* h = new b200fe_handle();
   h->cfg = *cfg;
+  { const char* ft = getenv("B200FE_FORCE_TILE"); h->force_tile = ft && ft[0] == '1'; }
   h->L = L; h->S = S; h->nfft = nfft;
   h->D = cfg->lfr_m * cfg->n_mels;
   h->rows_per_tile = (kFMax - cfg->lfr_m) / cfg->lfr_n + 1;
@@ -510,7 +547,7 @@ int b200fe_plan(b200fe_handle* h, const int64_t* lengths_host, int batch, int64_
     if (n_rows_out) n_rows_out[u] = pl.utts[u].n_rows;
   }
   if (max_rows_out) *max_rows_out = pl.max_rows;
-  if (workspace_bytes) *workspace_bytes = workspace_need(batch, pl.n_tiles);
+  if (workspace_bytes) *workspace_bytes = workspace_need(batch, pl.n_tiles, pl.n_quads);
   return B200FE_OK;
 }
 
@@ -527,7 +564,7 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
   Plan pl;
   int rc = make_plan(h, lengths_host, offsets_host, row_stride, batch, pl);
   if (rc) return rc;
-  if (workspace_bytes < workspace_need(batch, pl.n_tiles)) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
+  if (workspace_bytes < workspace_need(batch, pl.n_tiles, pl.n_quads)) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
   if (pl.max_rows > rows_cap) return fail(h, B200FE_E_INVALID, "rows_cap smaller than the longest utterance's row count");
   for (int u = 0; u < batch; ++u) {
     const long long end = pl.utts[u].wave_off + lengths_host[u];
@@ -536,8 +573,17 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
   UttDesc* d_utts = reinterpret_cast<UttDesc*>(workspace_dev);
   ShortDesc* d_shorts = reinterpret_cast<ShortDesc*>((char*)workspace_dev + align256((size_t)batch * sizeof(UttDesc)));
   TileDesc* d_tiles = reinterpret_cast<TileDesc*>((char*)d_shorts + align256((size_t)batch * sizeof(ShortDesc)));
+  QuadDesc* d_quads = reinterpret_cast<QuadDesc*>(d_tiles);   // same region: a launch uses one of the two lists
   if ((rc = upload(h, pl.utts.data(), (size_t)batch * sizeof(UttDesc), d_utts, st))) return rc;
-  if (pl.n_tiles > 0) {
+  // the warp kernel does everything except the CMVN statistics (which need the row-major tile pass)
+  const bool use_warp = stats_dev == nullptr && warp_kernel_fits(h->L, h->S) && !h->force_tile &&
+                        pl.max_rows * (long long)h->D < (1ll << kTargetOffBits) - 1;
+  if (use_warp && pl.n_quads > 0) {
+    build_quads_kernel<<<(pl.n_quads + 255) / 256, 256, 0, st>>>(d_utts, batch, pl.n_quads, h->S, h->cfg.lfr_m,
+                                                                 h->cfg.lfr_n, h->cfg.n_mels, d_quads);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+  } else if (pl.n_tiles > 0) {
     build_tiles_kernel<<<(pl.n_tiles + 255) / 256, 256, 0, st>>>(d_utts, batch, pl.n_tiles, h->rows_per_tile, h->cfg.lfr_m,
                                                                  h->cfg.lfr_n, h->S, d_tiles);
     CUDA_TRY(h, cudaGetLastError());
@@ -553,8 +599,27 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
   }
-  // 2. the fused tile kernel over all regular utterances
-  if (pl.n_tiles > 0) {
+  // 2. the fused kernel over all regular utterances: warp kernel, or tile kernel for the statistics pass
+  if (use_warp && pl.n_quads > 0) {
+    QuadParams p;
+    p.wave = wave_dev; p.wave_total = wave_total; p.quads = d_quads; p.n_quads = pl.n_quads;
+    p.feats = feats_dev; p.rows_cap = rows_cap;
+    p.frame_len = h->L; p.frame_shift = h->S; p.n_mels = h->cfg.n_mels; p.lfr_m = h->cfg.lfr_m; p.lfr_n = h->cfg.lfr_n;
+    p.preemph = h->cfg.preemphasis; p.remove_dc = h->cfg.remove_dc_offset; p.log_floor = h->cfg.log_floor;
+    p.dither = h->cfg.dither / (h->cfg.upscale_samples ? 32768.f : 1.f);   // TA:179 adds it after the 2^15 upscale
+    p.seed = dither_seed;
+    p.window = h->d_window; p.twiddle = h->d_twiddle; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_rounds = h->mel_rounds;
+    for (int r = 0; r < kMelRounds; ++r) { p.mel_cnt[r] = h->mel_cnt[r]; p.mel_base[r] = h->mel_base[r]; }
+    p.cmvn = h->d_cmvn;
+    const int ctas = (pl.n_quads + kWarps - 1) / kWarps;
+    const int grid = ctas < 4 * h->n_sms ? ctas : 4 * h->n_sms;
+    const bool dither = h->cfg.dither != 0.f;
+    if (h->L == 400 && h->S == 160 && h->mel_paraformer) rc = launch_warp<25, true, MelShapeParaformer, 10>(h, p, grid, dither, st);
+    else if (h->L == 400 && h->S == 160) rc = launch_warp<25, true, MelShapeRuntime, 10>(h, p, grid, dither, st);
+    else if (h->L == 400) rc = launch_warp<25, true, MelShapeRuntime, 0>(h, p, grid, dither, st);
+    else rc = launch_warp<32, false, MelShapeRuntime, 0>(h, p, grid, dither, st);
+    if (rc) return rc;
+  } else if (pl.n_tiles > 0) {
     TileParams p;
     p.wave = wave_dev; p.wave_total = wave_total; p.utts = d_utts; p.tiles = d_tiles; p.batch = batch; p.n_tiles = pl.n_tiles;
     p.feats = feats_dev; p.rows_cap = rows_cap; p.stats = stats_dev;

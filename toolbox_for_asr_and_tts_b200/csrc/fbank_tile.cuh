@@ -56,6 +56,8 @@ struct UttDesc {          // built on the host by b200fe_plan/forward
   int n_frames;           // T      (TA:65-70)
   int n_rows;             // T_lfr  (VF:43)
   int tile_begin;         // index of the utterance's first tile in the launch-wide tile list
+  int quad_begin;         // index of the utterance's first quad in the launch-wide quad list (fbank_warp.cuh)
+  int reserved;
 };
 
 // One tile of the launch-wide work list, fully resolved by build_tiles_kernel so that the fused kernel never chases a
@@ -177,9 +179,10 @@ struct MelShapeFixed {
 using MelShapeParaformer = MelShapeFixed<3, 2, 5, 9>;
 
 // One round of the interval mel: lane <-> interval 31 r + lane.  CNT >= 0: compile-time trip count (fully unrolled).
-template <int CNT>
+// epi(iv, a, b, c, d) receives the natural-log mel energies of filter iv for the warp's 4 frames.
+template <int CNT, class EPI>
 __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, int base, const float2* pg, int lane, int M,
-                                          int F, int quad, float log_floor, float* logmel) {
+                                          float log_floor, EPI&& epi) {
   const int cnt = CNT >= 0 ? CNT : cnt_rt;
   const int iv = lane + 31 * r;
   const int lo = __ldg(mel.lo + 32 * r + lane);
@@ -206,13 +209,31 @@ __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, 
   const float ey = up.y + __shfl_down_sync(0xffffffffu, dn.y, 1);
   const float ez = up.z + __shfl_down_sync(0xffffffffu, dn.z, 1);
   const float ew = up.w + __shfl_down_sync(0xffffffffu, dn.w, 1);
-  if (lane < 31 && iv < M) {
-    const int fr = 4 * quad;
-    float* dst = logmel + fr * M + iv;
-    if (fr < F) dst[0] = fast_ln(fmaxf(ex, log_floor));
-    if (fr + 1 < F) dst[M] = fast_ln(fmaxf(ey, log_floor));
-    if (fr + 2 < F) dst[2 * M] = fast_ln(fmaxf(ez, log_floor));
-    if (fr + 3 < F) dst[3 * M] = fast_ln(fmaxf(ew, log_floor));
+  if (lane < 31 && iv < M)
+    epi(iv, fast_ln(fmaxf(ex, log_floor)), fast_ln(fmaxf(ey, log_floor)), fast_ln(fmaxf(ez, log_floor)),
+        fast_ln(fmaxf(ew, log_floor)));
+}
+
+// Sparse mel + log for the warp's 4 frames.  lane <-> interval between two filter centres: every FFT bin lies in
+// exactly one interval and feeds the up-slope of filter j and the down-slope of filter j-1, so each bin is read once:
+// energy[m] = up[m] + down[m+1].  Trip counts are warp-uniform (zero-padded weights): no divergence.
+template <class MELS, class EPI>
+__device__ __forceinline__ void mel_stage(const MelTab& mel, const float4* pbuf4, int lane, int M, float log_floor, EPI&& epi) {
+  const float2* pg = reinterpret_cast<const float2*>(pbuf4);
+  if constexpr (MELS::kFixed) {
+    static_for<0, MELS::kRounds>([&](auto ic) {
+      constexpr int r = decltype(ic)::value;
+      mel_round<MELS::cnt(r)>(mel, r, 0, MELS::base(r), pg, lane, M, log_floor, epi);
+    });
+  } else {
+#pragma unroll 1
+    for (int r = 0; r < mel.rounds; ++r) {
+      int cnt = mel.cnt[0], base = mel.base[0];   // selected with static indices so that they stay warp-uniform
+#pragma unroll
+      for (int t = 1; t < kMelRounds; ++t)
+        if (r == t) { cnt = mel.cnt[t]; base = mel.base[t]; }
+      mel_round<-1>(mel, r, cnt, base, pg, lane, M, log_floor, epi);
+    }
   }
 }
 
@@ -321,42 +342,54 @@ __device__ __forceinline__ const float2* fft_twiddle_row(const float2* tw_s, int
 //            bins beyond 256 are the conjugates of bins (32 - col) + 32 (15 - k2) and have the same power.
 //   column 0 thread t < 8: X[32 t] = sum_c Y_c[0] W16^(c t)  (real input: 8 folded terms).
 // All stored powers are 4 |X[k]|^2 (the mel weights carry the 0.25).
-template <int NROWS, bool EXACT, bool DITHER, class MELS>
-__device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_s, const float* xl_s, int F, int quad,
-                                           int S, int L, const float (&win)[NROWS + 1], float4* yg, float4* pbuf4,
-                                           const float2* tw_row, const float2* c0_row, const MelTab& mel, int M,
-                                           float preemph, int remove_dc, float log_floor, float dither,
-                                           unsigned long long seed, unsigned utt, unsigned frame_abs0, float* logmel,
-                                           int j, int grp_in_warp, int lane) {
+// Stage 1 of a group's frame pair: load, [dither], frame-start rule, DC removal, window, real 32-point FFT.
+//   eA        first (pre-emphasised) sample of frame A in shared memory; frame B starts S samples later
+//   x0 / xl   raw first / last sample of the two frames (lane .x = frame A)
+// Out: zr/zi[1..15] = 2 Y[k1], zr/zi[8] = Y[8], y0 = Y[0], y16 = Y[16] (real).
+// SR > 0: the frame shift is SR 16-sample rows (compile-time), so frame B's row i is frame A's row i + SR and the
+// overlapping rows are loaded once.
+template <int NROWS, bool EXACT, bool DITHER, int SR = 0>
+__device__ __forceinline__ void quad_stage1(const float* eA, f2 x0, f2 xl, bool vA, bool vB, int S, int L,
+                                            const float (&win)[NROWS + 1], float preemph, int remove_dc, float dither,
+                                            unsigned long long seed, unsigned utt, unsigned frame_abs_a, int j, int g,
+                                            f2 (&zr)[16], f2 (&zi)[16], f2& y0, f2& y16) {
   constexpr bool ROT = NROWS < 32;
   constexpr int NR = ROT ? NROWS + 1 : NROWS;      // register rows in use
   constexpr int LIVE = (NR + 1) / 2;               // complex points z[m] that can be non-zero
   static_assert(LIVE == 16 || LIVE > 8, "frame rows must cover more than half of the FFT");
-  const int g = ROT ? grp_in_warp : 0;
-  const int fA = 4 * quad + 2 * grp_in_warp;   // tile-local frame of lane .x; fA + 1 is lane .y
-  const bool vA = fA < F, vB = fA + 1 < F;
-  f2 zr[16], zi[16];
-  f2 y0, y16;
   {
     f2 y[2 * LIVE];
-    // stage 1 load: thread j owns samples n = 16*row + j of both frames; register i holds row i - g
-    const float* eA = e_base + fA * S + j - 16 * g;
-    const float* eB = eA + S;
+    // thread j owns samples n = 16*row + j of both frames; register i holds row i - g
+    eA += j - 16 * g;
+    auto row_in = [&](int i) {
+      if constexpr (EXACT) return ROT ? (i == 0 ? g == 0 : (i == NROWS ? g == 1 : i < NROWS)) : true;
+      else return (i - g >= 0) && (i < NR) && (16 * (i - g) + j < L);
+    };
+    if constexpr (SR > 0 && EXACT) {
+      float r[2 * LIVE + SR];
 #pragma unroll
-    for (int i = 0; i < 2 * LIVE; ++i) {
-      bool in;
-      if constexpr (EXACT) in = ROT ? (i == 0 ? g == 0 : (i == NROWS ? g == 1 : i < NROWS)) : true;
-      else in = (i - g >= 0) && (i < NR) && (16 * (i - g) + j < L);
-      y[i].x = (vA && in) ? eA[16 * i] : 0.f;
-      y[i].y = (vB && in) ? eB[16 * i] : 0.f;
+      for (int i = 0; i < 2 * LIVE + SR; ++i) {
+        const bool need = (i < 2 * LIVE && vA && row_in(i)) || (i >= SR && vB && row_in(i - SR));
+        r[i] = need ? eA[16 * i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 2 * LIVE; ++i) {
+        y[i].x = (vA && row_in(i)) ? r[i] : 0.f;
+        y[i].y = (vB && row_in(i)) ? r[i + SR] : 0.f;
+      }
+    } else {
+      const float* eB = eA + S;
+#pragma unroll
+      for (int i = 0; i < 2 * LIVE; ++i) {
+        const bool in = row_in(i);
+        y[i].x = (vA && in) ? eA[16 * i] : 0.f;
+        y[i].y = (vB && in) ? eB[16 * i] : 0.f;
+      }
     }
-    f2 x0 = make_float2(0.f, 0.f), xl = make_float2(0.f, 0.f);
-    if (vA) { x0.x = x0_s[fA]; xl.x = xl_s[fA]; }
-    if (vB) { x0.y = x0_s[fA + 1]; xl.y = xl_s[fA + 1]; }
     if constexpr (DITHER) {
       // x'[n] = x[n] + dither*g(frame, n)  (TA:179-181: independent noise per (frame, sample));
       // the pre-emphasised value picks up dither*(g(n) - preemph*g(n-1))
-      const unsigned fa = frame_abs0 + (unsigned)fA;
+      const unsigned fa = frame_abs_a;
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int n = 16 * (i - g) + j;
@@ -407,9 +440,14 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
   }
   fft_dit2<16, LIVE>(zr, zi);
   real32_split2(zr, zi, y0, y16);
+}
 
-  // ---- transpose: row k1 of the group's buffer <- Y_j[k1]
-  __syncwarp();   // earlier readers of the (aliased) buffer are done
+// Stage 2: transpose through the group's buffer, twiddle, complex 16-point FFT of this thread's column, column 0,
+// and the power spectra of the group's two frames into pbuf4 = [2 groups][256 bins] x (frame A, frame B), which
+// aliases both groups' transpose buffers.  The caller has passed a __syncwarp since the last reader of that memory;
+// on return every lane has passed a __syncwarp after the last write.
+__device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[16], f2 y0, f2 y16, float4* yg, float4* pbuf4,
+                                            const float2* tw_row, const float2* c0_row, int j, int grp_in_warp) {
   // 64-bit stores (the register allocator does not form the aligned quads a 128-bit store needs).  Slots 8..15 hold
   // (im, re) instead of (re, im), so the 16 lanes of a group always write 32 distinct banks.
   {
@@ -426,7 +464,6 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
   reinterpret_cast<float2*>(yg + 16 * kYPitch)[j] = y0;
   __syncwarp();
 
-  // ---- stage 2: twiddle and 16-point complex FFT of this thread's column
   const int col = j == 0 ? 16 : j;
   f2 ar[16], ai[16];
   {
@@ -457,14 +494,14 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
     const float4* u4 = reinterpret_cast<const float4*>(yg + 16 * kYPitch);   // 16 x (A, B)
     const float4* w4 = reinterpret_cast<const float4*>(c0_row);
     const float sgn = (j & 1) ? -1.f : 1.f;
-    f2 cr, ci;
+    f2 cr = make_float2(0.f, 0.f), ci = make_float2(0.f, 0.f);
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       const float4 ua = u4[h], ub = u4[h + 4], w = w4[h];
       const f2 v0 = fma2s(make_float2(ub.x, ub.y), sgn, make_float2(ua.x, ua.y));
       const f2 v1 = fma2s(make_float2(ub.z, ub.w), sgn, make_float2(ua.z, ua.w));
-      if (h == 0) { cr = mul2s(v0, w.x); ci = mul2s(v0, w.y); }
-      else { cr = fma2s(v0, w.x, cr); ci = fma2s(v0, w.y, ci); }
+      cr = fma2s(v0, w.x, cr);
+      ci = fma2s(v0, w.y, ci);
       cr = fma2s(v1, w.z, cr);
       ci = fma2s(v1, w.w, ci);
     }
@@ -472,8 +509,6 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
   }
   fft_dit2<16>(ar, ai);
   __syncwarp();   // every lane has consumed the transpose buffer: the spectra may overwrite it
-
-  // ---- power spectra of the group's two frames: [2 groups][256 bins] x (frame A, frame B)
   {
     float2* pb2 = reinterpret_cast<float2*>(pbuf4) + grp_in_warp * 256;
     static_for<0, 16>([&](auto ic) {
@@ -485,28 +520,35 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
     if (j < 8) pb2[32 * j] = p0;   // bin 0 carries no mel weight
   }
   __syncwarp();
+}
 
-  // ---- sparse mel + log for the warp's 4 frames.  lane <-> interval between two filter centres: every FFT bin lies in
-  //      exactly one interval and feeds the up-slope of filter j and the down-slope of filter j-1, so each bin is read
-  //      once: energy[m] = up[m] + down[m+1].  Trip counts are warp-uniform (zero-padded weights): no divergence.
-  {
-    const float2* pg = reinterpret_cast<const float2*>(pbuf4);
-    if constexpr (MELS::kFixed) {
-      static_for<0, MELS::kRounds>([&](auto ic) {
-        constexpr int r = decltype(ic)::value;
-        mel_round<MELS::cnt(r)>(mel, r, 0, MELS::base(r), pg, lane, M, F, quad, log_floor, logmel);
-      });
-    } else {
-#pragma unroll 1
-      for (int r = 0; r < mel.rounds; ++r) {
-        int cnt = mel.cnt[0], base = mel.base[0];   // selected with static indices so that they stay warp-uniform
-#pragma unroll
-        for (int t = 1; t < kMelRounds; ++t)
-          if (r == t) { cnt = mel.cnt[t]; base = mel.base[t]; }
-        mel_round<-1>(mel, r, cnt, base, pg, lane, M, F, quad, log_floor, logmel);
-      }
-    }
-  }
+// Log-mel of tile-local frames 4*quad .. 4*quad+3 into logmel[F][M] (shared memory): tile and streaming kernels.
+template <int NROWS, bool EXACT, bool DITHER, class MELS>
+__device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_s, const float* xl_s, int F, int quad,
+                                           int S, int L, const float (&win)[NROWS + 1], float4* yg, float4* pbuf4,
+                                           const float2* tw_row, const float2* c0_row, const MelTab& mel, int M,
+                                           float preemph, int remove_dc, float log_floor, float dither,
+                                           unsigned long long seed, unsigned utt, unsigned frame_abs0, float* logmel,
+                                           int j, int grp_in_warp, int lane) {
+  const int g = NROWS < 32 ? grp_in_warp : 0;
+  const int fA = 4 * quad + 2 * grp_in_warp;   // tile-local frame of lane .x; fA + 1 is lane .y
+  const bool vA = fA < F, vB = fA + 1 < F;
+  f2 x0 = make_float2(0.f, 0.f), xl = make_float2(0.f, 0.f);
+  if (vA) { x0.x = x0_s[fA]; xl.x = xl_s[fA]; }
+  if (vB) { x0.y = x0_s[fA + 1]; xl.y = xl_s[fA + 1]; }
+  f2 zr[16], zi[16], y0, y16;
+  quad_stage1<NROWS, EXACT, DITHER>(e_base + fA * S, x0, xl, vA, vB, S, L, win, preemph, remove_dc, dither, seed, utt,
+                                    frame_abs0 + (unsigned)fA, j, g, zr, zi, y0, y16);
+  __syncwarp();   // earlier readers of the (aliased) buffer are done
+  quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
+  const int fr = 4 * quad;
+  mel_stage<MELS>(mel, pbuf4, lane, M, log_floor, [&](int iv, float a, float b, float c, float d) {
+    float* dst = logmel + fr * M + iv;
+    if (fr < F) dst[0] = a;
+    if (fr + 1 < F) dst[M] = b;
+    if (fr + 2 < F) dst[2 * M] = c;
+    if (fr + 3 < F) dst[3 * M] = d;
+  });
 }
 
 template <bool STATS>

@@ -137,7 +137,7 @@ std::tuple<at::Tensor, at::Tensor> fe_lfr_cmvn(int64_t h, const at::Tensor& fban
   max_rows = tmax;
   auto feats_full = at::empty({b, max_rows, d}, x.options());
   auto lens = at::empty({b}, x.options().dtype(at::kLong));
-  auto work = at::empty({(int64_t)(256 + 64 * (int64_t)b + 512)}, x.options().dtype(at::kByte));
+  auto work = at::empty({(int64_t)(1024 + 128 * (int64_t)b)}, x.options().dtype(at::kByte));
   check(b200fe_lfr_cmvn(H(h), x.data_ptr<float>(), x.size(1), nf.data_ptr<int64_t>(), b, feats_full.data_ptr<float>(), max_rows,
                         lens.data_ptr<int64_t>(), work.data_ptr(), (size_t)work.numel(), cur_stream()),
         H(h), "b200fe_lfr_cmvn");
