@@ -251,7 +251,7 @@ def run_ours(args, rank, world, local_rank):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "fbank_lfr_cmvn_tile_kernel", "kernel_ms_per_launch": kern_ms / max(kern_n, 1),
+                "kernel": "fbank_warp_kernel", "kernel_ms_per_launch": kern_ms / max(kern_n, 1),
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": (kern_ms / ms_total) if ms_total else None}
 

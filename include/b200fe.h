@@ -154,7 +154,19 @@ int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int6
 /* Kernel launches issued by this handle since create() (bench.py's gpu_launches). */
 int64_t b200fe_launch_count(const b200fe_handle* h);
 
-/* Roofline support: while enabled, every launch of the dominant (fused tile) kernel is bracketed by CUDA events
+/* Where one fbank frame lands in the LFR-stacked output (VF:40-60, closed form: frame f is slot jj of row i wherever
+ * clamp(lfr_n*i + jj - (lfr_m-1)/2, 0, n_frames-1) == f).  Host-side, no device needed: this is the planner the quad
+ * list of the fused kernel is built with, exported so that it can be tested against apply_lfr on the CPU.
+ * targets_out[k] = (jj << 27) | (row * lfr_m*n_mels + jj * n_mels), or 0xFFFFFFFF when unused.
+ * Returns 1 when the frame takes the generic path instead (first / last frame of the utterance, or more than two
+ * slots per frame), 0 otherwise, negative on bad arguments. */
+int b200fe_lfr_targets(int frame, int n_frames, int n_rows, int lfr_m, int lfr_n, int n_mels, uint32_t targets_out[2]);
+
+/* Kernel selection for A/B measurements and tests: 0 = automatic (warp-autonomous kernel whenever it applies),
+ * 1 = always the tile kernel (the one that also accumulates CMVN statistics).  Results are identical. */
+int b200fe_select_kernel(b200fe_handle* h, int which);
+
+/* Roofline support: while enabled, every launch of the dominant (fused) kernel is bracketed by CUDA events
  * recorded on the launching stream.  b200fe_profile_collect synchronises those events, returns the summed kernel
  * time and the number of launches since the last collect, and clears the list. */
 int b200fe_profile_enable(b200fe_handle* h, int on);

@@ -425,3 +425,59 @@ def test_tts_log_mel_against_frozen_definition():
         assert not mel[i, :, ref.shape[1]:].any()           # padded frames are zero
     with pytest.raises(RuntimeError):
         fe(torch.zeros(1, 24000), [24000])                  # CPU tensors are rejected
+
+
+@pytest.mark.parametrize("m,n", [(7, 6), (5, 1), (1, 1), (3, 2), (9, 4)])
+def test_warp_kernel_equals_tile_kernel(m, n):
+    """The warp-autonomous kernel (quad list, scattered LFR rows) and the tile kernel (row-major LFR pass) run the
+    same arithmetic up to which half of a warp a frame lands in (the two halves use differently rotated sample rows
+    and twiddle tables): same shapes, lengths and zero padding, values equal to float32 rounding noise, whatever the
+    frame count modulo 4 / lfr_n, including utterances of 1..3 frames and the LFR settings of the reference's other
+    models (FSMN-VAD uses 5/1).  Both are then checked against the oracle."""
+    rng = np.random.default_rng(m * 10 + n)
+    cm = np.stack([rng.normal(-8.0, 1.0, m * 80), rng.uniform(0.2, 0.5, m * 80)]).astype(np.float32)
+    conf = dict(PARAFORMER, dither=0.0, lfr_m=m, lfr_n=n)
+    lens = np.array([400, 559, 560, 720, 880, 1040, 1200, 4001, 16003, 7777, 32000, 1601, 48017], dtype=np.int64)
+    waves = [synth.uniform_pcm(77, i, int(k)) for i, k in enumerate(lens)]
+    x = dense_batch(waves)
+    fe_w = WavFrontend(cmvn=torch.from_numpy(cm), **conf)
+    fe_t = WavFrontend(cmvn=torch.from_numpy(cm), **conf)
+    fe_t.select_kernel("tile")
+    a, la = fe_w(x, lens.tolist())
+    b, lb = fe_t(x, lens.tolist())
+    assert torch.equal(la, lb) and a.shape == b.shape
+    assert torch.equal(a == 0, b == 0)
+    assert_feats_close(a, b, cm)
+    ref, rl = wf.frontend_forward(waves, lens, cmvn=cm, **dict(PARAFORMER, lfr_m=m, lfr_n=n))
+    assert np.array_equal(la.cpu().numpy(), rl)
+    got = a.cpu().numpy()
+    sh, sc = cm[0].astype(np.float64), cm[1].astype(np.float64)
+    lg = (got.astype(np.float64) / sc - sh).reshape(got.shape[:-1] + (m, 80))
+    lr = (ref.astype(np.float64) / sc - sh).reshape(ref.shape[:-1] + (m, 80))
+    for i, k in enumerate(rl):
+        assert_logmel_close(lg[i, :k], lr[i, :k])
+        assert not got[i, k:].any()
+
+
+def test_fsmn_vad_frontend_configuration():
+    """the FSMN-VAD front-end the reference runs per chunk (R:voice_interface.py:1585-1590) is the same
+    fbank with LFR 5/1; offline and streaming in 600 ms chunks against the oracle."""
+    rng = np.random.default_rng(5)
+    cm = np.stack([rng.normal(-8.0, 1.0, 400), rng.uniform(0.2, 0.5, 400)]).astype(np.float32)
+    conf = dict(PARAFORMER, lfr_m=5, lfr_n=1)
+    w = synth.uniform_pcm(63, 0, 48000)
+    fe = WavFrontend(cmvn=torch.from_numpy(cm), dither=0.0, **conf)
+    feats, fl = fe(torch.from_numpy(w)[None].to(DEV), [48000])
+    ref, rl = wf.frontend_forward([w], [48000], cmvn=cm, **conf)
+    assert int(fl[0]) == int(rl[0]) == 298
+    assert_feats_close(feats[0], ref[0], cm)
+    on = WavFrontendOnline(cmvn=torch.from_numpy(cm), max_chunk_samples=9600, dither=0.0, **conf)
+    cache, outs = {}, []
+    for s in range(0, 48000, 9600):
+        c = torch.from_numpy(w[s:s + 9600])[None].to(DEV)
+        f, l = on(c, [9600], cache=cache, is_final=(s + 9600 >= 48000))
+        if f.numel():
+            outs.append(f[0])
+    cat = torch.cat(outs)
+    assert cat.shape[0] == 298
+    assert_feats_close(cat, feats[0], cm)

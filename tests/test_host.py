@@ -135,3 +135,43 @@ def test_two_rank_gloo_sharding_and_stats_allreduce(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GLOO_OK" in outs[0]
+
+
+@pytest.mark.parametrize("m,n", [(7, 6), (5, 1), (1, 1), (3, 2), (8, 3), (4, 6), (2, 5)])
+def test_lfr_target_planner_reproduces_apply_lfr(m, n):
+    """The quad list of the fused kernel routes every fbank frame to its (row, slot) pairs with b200fe_lfr_targets
+    (host code of the C ABI).  Scattering frames with those targets, plus the generic clamp rule for the frames it
+    flags, must rebuild apply_lfr (VF:40-60) exactly, for every utterance length."""
+    from oracle import wav_frontend_np as wf
+    lib = _native.cdll()
+    lib.b200fe_lfr_targets.restype = ctypes.c_int
+    M = 4
+    D = m * M
+    left = (m - 1) // 2
+    out2 = (ctypes.c_uint32 * 2)()
+    for T in list(range(1, 40)) + [97, 98, 99, 100, 101, 102, 103, 600]:
+        feats = np.arange(T * M, dtype=np.float32).reshape(T, M) + 1.0
+        ref = wf.apply_lfr(feats, m, n)
+        rows = ref.shape[0]
+        got = np.zeros_like(ref)
+        hits = np.zeros(ref.shape, dtype=np.int32)
+        for f in range(T):
+            rc = lib.b200fe_lfr_targets(f, T, rows, m, n, M, out2)
+            assert rc in (0, 1)
+            if rc == 1:      # generic path of the kernel: every (row, slot) whose clamped source frame is f
+                assert out2[0] == 0xFFFFFFFF and out2[1] == 0xFFFFFFFF
+                for i in range(rows):
+                    for jj in range(m):
+                        if min(max(n * i + jj - left, 0), T - 1) == f:
+                            got[i, jj * M:(jj + 1) * M] = feats[f]
+                            hits[i, jj * M:(jj + 1) * M] += 1
+            else:
+                for code in out2:
+                    if code == 0xFFFFFFFF:
+                        continue
+                    jj, off = code >> 27, code & ((1 << 27) - 1)
+                    assert off % M == 0 and (off % D) == jj * M
+                    got.reshape(-1)[off:off + M] = feats[f]
+                    hits.reshape(-1)[off:off + M] += 1
+        assert np.array_equal(got, ref), (m, n, T)
+        assert (hits == 1).all(), (m, n, T)       # every output element is written exactly once

@@ -501,6 +501,22 @@ int b200fe_shift_samples(const b200fe_handle* h) { return h ? h->S : B200FE_E_IN
 int b200fe_fft_size(const b200fe_handle* h) { return h ? h->nfft : B200FE_E_INVALID; }
 int64_t b200fe_launch_count(const b200fe_handle* h) { return h ? h->launches : 0; }
 
+int b200fe_lfr_targets(int frame, int n_frames, int n_rows, int lfr_m, int lfr_n, int n_mels, uint32_t targets_out[2]) {
+  if (!targets_out || frame < 0 || frame >= n_frames || n_rows < 1 || lfr_m < 1 || lfr_n < 1 || n_mels < 1) return B200FE_E_INVALID;
+  unsigned t2[2];
+  const bool slow = quad_targets(frame, n_frames, n_rows, lfr_m, lfr_n, n_mels, t2);
+  targets_out[0] = t2[0];
+  targets_out[1] = t2[1];
+  return slow ? 1 : 0;
+}
+
+int b200fe_select_kernel(b200fe_handle* h, int which) {
+  if (!h || which < 0 || which > 1) return B200FE_E_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->force_tile = which == 1;
+  return B200FE_OK;
+}
+
 int b200fe_profile_enable(b200fe_handle* h, int on) {
   if (!h) return B200FE_E_INVALID;
   std::lock_guard<std::mutex> lock(h->mu);

@@ -267,6 +267,8 @@ std::tuple<at::Tensor, at::Tensor> tts_forward(int64_t t, const at::Tensor& wave
 
 int64_t fe_launch_count(int64_t h) { return b200fe_launch_count(H(h)); }
 
+void fe_select_kernel(int64_t h, int64_t which) { check(b200fe_select_kernel(H(h), (int)which), H(h), "b200fe_select_kernel"); }
+
 void fe_profile_enable(int64_t h, bool on) { check(b200fe_profile_enable(H(h), on), H(h), "b200fe_profile_enable"); }
 
 std::tuple<double, int64_t> fe_profile_collect(int64_t h) {
@@ -299,6 +301,7 @@ TORCH_LIBRARY(b200fe, m) {
   m.def("tts_destroy(int t) -> ()", tts_destroy);
   m.def("tts_forward(int t, Tensor wave, Tensor? offsets, Tensor lengths, int hop, int n_mels) -> (Tensor, Tensor)", tts_forward);
   m.def("launch_count(int h) -> int", fe_launch_count);
+  m.def("select_kernel(int h, int which) -> ()", fe_select_kernel);
   m.def("profile_enable(int h, bool on) -> ()", fe_profile_enable);
   m.def("profile_collect(int h) -> (float, int)", fe_profile_collect);
 }

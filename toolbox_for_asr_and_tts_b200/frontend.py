@@ -113,13 +113,23 @@ class WavFrontend(nn.Module):
                 preemph=self.preemphasis_coefficient, remove_dc=self.remove_dc_offset, low_freq=self.low_freq,
                 high_freq=self.high_freq, blackman_coeff=self.blackman_coeff,
                 cmvn=self.cmvn if (cmvn and self.cmvn is not None) else None)
+            code = getattr(self, "_kernel_code", 0)
+            if code:
+                self._handles[key].ops.select_kernel(self._handles[key].h, code)
         return self._handles[key]
 
     def launch_count(self) -> int:
         return sum(int(h.ops.launch_count(h.h)) for h in self._handles.values())
 
+    def select_kernel(self, which: str) -> None:
+        """'auto' (warp-autonomous kernel whenever it applies) or 'tile' (the kernel that also does the statistics
+        pass): for A/B measurements and tests; results are identical."""
+        self._kernel_code = {"auto": 0, "tile": 1}[which]
+        for h in self._handles.values():
+            h.ops.select_kernel(h.h, self._kernel_code)
+
     def profile(self, on: bool) -> None:
-        """Bracket every launch of the fused tile kernel with CUDA events on its stream (bench.py roofline)."""
+        """Bracket every launch of the fused kernel with CUDA events on its stream (bench.py roofline)."""
         h = self._handle(lfr=True, cmvn=True)
         h.ops.profile_enable(h.h, bool(on))
 
