@@ -49,7 +49,7 @@ def main():
         rd = sum(mb(v) for v in vals["dram__bytes_read.sum"]) / len(data)
         wr = sum(mb(v) for v in vals["dram__bytes_write.sum"]) / len(data)
         json.dump({"dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr, "source": rep,
-                   "kernel": "fbank_lfr_cmvn_tile_kernel"}, open(sys.argv[3], "w"), indent=1)
+                   "kernel": data[0][name_i].split("<")[0].replace("void ", "")}, open(sys.argv[3], "w"), indent=1)
     print("\n".join(lines))
 
 
