@@ -234,6 +234,31 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = audio_s * world * e2e_steps / (e2e_ms * 1e-3)
     assert torch.equal(l2.cpu(), flens.cpu())
 
+    # ---------------- the same end-to-end loop on int16 PCM (the wire format upstream of the reference's front-end;
+    #                  SURVEY.md 8(f)2): reported beside `e2e`, never mixed into it
+    host16 = torch.empty(total + 8, dtype=torch.int16).pin_memory()
+    host16.copy_((wave.cpu() * 32768.0).round().clamp_(-32768, 32767).to(torch.int16))
+    stage16 = torch.empty(total + 8, dtype=torch.int16, device=dev)
+    for _ in range(2):
+        stage16.copy_(host16, non_blocking=True)
+        f3, l3 = fe.forward_packed(stage16, offs_t, lens_t)
+        lens_host.copy_(l3, non_blocking=True)
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        stage16.copy_(host16, non_blocking=True)
+        f3, l3 = fe.forward_packed(stage16, offs_t, lens_t)
+        lens_host.copy_(l3, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ev1.record()
+    barrier()
+    e2e16_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([e2e16_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e16_ms = float(t[0])
+    e2e16_value = audio_s * world * e2e_steps / (e2e16_ms * 1e-3)
+
     if rank != 0:
         return
     peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -292,6 +317,10 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(lens_host.numel() * 8), "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps,
                     "note": "features stay in HBM for the acoustic model; only feature lengths return to the host"},
+            "e2e_pcm16": {"value": e2e16_value, "unit": UNIT, "h2d_bytes_per_step": int(host16.numel() * 2),
+                          "d2h_bytes_per_step": int(lens_host.numel() * 8), "ms_per_step": e2e16_ms / e2e_steps,
+                          "note": "side measurement: int16 PCM in, converted inside the kernel's loads (bit-identical "
+                                  "features); the headline e2e above takes the reference's float32 input"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu}

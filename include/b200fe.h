@@ -112,6 +112,16 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total,
                    float* feats_dev, int64_t rows_cap, int64_t* feat_lens_dev, double* stats_dev,
                    uint64_t dither_seed, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Same as b200fe_forward for int16 PCM that is still in its wire format: sample value = s / 32768, the conversion the
+ * reference applies on the host before it reaches the front-end (base64_to_audio_np, R:voice-service/app/services/
+ * voice_interface.py:1008-1013).  Fused into the kernel's sample loads: half the HBM and PCIe bytes per audio-second
+ * (69 333 B instead of 101 333 B algorithmic), results bit-identical to converting first and calling b200fe_forward.
+ * wave_total counts int16 elements.  No statistics pass (use the float entry point for that). */
+int b200fe_forward_pcm16(b200fe_handle* h, const int16_t* wave_dev, int64_t wave_total,
+                         const int64_t* offsets_host, int64_t row_stride, const int64_t* lengths_host, int batch,
+                         float* feats_dev, int64_t rows_cap, int64_t* feat_lens_dev, uint64_t dither_seed,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Replaces WavFrontend.forward_lfr_cmvn (VF:198-218): LFR + CMVN of given [batch, frames_cap, n_mels] features. */
 int b200fe_lfr_cmvn(b200fe_handle* h, const float* fbank_dev, int64_t frames_cap, const int64_t* n_frames_host,
                     int batch, float* feats_dev, int64_t rows_cap, int64_t* feat_lens_dev, void* workspace_dev,

@@ -481,3 +481,35 @@ def test_fsmn_vad_frontend_configuration():
     cat = torch.cat(outs)
     assert cat.shape[0] == 298
     assert_feats_close(cat, feats[0], cm)
+
+
+def test_pcm16_input_is_bit_identical_to_converted_float(cmvn):
+    """int16 PCM in its wire format, converted inside the kernel's loads with the reference's rule
+    s / 32768 (R:voice_interface.py:1008-1013), must give exactly what the float path gives for the converted buffer:
+    dense and length-packed with odd offsets, including an utterance shorter than one frame."""
+    fe = make_fe(cmvn)
+    rng = np.random.default_rng(16)
+    lens = np.array([4001, 16003, 399, 7777, 32000, 401, 1601], dtype=np.int64)
+    ints = [rng.integers(-20000, 20000, size=int(n), dtype=np.int16) for n in lens]
+    floats = [w.astype(np.float32) / np.float32(32768.0) for w in ints]
+    nmax = int(lens.max())
+    xi = torch.zeros(len(lens), nmax, dtype=torch.int16)
+    for i, w in enumerate(ints):
+        xi[i, :len(w)] = torch.from_numpy(w)
+    ref_f, ref_l = fe(dense_batch(floats), lens.tolist())
+    got, gl = fe(xi.to(DEV), lens.tolist())
+    assert got.dtype == torch.float32 and torch.equal(gl, ref_l) and torch.equal(got, ref_f)
+    for lead in (0, 1, 3, 5):
+        offs, total = synth.packed_offsets(lens, align=1)
+        offs = offs + lead
+        flat = torch.zeros(int(total) + lead + 16, dtype=torch.int16)
+        for o, w in zip(offs, ints):
+            flat[o:o + len(w)] = torch.from_numpy(w)
+        p, pl = fe.forward_packed(flat.to(DEV), offs, lens)
+        assert torch.equal(pl, ref_l) and torch.equal(p, ref_f), lead
+    oracle, ol = wf.frontend_forward(floats, lens, cmvn=cmvn, **PARAFORMER)
+    assert np.array_equal(gl.cpu().numpy(), ol)
+    for i, k in enumerate(ol):
+        assert_feats_close(got[i, :k], oracle[i, :k], cmvn)
+    with pytest.raises(RuntimeError, match="statistics pass takes float32"):
+        fe.forward_packed(flat.to(DEV), offs, lens, stats=torch.zeros(1121, dtype=torch.float64, device=DEV))

@@ -164,6 +164,12 @@ __global__ void build_tiles_kernel(const UttDesc* utts, int batch, int n_tiles, 
   tiles[t] = d;
 }
 
+// int16 PCM -> float32 with the reference's rule s / 32768 (R:voice_interface.py:1008-1013); used for the few samples
+// of utterances shorter than one frame when the batch arrives as int16.
+__global__ void pcm16_to_float_kernel(const short* src, int n, float* dst) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (float)src[i] * (1.0f / 32768.0f);
+}
+
 // Expands the per-utterance descriptors into the launch-wide quad list of the warp kernel: quad q of utterance u covers
 // frames 4 (q - quad_begin[u]) .. +3.  One thread per quad; utterances without frames own no quads.
 __global__ void build_quads_kernel(const UttDesc* utts, int batch, int n_quads, int S, int lfr_m, int lfr_n, int M,

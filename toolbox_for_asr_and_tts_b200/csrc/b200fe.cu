@@ -260,9 +260,11 @@ int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, 
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // the tile list (statistics pass) and the quad list (warp kernel) share one region: a launch uses one of them
-size_t workspace_need(int batch, int n_tiles = 0, int n_quads = 0) {
+// then 512 floats per utterance shorter than one frame (scratch for int16 input: the short path reads float32)
+size_t workspace_need(int batch, int n_tiles = 0, int n_quads = 0, int n_short = 0) {
   const size_t lists = std::max((size_t)n_tiles * sizeof(TileDesc), (size_t)n_quads * sizeof(QuadDesc));
-  return align256((size_t)batch * sizeof(UttDesc)) + align256((size_t)batch * sizeof(ShortDesc)) + align256(lists);
+  return align256((size_t)batch * sizeof(UttDesc)) + align256((size_t)batch * sizeof(ShortDesc)) + align256(lists) +
+         align256((size_t)n_short * 512 * sizeof(float));
 }
 
 // stream-ordered upload through a small ring of pinned buffers
@@ -316,12 +318,12 @@ int launch_tile(b200fe_handle* h, const TileParams& p, int grid, bool dither, bo
   return 0;
 }
 
-template <int NROWS, bool EXACT, class MELS, int SR>
+template <int NROWS, bool EXACT, class MELS, int SR, class SampleT>
 int launch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cudaStream_t st) {
   const size_t smem = warp_smem_bytes();
 #define LAUNCHW(DI)                                                                                   \
   do {                                                                                                \
-    auto k = fbank_warp_kernel<NROWS, EXACT, DI, MELS, SR>;                                             \
+    auto k = fbank_warp_kernel<NROWS, EXACT, DI, MELS, SR, SampleT>;                                             \
     CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     k<<<grid, kCtaThreads, smem, st>>>(p);                                                            \
   } while (0)
@@ -563,14 +565,28 @@ int b200fe_plan(b200fe_handle* h, const int64_t* lengths_host, int batch, int64_
     if (n_rows_out) n_rows_out[u] = pl.utts[u].n_rows;
   }
   if (max_rows_out) *max_rows_out = pl.max_rows;
-  if (workspace_bytes) *workspace_bytes = workspace_need(batch, pl.n_tiles, pl.n_quads);
+  if (workspace_bytes) *workspace_bytes = workspace_need(batch, pl.n_tiles, pl.n_quads, (int)pl.shorts.size());
   return B200FE_OK;
 }
 
-int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, const int64_t* offsets_host,
-                   int64_t row_stride, const int64_t* lengths_host, int batch, float* feats_dev, int64_t rows_cap,
-                   int64_t* feat_lens_dev, double* stats_dev, uint64_t dither_seed, void* workspace_dev,
-                   size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+namespace {
+
+template <class SampleT>
+int dispatch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cudaStream_t st) {
+  if (h->L == 400 && h->S == 160 && h->mel_paraformer) return launch_warp<25, true, MelShapeParaformer, 10, SampleT>(h, p, grid, dither, st);
+  if (h->L == 400 && h->S == 160) return launch_warp<25, true, MelShapeRuntime, 10, SampleT>(h, p, grid, dither, st);
+  if (h->L == 400) return launch_warp<25, true, MelShapeRuntime, 0, SampleT>(h, p, grid, dither, st);
+  return launch_warp<32, false, MelShapeRuntime, 0, SampleT>(h, p, grid, dither, st);
+}
+
+// b200fe_forward / b200fe_forward_pcm16.  pcm16: `wave_dev` is int16 PCM, sample value = s / 32768.
+int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wave_total, const int64_t* offsets_host,
+                 int64_t row_stride, const int64_t* lengths_host, int batch, float* feats_dev, int64_t rows_cap,
+                 int64_t* feat_lens_dev, double* stats_dev, uint64_t dither_seed, void* workspace_dev,
+                 size_t workspace_bytes, void* stream) {
+  const float* wave_dev = static_cast<const float*>(wave_any);   // only dereferenced when !pcm16
   if (!h) return B200FE_E_INVALID;
   if (batch == 0) return B200FE_OK;
   if (!wave_dev || !lengths_host || !feats_dev || !workspace_dev || batch < 0)
@@ -580,7 +596,7 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
   Plan pl;
   int rc = make_plan(h, lengths_host, offsets_host, row_stride, batch, pl);
   if (rc) return rc;
-  if (workspace_bytes < workspace_need(batch, pl.n_tiles, pl.n_quads)) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
+  if (workspace_bytes < workspace_need(batch, pl.n_tiles, pl.n_quads, (int)pl.shorts.size())) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
   if (pl.max_rows > rows_cap) return fail(h, B200FE_E_INVALID, "rows_cap smaller than the longest utterance's row count");
   for (int u = 0; u < batch; ++u) {
     const long long end = pl.utts[u].wave_off + lengths_host[u];
@@ -592,8 +608,11 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
   QuadDesc* d_quads = reinterpret_cast<QuadDesc*>(d_tiles);   // same region: a launch uses one of the two lists
   if ((rc = upload(h, pl.utts.data(), (size_t)batch * sizeof(UttDesc), d_utts, st))) return rc;
   // the warp kernel does everything except the CMVN statistics (which need the row-major tile pass)
-  const bool use_warp = stats_dev == nullptr && warp_kernel_fits(h->L, h->S) && !h->force_tile &&
+  const bool use_warp = stats_dev == nullptr && warp_kernel_fits(h->L, h->S) && (!h->force_tile || pcm16) &&
                         pl.max_rows * (long long)h->D < (1ll << kTargetOffBits) - 1;
+  if (pcm16 && !use_warp)
+    return fail(h, B200FE_E_UNSUPPORTED, "int16 input is implemented in the warp kernel only (no statistics pass, "
+                                         "frame shifts whose quad fits its buffer)");
   if (use_warp && pl.n_quads > 0) {
     build_quads_kernel<<<(pl.n_quads + 255) / 256, 256, 0, st>>>(d_utts, batch, pl.n_quads, h->S, h->cfg.lfr_m,
                                                                  h->cfg.lfr_n, h->cfg.n_mels, d_quads);
@@ -618,7 +637,7 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
   // 2. the fused kernel over all regular utterances: warp kernel, or tile kernel for the statistics pass
   if (use_warp && pl.n_quads > 0) {
     QuadParams p;
-    p.wave = wave_dev; p.wave_total = wave_total; p.quads = d_quads; p.n_quads = pl.n_quads;
+    p.wave = wave_any; p.wave_total = wave_total; p.quads = d_quads; p.n_quads = pl.n_quads;
     p.feats = feats_dev; p.rows_cap = rows_cap;
     p.frame_len = h->L; p.frame_shift = h->S; p.n_mels = h->cfg.n_mels; p.lfr_m = h->cfg.lfr_m; p.lfr_n = h->cfg.lfr_n;
     p.preemph = h->cfg.preemphasis; p.remove_dc = h->cfg.remove_dc_offset; p.log_floor = h->cfg.log_floor;
@@ -630,10 +649,7 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
     const int ctas = (pl.n_quads + kWarps - 1) / kWarps;
     const int grid = ctas < 4 * h->n_sms ? ctas : 4 * h->n_sms;
     const bool dither = h->cfg.dither != 0.f;
-    if (h->L == 400 && h->S == 160 && h->mel_paraformer) rc = launch_warp<25, true, MelShapeParaformer, 10>(h, p, grid, dither, st);
-    else if (h->L == 400 && h->S == 160) rc = launch_warp<25, true, MelShapeRuntime, 10>(h, p, grid, dither, st);
-    else if (h->L == 400) rc = launch_warp<25, true, MelShapeRuntime, 0>(h, p, grid, dither, st);
-    else rc = launch_warp<32, false, MelShapeRuntime, 0>(h, p, grid, dither, st);
+    rc = pcm16 ? dispatch_warp<short>(h, p, grid, dither, st) : dispatch_warp<float>(h, p, grid, dither, st);
     if (rc) return rc;
   } else if (pl.n_tiles > 0) {
     TileParams p;
@@ -658,9 +674,25 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
   if (!pl.shorts.empty()) {
     if (h->cfg.dither != 0.f) return fail(h, B200FE_E_UNSUPPORTED, "dither on utterances shorter than one frame");
     if ((rc = ensure_short_banks(h, pl, st))) return rc;
-    if ((rc = upload(h, pl.shorts.data(), pl.shorts.size() * sizeof(ShortDesc), d_shorts, st))) return rc;
+    const float* short_wave = wave_dev;
+    if (pcm16) {   // the short path reads float32: convert those few samples into the workspace scratch
+      float* scratch = reinterpret_cast<float*>((char*)d_tiles + align256(std::max((size_t)pl.n_tiles * sizeof(TileDesc),
+                                                                                 (size_t)pl.n_quads * sizeof(QuadDesc))));
+      std::vector<long long> src_off(pl.shorts.size());
+      for (size_t k = 0; k < pl.shorts.size(); ++k) { src_off[k] = pl.shorts[k].wave_off; pl.shorts[k].wave_off = (long long)k * 512; }
+      if ((rc = upload(h, pl.shorts.data(), pl.shorts.size() * sizeof(ShortDesc), d_shorts, st))) return rc;
+      for (size_t k = 0; k < pl.shorts.size(); ++k) {
+        pcm16_to_float_kernel<<<1, 256, 0, st>>>(static_cast<const short*>(wave_any) + src_off[k], pl.shorts[k].n_samples,
+                                                 scratch + k * 512);
+        h->launches++;
+      }
+      CUDA_TRY(h, cudaGetLastError());
+      short_wave = scratch;
+    } else if ((rc = upload(h, pl.shorts.data(), pl.shorts.size() * sizeof(ShortDesc), d_shorts, st))) {
+      return rc;
+    }
     short_utt_kernel<<<(int)pl.shorts.size(), 256, 0, st>>>(
-        wave_dev, d_shorts, h->d_short_mel, h->S, h->cfg.n_mels, h->cfg.lfr_m, h->cfg.lfr_n, h->cfg.window_type,
+        short_wave, d_shorts, h->d_short_mel, h->S, h->cfg.n_mels, h->cfg.lfr_m, h->cfg.lfr_n, h->cfg.window_type,
         h->cfg.blackman_coeff, h->cfg.preemphasis, h->cfg.remove_dc_offset, h->cfg.upscale_samples ? 32768.f : 1.f,
         h->cfg.log_floor, h->d_cmvn, feats_dev, rows_cap);
     CUDA_TRY(h, cudaGetLastError());
@@ -672,6 +704,26 @@ int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, 
     h->launches++;
   }
   return B200FE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200fe_forward(b200fe_handle* h, const float* wave_dev, int64_t wave_total, const int64_t* offsets_host,
+                   int64_t row_stride, const int64_t* lengths_host, int batch, float* feats_dev, int64_t rows_cap,
+                   int64_t* feat_lens_dev, double* stats_dev, uint64_t dither_seed, void* workspace_dev,
+                   size_t workspace_bytes, void* stream) {
+  return forward_impl(h, wave_dev, false, wave_total, offsets_host, row_stride, lengths_host, batch, feats_dev, rows_cap,
+                      feat_lens_dev, stats_dev, dither_seed, workspace_dev, workspace_bytes, stream);
+}
+
+int b200fe_forward_pcm16(b200fe_handle* h, const int16_t* wave_dev, int64_t wave_total, const int64_t* offsets_host,
+                         int64_t row_stride, const int64_t* lengths_host, int batch, float* feats_dev, int64_t rows_cap,
+                         int64_t* feat_lens_dev, uint64_t dither_seed, void* workspace_dev, size_t workspace_bytes,
+                         void* stream) {
+  return forward_impl(h, wave_dev, true, wave_total, offsets_host, row_stride, lengths_host, batch, feats_dev, rows_cap,
+                      feat_lens_dev, nullptr, dither_seed, workspace_dev, workspace_bytes, stream);
 }
 
 int b200fe_lfr_cmvn(b200fe_handle* h, const float* fbank_dev, int64_t frames_cap, const int64_t* n_frames_host, int batch,

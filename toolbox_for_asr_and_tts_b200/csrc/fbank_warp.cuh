@@ -40,8 +40,8 @@ struct __align__(16) QuadDesc {
 };
 
 struct QuadParams {
-  const float* wave;
-  long long wave_total;
+  const void* wave;       // float32 PCM in [-1, 1] or int16 PCM (sample / 32768, R:voice_interface.py:1008-1013)
+  long long wave_total;   // samples addressable behind `wave`
   const QuadDesc* quads;
   int n_quads;
   float* feats;           // [batch, rows_cap, out_dim]
@@ -83,17 +83,33 @@ __host__ __device__ inline bool quad_targets(int f, int T, int rows, int lfr_m, 
   return false;
 }
 
-// Raw samples of a quad -> registers, on the 16-byte grid of the wave buffer (vector v holds samples 4v - a_off ..
-// of the quad's first frame), plus the raw first / last sample of every frame in lanes 0..3 / 4..7.
-__device__ __forceinline__ void quad_load(const QuadParams& p, long long g0, int nF, unsigned wave_mis, int lane,
-                                          float4 (&x)[kQuadVecs], float& cap) {
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// Samples of a quad: HBM/L2 -> registers (128-bit streaming loads on the 16-byte grid of the wave buffer; the samples
+// must not evict the mel / CMVN tables from the few KB of L1 left beside 4 CTAs) -> pre-emphasis -> the warp's buffer:
+// buf[a_off + n] = x[n] - preemph * x[n-1] for sample n of the quad's first frame (the predecessor of a vector's first
+// sample comes from the previous lane through one shuffle).  Also returns the raw first / last sample of the group's
+// two frames (x0 / xl, for the DC correction), read by lanes 0..7 and shuffled.  Quads touching the ends of the wave
+// buffer load element-wise.  Returns a_off.
+template <class SampleT>
+__device__ __forceinline__ int quad_samples(const QuadParams& p, long long g0, int nF, int lane, int grp_in_warp,
+                                            float* buf, f2& x0, f2& xl);
+
+template <>
+__device__ __forceinline__ int quad_samples<float>(const QuadParams& p, long long g0, int nF, int lane, int grp_in_warp,
+                                                   float* buf, f2& x0, f2& xl) {
+  const float* wave = static_cast<const float*>(p.wave);
+  const unsigned wave_mis = (unsigned)((reinterpret_cast<uintptr_t>(wave) >> 2) & 3);
   const int a_off = (int)((wave_mis + (unsigned)(g0 & 3)) & 3);
   const long long ga = g0 - a_off;
   const int nv = (a_off + (nF - 1) * p.frame_shift + p.frame_len + 3) >> 2;
-  const bool interior = ga >= 0 && ga + 4ll * nv <= p.wave_total;
-  if (interior) {
-    // streaming loads: the samples must not evict the mel / CMVN tables from the few KB of L1 left beside 4 CTAs
-    const float* src = p.wave + ga + 4 * lane;
+  float4 x[kQuadVecs];
+  if (ga >= 0 && ga + 4ll * nv <= p.wave_total) {
+    const float* src = wave + ga + 4 * lane;
 #pragma unroll
     for (int u = 0; u < kQuadVecs; ++u)
       x[u] = lane + 32 * u < nv ? ldg_stream4(src + 128 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -103,21 +119,110 @@ __device__ __forceinline__ void quad_load(const QuadParams& p, long long g0, int
       const long long ab = ga + 4ll * (lane + 32 * u);
       x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (lane + 32 * u < nv) {
-        if (ab >= 0 && ab < p.wave_total) x[u].x = p.wave[ab];
-        if (ab + 1 >= 0 && ab + 1 < p.wave_total) x[u].y = p.wave[ab + 1];
-        if (ab + 2 >= 0 && ab + 2 < p.wave_total) x[u].z = p.wave[ab + 2];
-        if (ab + 3 >= 0 && ab + 3 < p.wave_total) x[u].w = p.wave[ab + 3];
+        if (ab >= 0 && ab < p.wave_total) x[u].x = wave[ab];
+        if (ab + 1 >= 0 && ab + 1 < p.wave_total) x[u].y = wave[ab + 1];
+        if (ab + 2 >= 0 && ab + 2 < p.wave_total) x[u].z = wave[ab + 2];
+        if (ab + 3 >= 0 && ab + 3 < p.wave_total) x[u].w = wave[ab + 3];
       }
     }
   }
-  cap = 0.f;
+  float cap = 0.f;
   if (lane < 8 && (lane & 3) < nF)
-    cap = __ldg(p.wave + g0 + (long long)(lane & 3) * p.frame_shift + (lane < 4 ? 0 : p.frame_len - 1));
+    cap = __ldg(wave + g0 + (long long)(lane & 3) * p.frame_shift + (lane < 4 ? 0 : p.frame_len - 1));
+  float4* buf4 = reinterpret_cast<float4*>(buf);
+  float below = 0.f;   // lane 31's last sample of the previous vector row (lane 0's predecessor)
+#pragma unroll
+  for (int u = 0; u < kQuadVecs; ++u) {
+    const float rot = __shfl_sync(0xffffffffu, x[u].w, (lane + 31) & 31);
+    const float pv = lane == 0 ? below : rot;
+    below = rot;   // only lane 0 uses it: there rot is lane 31's value
+    if (lane + 32 * u < nv) {
+      float4 e;
+      e.x = fmaf(-p.preemph, pv, x[u].x);
+      e.y = fmaf(-p.preemph, x[u].x, x[u].y);
+      e.z = fmaf(-p.preemph, x[u].y, x[u].z);
+      e.w = fmaf(-p.preemph, x[u].z, x[u].w);
+      buf4[lane + 32 * u] = e;
+    }
+  }
+  const int fa = 2 * grp_in_warp;
+  x0.x = __shfl_sync(0xffffffffu, cap, fa);
+  x0.y = __shfl_sync(0xffffffffu, cap, fa + 1);
+  xl.x = __shfl_sync(0xffffffffu, cap, fa + 4);
+  xl.y = __shfl_sync(0xffffffffu, cap, fa + 5);
+  return a_off;
+}
+
+// int16 PCM: 8 samples per 16-byte vector, converted with the reference's own rule float(s) / 32768 (exact), so the
+// result is bit-identical to handing the converted float32 buffer to the float path - at half the HBM / PCIe bytes.
+constexpr int kQuadVecs16 = 4;
+template <>
+__device__ __forceinline__ int quad_samples<short>(const QuadParams& p, long long g0, int nF, int lane, int grp_in_warp,
+                                                   float* buf, f2& x0, f2& xl) {
+  const short* wave = static_cast<const short*>(p.wave);
+  const unsigned wave_mis = (unsigned)((reinterpret_cast<uintptr_t>(wave) >> 1) & 7);
+  const int a_off = (int)((wave_mis + (unsigned)(g0 & 7)) & 7);
+  const long long ga = g0 - a_off;
+  const int nv = (a_off + (nF - 1) * p.frame_shift + p.frame_len + 7) >> 3;
+  constexpr float kScale = 1.0f / 32768.0f;
+  float x[kQuadVecs16][8];
+  if (ga >= 0 && ga + 8ll * nv <= p.wave_total) {
+    const short* src = wave + ga + 8 * lane;
+#pragma unroll
+    for (int u = 0; u < kQuadVecs16; ++u) {
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      if (lane + 32 * u < nv) r = ldg_stream_u4(src + 256 * u);
+      const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        x[u][2 * k] = (float)(short)(w[k] & 0xffffu) * kScale;
+        x[u][2 * k + 1] = (float)(short)(w[k] >> 16) * kScale;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < kQuadVecs16; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long long ab = ga + 8ll * (lane + 32 * u) + k;
+        x[u][k] = (lane + 32 * u < nv && ab >= 0 && ab < p.wave_total) ? (float)wave[ab] * kScale : 0.f;
+      }
+  }
+  float cap = 0.f;
+  if (lane < 8 && (lane & 3) < nF)
+    cap = (float)wave[g0 + (long long)(lane & 3) * p.frame_shift + (lane < 4 ? 0 : p.frame_len - 1)] * kScale;
+  float4* buf4 = reinterpret_cast<float4*>(buf);
+  float below = 0.f;
+#pragma unroll
+  for (int u = 0; u < kQuadVecs16; ++u) {
+    const float rot = __shfl_sync(0xffffffffu, x[u][7], (lane + 31) & 31);
+    const float pv = lane == 0 ? below : rot;
+    below = rot;
+    if (lane + 32 * u < nv) {
+      float4 e0, e1;
+      e0.x = fmaf(-p.preemph, pv, x[u][0]);
+      e0.y = fmaf(-p.preemph, x[u][0], x[u][1]);
+      e0.z = fmaf(-p.preemph, x[u][1], x[u][2]);
+      e0.w = fmaf(-p.preemph, x[u][2], x[u][3]);
+      e1.x = fmaf(-p.preemph, x[u][3], x[u][4]);
+      e1.y = fmaf(-p.preemph, x[u][4], x[u][5]);
+      e1.z = fmaf(-p.preemph, x[u][5], x[u][6]);
+      e1.w = fmaf(-p.preemph, x[u][6], x[u][7]);
+      buf4[2 * (lane + 32 * u)] = e0;
+      buf4[2 * (lane + 32 * u) + 1] = e1;
+    }
+  }
+  const int fa = 2 * grp_in_warp;
+  x0.x = __shfl_sync(0xffffffffu, cap, fa);
+  x0.y = __shfl_sync(0xffffffffu, cap, fa + 1);
+  xl.x = __shfl_sync(0xffffffffu, cap, fa + 4);
+  xl.y = __shfl_sync(0xffffffffu, cap, fa + 5);
+  return a_off;
 }
 
 // SR: frame shift in 16-sample rows when it is a whole number of rows and known at compile time (10 for 400/160):
 // the two frames of a pair then share their overlapping sample loads.  0 = generic.
-template <int NROWS, bool EXACT, bool DITHER, class MELS, int SR>
+template <int NROWS, bool EXACT, bool DITHER, class MELS, int SR, class SampleT>
 __global__ void __launch_bounds__(kCtaThreads, 4)
 fbank_warp_kernel(const QuadParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -146,13 +251,11 @@ fbank_warp_kernel(const QuadParams p) {
   __syncthreads();   // the only CTA-wide barrier: the twiddle tables
 
   float* buf = bufs + warp * kQuadBuf;
-  float4* buf4 = reinterpret_cast<float4*>(buf);
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;
   float4* pbuf4 = xbuf + warp * kYWarpF4;
   float* lm_s = reinterpret_cast<float*>(pbuf4 + 256);   // log-mel staging tile, behind the warp's spectra
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
   const float2* c0_row = tw_s + 2 * kTw2Table + (j & 7) * kC0Pitch;
-  const unsigned wave_mis = (unsigned)((reinterpret_cast<uintptr_t>(p.wave) >> 2) & 3);
   const int M4 = M >> 2;
   const bool act = lane < M4;      // lanes that move a float4 of a log-mel row (n_mels <= 128)
 
@@ -178,39 +281,12 @@ fbank_warp_kernel(const QuadParams p) {
     const int4 hd1 = __ldg(reinterpret_cast<const int4*>(p.quads + q) + 1);   // nF | slow << 8, T, rows, pad
     const int utt = hd.z, f0 = hd.w;
     const int nF = nf_cur & 0xff, slow = (nf_cur >> 8) & 0xf, T = hd1.y, rows = hd1.z;
-    const int a_off = (int)((wave_mis + (unsigned)(g0_cur & 3)) & 3);
-    const int nv = (a_off + (nF - 1) * S + L + 3) >> 2;
 
-    // ---- this quad's samples: HBM -> L2 was started a whole quad ago (prefetch below), so these loads hit L2
-    float4 x[kQuadVecs];
-    float cap;
-    quad_load(p, g0_cur, nF, wave_mis, lane, x, cap);
-
-    // ---- pre-emphasis on the way from registers to the warp's buffer: buf[a_off + n] = x[n] - preemph * x[n-1]
+    // ---- this quad's samples: HBM -> L2 was started a whole quad ago (prefetch below), so these loads hit L2;
+    //      pre-emphasis on the way from registers to the warp's buffer
     f2 x0, xl;
-    {
-      float below = 0.f;   // lane 31's last sample of the previous vector row (lane 0's predecessor)
-#pragma unroll
-      for (int u = 0; u < kQuadVecs; ++u) {
-        const float rot = __shfl_sync(0xffffffffu, x[u].w, (lane + 31) & 31);
-        const float pv = lane == 0 ? below : rot;
-        below = rot;   // only lane 0 uses it: there rot is lane 31's value
-        if (lane + 32 * u < nv) {
-          float4 e;
-          e.x = fmaf(-p.preemph, pv, x[u].x);
-          e.y = fmaf(-p.preemph, x[u].x, x[u].y);
-          e.z = fmaf(-p.preemph, x[u].y, x[u].z);
-          e.w = fmaf(-p.preemph, x[u].z, x[u].w);
-          buf4[lane + 32 * u] = e;
-        }
-      }
-      const int fa = 2 * grp_in_warp;
-      x0.x = __shfl_sync(0xffffffffu, cap, fa);
-      x0.y = __shfl_sync(0xffffffffu, cap, fa + 1);
-      xl.x = __shfl_sync(0xffffffffu, cap, fa + 4);
-      xl.y = __shfl_sync(0xffffffffu, cap, fa + 5);
-      __syncwarp();
-    }
+    const int a_off = quad_samples<SampleT>(p, g0_cur, nF, lane, grp_in_warp, buf, x0, xl);
+    __syncwarp();
 
     // ---- stage 1 (samples -> registers -> real 32-point FFT) and stage 2 (transpose, 16-point FFT, power spectra)
     const int fA = 2 * grp_in_warp;
@@ -225,9 +301,12 @@ fbank_warp_kernel(const QuadParams p) {
 
     // ---- the next quad's samples start their way from HBM to L2 now (one 128-byte line per lane)
     if (have_next) {
-      const long long line0 = (g0_next - 3) & ~31ll;   // 128-byte lines covering the aligned load grid
-      const long long idx = line0 + 32ll * lane;
-      if (idx >= 0 && idx < g0_next + 3 * S + L && idx < p.wave_total) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wave + idx));
+      const char* base = static_cast<const char*>(p.wave);
+      const long long first = (g0_next * (long long)sizeof(SampleT) - 16) & ~127ll;
+      const long long idx = first + 128ll * lane;
+      const long long last = (g0_next + 3 * S + L) * (long long)sizeof(SampleT);
+      if (idx >= 0 && idx < last && idx < p.wave_total * (long long)sizeof(SampleT))
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + idx));
     }
     const uint4 tg0 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 2);   // targets of frames 0, 1
     const uint4 tg1 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 3);   // targets of frames 2, 3

@@ -75,12 +75,14 @@ std::tuple<at::Tensor, at::Tensor> fe_plan(int64_t h, const at::Tensor& lengths)
   return {nf, nr};
 }
 
-// wave: CUDA float32, either [B, Nmax] (offsets undefined) or a flat length-packed buffer with host offsets.
+// wave: CUDA float32 (or int16 PCM, value = s / 32768), either [B, Nmax] (offsets undefined) or a flat length-packed
+// buffer with host offsets.
 std::tuple<at::Tensor, at::Tensor> fe_forward(int64_t h, const at::Tensor& wave, const c10::optional<at::Tensor>& offsets,
                                               const at::Tensor& lengths, int64_t rows_cap,
                                               const c10::optional<at::Tensor>& stats, int64_t seed) {
   TORCH_CHECK(wave.is_cuda(), "b200fe.forward: waveform must be a CUDA tensor (there is no CPU fallback)");
-  TORCH_CHECK(wave.scalar_type() == at::kFloat, "b200fe.forward: waveform must be float32");
+  const bool pcm16 = wave.scalar_type() == at::kShort;
+  TORCH_CHECK(pcm16 || wave.scalar_type() == at::kFloat, "b200fe.forward: waveform must be float32 or int16");
   c10::cuda::CUDAGuard guard(wave.device());
   auto w = wave.contiguous();
   auto len = lengths.to(at::kCPU, at::kLong).contiguous();
@@ -101,7 +103,7 @@ std::tuple<at::Tensor, at::Tensor> fe_forward(int64_t h, const at::Tensor& wave,
   check(b200fe_plan(H(h), len.data_ptr<int64_t>(), b, nullptr, nullptr, &max_rows, &ws), H(h), "b200fe_plan");
   if (rows_cap <= 0) rows_cap = max_rows;
   const int64_t d = b200fe_output_dim(H(h));
-  auto opts = w.options();
+  auto opts = w.options().dtype(at::kFloat);
   auto feats = at::empty({b, rows_cap, d}, opts);
   auto lens = at::empty({b}, opts.dtype(at::kLong));
   auto work = at::empty({(int64_t)(ws ? ws : 256)}, opts.dtype(at::kByte));
@@ -110,6 +112,14 @@ std::tuple<at::Tensor, at::Tensor> fe_forward(int64_t h, const at::Tensor& wave,
     TORCH_CHECK(stats->is_cuda() && stats->scalar_type() == at::kDouble && stats->is_contiguous() &&
                     stats->numel() == 2 * d + 1, "stats must be a contiguous CUDA float64 [2*D+1] tensor");
     st = stats->data_ptr<double>();
+  }
+  if (pcm16) {
+    TORCH_CHECK(st == nullptr, "b200fe.forward: the statistics pass takes float32 input");
+    check(b200fe_forward_pcm16(H(h), w.data_ptr<int16_t>(), w.numel(), off_ptr, row_stride, len.data_ptr<int64_t>(), b,
+                               feats.data_ptr<float>(), rows_cap, lens.data_ptr<int64_t>(), (uint64_t)seed, work.data_ptr(),
+                               (size_t)work.numel(), cur_stream()),
+          H(h), "b200fe_forward_pcm16");
+    return {feats, lens};
   }
   check(b200fe_forward(H(h), w.data_ptr<float>(), w.numel(), off_ptr, row_stride, len.data_ptr<int64_t>(), b,
                        feats.data_ptr<float>(), rows_cap, lens.data_ptr<int64_t>(), st, (uint64_t)seed, work.data_ptr(),
