@@ -156,6 +156,22 @@ int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total,
                        const int64_t* lengths_dev, int batch, int64_t max_frames, float* mel_dev, int64_t frames_cap,
                        int64_t* mel_lens_dev, void* stream);
 
+/* ---- by-products the reference computes on the host around its funasr calls.
+ * b200fe_audio_stats replaces _log_audio_statistics and the per-chunk energy gate (R:voice-service/app/services/
+ * voice_interface.py:873-939, 1298-1300, 1569-1570) for a whole ragged batch: out_dev is float64 [batch, 6] =
+ * {max, min, mean |x|, rms = sqrt(mean x^2), clipping ratio = fraction with |x| >= clip_level (0.999 upstream), max |x|}.
+ * offsets_dev / lengths_dev are int64 DEVICE arrays (offsets_dev NULL = dense [batch, row_stride]); max_length sizes the
+ * launch; the workspace holds the per-utterance accumulators. */
+size_t b200fe_audio_stats_workspace(int batch);
+int b200fe_audio_stats(const float* wave_dev, const int64_t* offsets_dev, int64_t row_stride, const int64_t* lengths_dev,
+                       int batch, int64_t max_length, float clip_level, double* out_dev, void* workspace_dev,
+                       size_t workspace_bytes, void* stream);
+/* Kaldi subtract_mean (TA:642-644, _subtract_column_mean), i.e. the utterance mean normalisation of the CAM++
+ * speaker-verification features (R:voice_interface.py:2430,2520,2558), in place on [batch, rows_cap, dim] features:
+ * feats[u, t, :] -= mean over t < n_rows[u]. */
+int b200fe_subtract_column_mean(float* feats_dev, int64_t rows_cap, int dim, const int64_t* n_rows_dev, int batch,
+                                void* stream);
+
 /* ---- bench / test support: counter-based synthetic PCM, identical to synth.py on the host.
  * x[u][n] = amp * (2*U01(hash(seed,u,n)) - 1) written at wave_dev[offsets_dev[u] + n], n < lengths_dev[u]. */
 int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int64_t* lengths_dev, int batch,

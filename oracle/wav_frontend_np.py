@@ -224,3 +224,20 @@ def stats_to_cmvn(s: np.ndarray, s2: np.ndarray, n: int) -> np.ndarray:
     mean = s / n
     var = s2 / n - mean * mean
     return np.stack([-mean, 1.0 / np.sqrt(var)]).astype(np.float32)
+
+
+# --------------------------------------------------------------------------- host-side by-products of the reference
+def audio_statistics(audio: np.ndarray, clip_level: float = 0.999) -> np.ndarray:
+    """R:voice-service/app/services/voice_interface.py:873-939 (_log_audio_statistics), the fields a consumer gates on:
+    [max, min, mean |x| (:1298, :1569), rms (:897, without its +1e-10), clipping ratio (:900-901), max |x| (:894)]."""
+    a = np.asarray(audio)
+    if a.size == 0:
+        return np.zeros(6)
+    a64 = a.astype(np.float64)
+    return np.array([a64.max(), a64.min(), np.abs(a64).mean(), np.sqrt((a64 ** 2).mean()),
+                     float((np.abs(a) >= np.float32(clip_level)).sum()) / a.size, np.abs(a64).max()])
+
+
+def subtract_column_mean(feats: np.ndarray) -> np.ndarray:
+    """TA:642-644 (_subtract_column_mean): mean over frames, per mel bin."""
+    return (feats - feats.mean(axis=0, keepdims=True)).astype(feats.dtype)

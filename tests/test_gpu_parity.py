@@ -513,3 +513,56 @@ def test_pcm16_input_is_bit_identical_to_converted_float(cmvn):
         assert_feats_close(got[i, :k], oracle[i, :k], cmvn)
     with pytest.raises(RuntimeError, match="statistics pass takes float32"):
         fe.forward_packed(flat.to(DEV), offs, lens, stats=torch.zeros(1121, dtype=torch.float64, device=DEV))
+
+
+def test_audio_statistics_match_reference_formulas():
+    """max / min / mean|x| / rms / clipping ratio of a ragged batch (R:voice_interface.py:873-939)."""
+    rng = np.random.default_rng(9)
+    lens = np.array([1, 400, 16000, 48017, 0, 7777], dtype=np.int64)
+    waves = [np.clip(0.5 * rng.standard_normal(int(n)), -1, 1).astype(np.float32) for n in lens]
+    waves[3][:100] = 1.0
+    waves[3][100:150] = -0.9995
+    ref = np.stack([wf.audio_statistics(w) for w in waves])
+    nmax = int(lens.max())
+    buf = torch.zeros(len(lens), nmax)
+    for i, w in enumerate(waves):
+        buf[i, :len(w)] = torch.from_numpy(w)
+    got = WavFrontend.audio_statistics(buf.to(DEV), lens).cpu().numpy()
+    assert got.shape == (6, 6)
+    assert np.array_equal(got[:, [0, 1, 5]], ref[:, [0, 1, 5]])            # max, min, max |x|: exact
+    assert np.array_equal(got[:, 4], ref[:, 4])                            # clipping ratio: exact counts
+    assert np.allclose(got[:, [2, 3]], ref[:, [2, 3]], rtol=1e-12, atol=0)   # float64 sums
+    offs, total = synth.packed_offsets(lens, align=1)
+    flat = torch.zeros(int(total) + 4)
+    for o, w in zip(offs, waves):
+        flat[o:o + len(w)] = torch.from_numpy(w)
+    got2 = WavFrontend.audio_statistics(flat.to(DEV), lens, offsets=offs).cpu().numpy()
+    assert np.array_equal(got2[:, [0, 1, 4, 5]], got[:, [0, 1, 4, 5]]) and np.allclose(got2, got, rtol=1e-12)
+
+
+def test_subtract_mean_speaker_verification_features():
+    """the CAM++ front-end = 80-mel Kaldi fbank + utterance mean normalisation (Kaldi subtract_mean,
+    TA:642-644), against torchaudio itself when present and the oracle."""
+    lens = [16000, 4001, 32000]
+    waves = [synth.uniform_pcm(91, i, n) for i, n in enumerate(lens)]
+    fe = WavFrontend(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, dither=0.0, subtract_mean=True)
+    feats, fl = fe(dense_batch(waves), lens)
+    for i, w in enumerate(waves):
+        fb = kf.fbank(w * np.float32(32768.0), num_mel_bins=80, frame_length=25.0, frame_shift=10.0, dither=0.0,
+                      energy_floor=0.0, window_type="hamming", sample_frequency=16000.0, dtype=np.float32)
+        ref = wf.subtract_column_mean(fb)
+        k = int(fl[i])
+        assert k == ref.shape[0]
+        got = feats[i, :k].cpu().numpy()
+        assert np.abs(got - ref).mean() <= 2e-5 and np.abs(got - ref).max() <= 3e-3
+        assert np.abs(got.mean(axis=0)).max() <= 1e-4            # columns are centred
+        assert not feats[i, k:].any()
+    try:
+        import torchaudio.compliance.kaldi as kaldi
+    except Exception:
+        return
+    t = kaldi.fbank(torch.from_numpy(waves[0])[None] * 32768.0, num_mel_bins=80, dither=0.0, energy_floor=0.0,
+                    window_type="hamming", sample_frequency=16000.0, subtract_mean=True)
+    assert (feats[0, :int(fl[0])].cpu() - t).abs().max() <= 3e-3
+    with pytest.raises(NotImplementedError):
+        WavFrontend(lfr_m=7, lfr_n=6, subtract_mean=True)

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "extras.cuh"
 #include "fbank_tile.cuh"
 #include "fbank_warp.cuh"
 #include "stream_kernel.cuh"
@@ -768,5 +769,6 @@ int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int6
 
 }  // extern "C"
 
+#include "extras_api.inl"
 #include "stream_api.inl"
 #include "tts_api.inl"

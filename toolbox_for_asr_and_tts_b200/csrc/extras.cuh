@@ -1,0 +1,114 @@
+// By-products of the front-end pass that the reference computes on the host around its funasr calls:
+//   * audio_stats_kernel   _log_audio_statistics / the per-chunk energy gate (R:voice-service/app/services/
+//                          voice_interface.py:873-939, 1298-1300, 1569-1570): max, min, mean |x|, RMS, clipping ratio
+//   * column_mean_kernel   Kaldi subtract_mean (TA:642-644, _subtract_column_mean) = the utterance mean
+//                          normalisation of the CAM++ speaker-verification features (R:voice_interface.py:2430,2520,2558)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200fe {
+
+// order-preserving float <-> unsigned map, so that max / min reduce with integer atomics
+__device__ __forceinline__ unsigned float_to_ordered(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+struct AudioStatsAcc {     // one per utterance, zero-initialised by audio_stats_init_kernel
+  double sum_abs, sum_sq;
+  unsigned long long n_clip;
+  unsigned max_ord, min_ord;
+};
+
+__global__ void audio_stats_init_kernel(AudioStatsAcc* acc, int batch) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= batch) return;
+  acc[u].sum_abs = 0.0;
+  acc[u].sum_sq = 0.0;
+  acc[u].n_clip = 0ull;
+  acc[u].max_ord = 0u;            // below every float
+  acc[u].min_ord = 0xffffffffu;   // above every float
+}
+
+// grid = (chunks, batch): every CTA reduces a strided slice of one utterance and adds it with a handful of atomics.
+__global__ void __launch_bounds__(256)
+audio_stats_kernel(const float* wave, const long long* offsets, const long long* lengths, long long row_stride,
+                   float clip_level, AudioStatsAcc* acc) {
+  const int u = blockIdx.y;
+  const long long n = lengths[u];
+  const float* x = wave + (offsets ? offsets[u] : (long long)u * row_stride);
+  double s_abs = 0.0, s_sq = 0.0;
+  unsigned n_clip = 0;
+  float mx = -INFINITY, mn = INFINITY;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i], a = fabsf(v);
+    s_abs += a;
+    s_sq += (double)v * v;
+    n_clip += a >= clip_level;
+    mx = fmaxf(mx, v);
+    mn = fminf(mn, v);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    s_abs += __shfl_xor_sync(0xffffffffu, s_abs, o);
+    s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o);
+    n_clip += __shfl_xor_sync(0xffffffffu, n_clip, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0 && (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31) < n) {
+    atomicAdd(&acc[u].sum_abs, s_abs);
+    atomicAdd(&acc[u].sum_sq, s_sq);
+    atomicAdd(&acc[u].n_clip, (unsigned long long)n_clip);
+    atomicMax(&acc[u].max_ord, float_to_ordered(mx));
+    atomicMin(&acc[u].min_ord, float_to_ordered(mn));
+  }
+}
+
+// out[u] = {max, min, mean |x|, rms, clipping ratio, max |x|}; an empty utterance yields zeros.
+__global__ void audio_stats_final_kernel(const AudioStatsAcc* acc, const long long* lengths, int batch, double* out) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= batch) return;
+  const long long n = lengths[u];
+  double* o = out + 6 * u;
+  if (n <= 0) {
+    for (int k = 0; k < 6; ++k) o[k] = 0.0;
+    return;
+  }
+  const double mx = ordered_to_float(acc[u].max_ord), mn = ordered_to_float(acc[u].min_ord);
+  o[0] = mx;
+  o[1] = mn;
+  o[2] = acc[u].sum_abs / (double)n;
+  o[3] = sqrt(acc[u].sum_sq / (double)n);
+  o[4] = (double)acc[u].n_clip / (double)n;
+  o[5] = fmax(fabs(mx), fabs(mn));
+}
+
+// feats[u, t, d] -= mean_t feats[u, :T_u, d]  (TA:642-644).  One CTA per (utterance, 32 columns): 8 row-lanes x 32
+// column-lanes, float64 column sums (the reference sums in float32; the difference is below its own rounding).
+__global__ void __launch_bounds__(256)
+column_mean_kernel(float* feats, long long rows_cap, int D, const long long* n_rows) {
+  __shared__ double part[8][33];
+  const int u = blockIdx.y;
+  const int d = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r0 = threadIdx.x >> 5;
+  const long long T = n_rows[u];
+  float* base = feats + (long long)u * rows_cap * D;
+  double s = 0.0;
+  if (d < D)
+    for (long long t = r0; t < T; t += 8) s += base[t * D + d];
+  part[r0][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (d >= D || T <= 0) return;
+  double tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += part[k][threadIdx.x & 31];
+  const float mean = (float)(tot / (double)T);
+  for (long long t = r0; t < T; t += 8) base[t * D + d] -= mean;
+}
+
+}  // namespace b200fe

@@ -275,6 +275,54 @@ std::tuple<at::Tensor, at::Tensor> tts_forward(int64_t t, const at::Tensor& wave
   return {mel, lens};
 }
 
+// float64 [B, 6] = {max, min, mean |x|, rms, clipping ratio, max |x|} per utterance
+at::Tensor fe_audio_stats(const at::Tensor& wave, const c10::optional<at::Tensor>& offsets, const at::Tensor& lengths,
+                          double clip_level) {
+  TORCH_CHECK(wave.is_cuda() && wave.scalar_type() == at::kFloat, "b200fe.audio_stats: waveform must be CUDA float32");
+  c10::cuda::CUDAGuard guard(wave.device());
+  auto w = wave.contiguous();
+  auto len_host = lengths.to(at::kCPU, at::kLong).contiguous();
+  const int b = (int)len_host.numel();
+  int64_t row_stride = 0, max_len = 0;
+  at::Tensor off_dev;
+  if (offsets.has_value() && offsets->defined()) {
+    auto off_host = offsets->to(at::kCPU, at::kLong).contiguous();
+    TORCH_CHECK(off_host.numel() == b, "offsets and lengths differ in size");
+    for (int i = 0; i < b; ++i)
+      TORCH_CHECK(off_host.data_ptr<int64_t>()[i] >= 0 &&
+                      off_host.data_ptr<int64_t>()[i] + len_host.data_ptr<int64_t>()[i] <= w.numel(),
+                  "utterance outside the wave buffer");
+    off_dev = off_host.to(w.device(), true);
+  } else {
+    TORCH_CHECK(w.dim() == 2 && w.size(0) == b, "waveform must be [B, Nmax] when no offsets are given");
+    row_stride = w.size(1);
+  }
+  for (int i = 0; i < b; ++i) {
+    const int64_t n = len_host.data_ptr<int64_t>()[i];
+    TORCH_CHECK(n >= 0 && (off_dev.defined() || n <= row_stride), "bad length");
+    max_len = std::max(max_len, n);
+  }
+  auto len_dev = len_host.to(w.device(), true);
+  auto out = at::zeros({b, 6}, w.options().dtype(at::kDouble));
+  auto work = at::empty({(int64_t)b200fe_audio_stats_workspace(b)}, w.options().dtype(at::kByte));
+  int rc = b200fe_audio_stats(w.data_ptr<float>(), off_dev.defined() ? off_dev.data_ptr<int64_t>() : nullptr, row_stride,
+                              len_dev.data_ptr<int64_t>(), b, max_len, (float)clip_level, out.data_ptr<double>(),
+                              work.data_ptr(), (size_t)work.numel(), cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_audio_stats failed (", rc, ")");
+  return out;
+}
+
+void fe_subtract_column_mean(at::Tensor feats, const at::Tensor& n_rows) {
+  TORCH_CHECK(feats.is_cuda() && feats.scalar_type() == at::kFloat && feats.dim() == 3 && feats.is_contiguous(),
+              "b200fe.subtract_column_mean: features must be a contiguous CUDA float32 [B, T, D] tensor");
+  c10::cuda::CUDAGuard guard(feats.device());
+  auto nr = n_rows.to(feats.device(), at::kLong).contiguous();
+  TORCH_CHECK(nr.numel() == feats.size(0), "n_rows must have one entry per utterance");
+  int rc = b200fe_subtract_column_mean(feats.data_ptr<float>(), feats.size(1), (int)feats.size(2), nr.data_ptr<int64_t>(),
+                                       (int)feats.size(0), cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_subtract_column_mean failed (", rc, ")");
+}
+
 int64_t fe_launch_count(int64_t h) { return b200fe_launch_count(H(h)); }
 
 void fe_select_kernel(int64_t h, int64_t which) { check(b200fe_select_kernel(H(h), (int)which), H(h), "b200fe_select_kernel"); }
@@ -310,6 +358,8 @@ TORCH_LIBRARY(b200fe, m) {
   m.def("tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_min, float f_max) -> int", tts_create);
   m.def("tts_destroy(int t) -> ()", tts_destroy);
   m.def("tts_forward(int t, Tensor wave, Tensor? offsets, Tensor lengths, int hop, int n_mels) -> (Tensor, Tensor)", tts_forward);
+  m.def("audio_stats(Tensor wave, Tensor? offsets, Tensor lengths, float clip_level) -> Tensor", fe_audio_stats);
+  m.def("subtract_column_mean(Tensor(a!) feats, Tensor n_rows) -> ()", fe_subtract_column_mean);
   m.def("launch_count(int h) -> int", fe_launch_count);
   m.def("select_kernel(int h, int which) -> ()", fe_select_kernel);
   m.def("profile_enable(int h, bool on) -> ()", fe_profile_enable);

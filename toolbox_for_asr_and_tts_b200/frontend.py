@@ -88,6 +88,11 @@ class WavFrontend(nn.Module):
         self.low_freq = float(kwargs.pop("low_freq", 20.0))
         self.high_freq = float(kwargs.pop("high_freq", 0.0))
         self.blackman_coeff = float(kwargs.pop("blackman_coeff", 0.42))
+        # Kaldi subtract_mean (TA:539, 642-644): utterance mean normalisation of the fbank, as the CAM++ speaker
+        # verification front-end applies it (R:voice_interface.py:2430,2520,2558); only without LFR / CMVN
+        self.subtract_mean = bool(kwargs.pop("subtract_mean", False))
+        if self.subtract_mean and (lfr_m != 1 or lfr_n != 1 or cmvn is not None or cmvn_file not in (None, "null")):
+            raise NotImplementedError("subtract_mean is implemented for plain fbank features (lfr_m = lfr_n = 1, no CMVN)")
         if cmvn is not None:
             self.cmvn = torch.as_tensor(cmvn, dtype=torch.float32)
         elif cmvn_file is not None and cmvn_file != "null":
@@ -153,6 +158,8 @@ class WavFrontend(nn.Module):
         self._calls += 1
         feats, feat_lens = h.ops.forward(h.h, self._pcm(input), None, lens, 0, kwargs.get("stats"),
                                          int(self.dither_seed + self._calls))
+        if self.subtract_mean:
+            h.ops.subtract_column_mean(feats, feat_lens)
         return feats, feat_lens
 
     @staticmethod
@@ -177,8 +184,11 @@ class WavFrontend(nn.Module):
         self._check_cuda(input, "input")
         h = self._handle(lfr=False, cmvn=False, fbank_only_cfg=True)
         self._calls += 1
-        return h.ops.forward(h.h, self._pcm(input), None, _as_length_tensor(input_lengths), 0, None,
-                             int(self.dither_seed + self._calls))
+        feats, feat_lens = h.ops.forward(h.h, self._pcm(input), None, _as_length_tensor(input_lengths), 0, None,
+                                         int(self.dither_seed + self._calls))
+        if self.subtract_mean:
+            h.ops.subtract_column_mean(feats, feat_lens)
+        return feats, feat_lens
 
     def forward_lfr_cmvn(self, input: torch.Tensor, input_lengths) -> Tuple[torch.Tensor, torch.Tensor]:
         """VF:198-218: LFR + CMVN of given [B, T, n_mels] features."""
@@ -188,6 +198,16 @@ class WavFrontend(nn.Module):
         feats, feat_lens = h.ops.lfr_cmvn(h.h, input.to(torch.float32), lens)
         rows = int(-(-int(lens.max()) // self.lfr_n)) if lens.numel() else 0
         return feats[:, :rows], feat_lens
+
+    @staticmethod
+    def audio_statistics(wave: torch.Tensor, lengths, offsets=None, clip_level: float = 0.999) -> torch.Tensor:
+        """Per-utterance statistics the reference logs / gates on around its funasr calls (_log_audio_statistics,
+        R:voice_interface.py:873-939; energy gate :1298-1300, :1569-1570), for a whole ragged batch on the GPU.
+        Returns float64 [B, 6]: max, min, mean |x|, rms, clipping ratio (|x| >= clip_level), max |x|."""
+        WavFrontend._check_cuda(wave, "wave")
+        from . import _native
+        return _native.ops().audio_stats(wave.to(torch.float32), None if offsets is None else _as_length_tensor(offsets),
+                                         _as_length_tensor(lengths), float(clip_level))
 
     # ------------------------------------------------------------------ extras used by tests / tools
     def frame_counts(self, input_lengths) -> Tuple[torch.Tensor, torch.Tensor]:
