@@ -566,3 +566,33 @@ def test_subtract_mean_speaker_verification_features():
     assert (feats[0, :int(fl[0])].cpu() - t).abs().max() <= 3e-3
     with pytest.raises(NotImplementedError):
         WavFrontend(lfr_m=7, lfr_n=6, subtract_mean=True)
+
+
+@pytest.mark.parametrize("opts", [
+    dict(frame_length=32, frame_shift=10, n_mels=40, window="povey"),
+    dict(frame_length=20, frame_shift=10, n_mels=64, window="hanning", preemphasis_coefficient=0.0, remove_dc_offset=False),
+    dict(frame_length=25, frame_shift=10, n_mels=80, window="blackman", low_freq=100.0, high_freq=-200.0),
+    dict(frame_length=25, frame_shift=5, n_mels=80, window="rectangular"),
+    dict(frame_length=25, frame_shift=20, n_mels=24, window="hamming"),
+])
+@pytest.mark.parametrize("kernel", ["auto", "tile"])
+def test_kaldi_option_variants_against_oracle(opts, kernel):
+    """The Kaldi fbank options surface (TA:514-541) away from the Paraformer values: other frame lengths / shifts
+    (generic 32-row FFT path, frames that are not whole 16-sample rows), mel counts, windows, no pre-emphasis, no DC
+    removal, band limits - through both fused kernels, fbank only."""
+    lens = [16000, 4001, 1603]
+    waves = [synth.uniform_pcm(55, i, n) for i, n in enumerate(lens)]
+    fe = WavFrontend(fs=16000, dither=0.0, **opts)
+    fe.select_kernel(kernel)
+    feats, fl = fe.forward_fbank(dense_batch(waves), lens)
+    kw = dict(num_mel_bins=opts["n_mels"], frame_length=float(opts["frame_length"]), frame_shift=float(opts["frame_shift"]),
+              dither=0.0, energy_floor=0.0, window_type=opts["window"], sample_frequency=16000.0,
+              preemphasis_coefficient=opts.get("preemphasis_coefficient", 0.97),
+              remove_dc_offset=opts.get("remove_dc_offset", True), low_freq=opts.get("low_freq", 20.0),
+              high_freq=opts.get("high_freq", 0.0), dtype=np.float32)
+    for i, w in enumerate(waves):
+        ref = kf.fbank(w * np.float32(32768.0), **kw)
+        k = int(fl[i])
+        assert k == ref.shape[0], (k, ref.shape)
+        assert_logmel_close(feats[i, :k].cpu().numpy(), ref)
+        assert not feats[i, k:].any()
