@@ -173,8 +173,9 @@ __global__ void pcm16_to_float_kernel(const short* src, int n, float* dst) {
 // Expands the per-utterance descriptors into the launch-wide quad list of the warp kernel: quad q of utterance u covers
 // frames 4 (q - quad_begin[u]) .. +3.  One thread per quad; utterances without frames own no quads.
 __global__ void build_quads_kernel(const UttDesc* utts, int batch, int n_quads, int S, int lfr_m, int lfr_n, int M,
-                                   QuadDesc* quads) {
+                                   QuadDesc* quads, int* next_quad) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0) *next_quad = 0;   // the warp kernel's work counter
   if (q >= n_quads) return;
   int lo = 0, hi = batch - 1;
   while (lo < hi) {   // last utterance whose quad_begin <= q (empty utterances share the next one's quad_begin)

@@ -264,7 +264,7 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // then 512 floats per utterance shorter than one frame (scratch for int16 input: the short path reads float32)
 size_t workspace_need(int batch, int n_tiles = 0, int n_quads = 0, int n_short = 0) {
   const size_t lists = std::max((size_t)n_tiles * sizeof(TileDesc), (size_t)n_quads * sizeof(QuadDesc));
-  return align256((size_t)batch * sizeof(UttDesc)) + align256((size_t)batch * sizeof(ShortDesc)) + align256(lists) +
+  return 256 /* work counter */ + align256((size_t)batch * sizeof(UttDesc)) + align256((size_t)batch * sizeof(ShortDesc)) + align256(lists) +
          align256((size_t)n_short * 512 * sizeof(float));
 }
 
@@ -603,8 +603,9 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
     const long long end = pl.utts[u].wave_off + lengths_host[u];
     if (pl.utts[u].wave_off < 0 || end > wave_total) return fail(h, B200FE_E_INVALID, "utterance outside the wave buffer");
   }
-  UttDesc* d_utts = reinterpret_cast<UttDesc*>(workspace_dev);
-  ShortDesc* d_shorts = reinterpret_cast<ShortDesc*>((char*)workspace_dev + align256((size_t)batch * sizeof(UttDesc)));
+  int* d_counter = reinterpret_cast<int*>(workspace_dev);
+  UttDesc* d_utts = reinterpret_cast<UttDesc*>((char*)workspace_dev + 256);
+  ShortDesc* d_shorts = reinterpret_cast<ShortDesc*>((char*)d_utts + align256((size_t)batch * sizeof(UttDesc)));
   TileDesc* d_tiles = reinterpret_cast<TileDesc*>((char*)d_shorts + align256((size_t)batch * sizeof(ShortDesc)));
   QuadDesc* d_quads = reinterpret_cast<QuadDesc*>(d_tiles);   // same region: a launch uses one of the two lists
   if ((rc = upload(h, pl.utts.data(), (size_t)batch * sizeof(UttDesc), d_utts, st))) return rc;
@@ -616,7 +617,7 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
                                          "frame shifts whose quad fits its buffer)");
   if (use_warp && pl.n_quads > 0) {
     build_quads_kernel<<<(pl.n_quads + 255) / 256, 256, 0, st>>>(d_utts, batch, pl.n_quads, h->S, h->cfg.lfr_m,
-                                                                 h->cfg.lfr_n, h->cfg.n_mels, d_quads);
+                                                                 h->cfg.lfr_n, h->cfg.n_mels, d_quads, d_counter);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
   } else if (pl.n_tiles > 0) {
@@ -638,7 +639,7 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   // 2. the fused kernel over all regular utterances: warp kernel, or tile kernel for the statistics pass
   if (use_warp && pl.n_quads > 0) {
     QuadParams p;
-    p.wave = wave_any; p.wave_total = wave_total; p.quads = d_quads; p.n_quads = pl.n_quads;
+    p.wave = wave_any; p.wave_total = wave_total; p.quads = d_quads; p.n_quads = pl.n_quads; p.next_quad = d_counter;
     p.feats = feats_dev; p.rows_cap = rows_cap;
     p.frame_len = h->L; p.frame_shift = h->S; p.n_mels = h->cfg.n_mels; p.lfr_m = h->cfg.lfr_m; p.lfr_n = h->cfg.lfr_n;
     p.preemph = h->cfg.preemphasis; p.remove_dc = h->cfg.remove_dc_offset; p.log_floor = h->cfg.log_floor;

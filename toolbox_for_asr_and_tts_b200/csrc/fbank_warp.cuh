@@ -44,6 +44,7 @@ struct QuadParams {
   long long wave_total;   // samples addressable behind `wave`
   const QuadDesc* quads;
   int n_quads;
+  int* next_quad;         // work counter (zeroed by build_quads_kernel): quads beyond the first wave are claimed dynamically
   float* feats;           // [batch, rows_cap, out_dim]
   long long rows_cap;
   int frame_len, frame_shift, n_mels, lfr_m, lfr_n;
@@ -262,14 +263,18 @@ fbank_warp_kernel(const QuadParams p) {
   // The 64-byte descriptor is read in pieces, each just before it is needed, so that it never occupies 16 registers:
   // {g0, utt, f0} and {nF, T, rows} at the top of a quad, the targets before the mel stage, and the next quad's
   // {g0, nF} (for its sample loads) one quad ahead.
-  const int wstride = gridDim.x * kWarps;
+  // Work distribution: the first quad of every warp is static (neighbouring warps start on neighbouring quads), all
+  // later ones are claimed from a global counter one quad ahead, so that no SM idles while another still has a queue.
+  const int first_wave = gridDim.x * kWarps;
   int q = blockIdx.x * kWarps + warp;
   if (q >= p.n_quads) return;
   long long g0_cur = __ldg(&p.quads[q].g0);
   int nf_cur = __ldg(&p.quads[q].nF);
 
   while (true) {
-    const int qn = q + wstride;
+    int qn = 0;
+    if (lane == 0) qn = first_wave + atomicAdd(p.next_quad, 1);
+    qn = __shfl_sync(0xffffffffu, qn, 0);
     const bool have_next = qn < p.n_quads;
     long long g0_next = 0;
     int nf_next = 0;
