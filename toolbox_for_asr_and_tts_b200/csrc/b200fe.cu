@@ -7,10 +7,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -62,7 +62,7 @@ struct b200fe_handle {
   int next_slot = 0;
   long long launches = 0;
   bool profile = false;
-  bool force_tile = false;           // B200FE_FORCE_TILE=1: keep the tile kernel (A/B measurements)
+  bool force_tile = false;           // b200fe_select_kernel(h, 1): keep the tile kernel (A/B measurements, tests)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   mutable std::string err;
 };
@@ -128,8 +128,17 @@ int build_mel(int n_mels, int nfft, double fs, double low, double high, std::vec
 
 // Sparse mel bank by interval between filter centres (see TileParams::mel_w).  `bank` is dense [nm, ld] (row stride ld),
 // only columns < nb are used.  A bin must feed at most two adjacent filters (triangular banks).
+//
+// Round r holds intervals 31 r .. 31 r + 31 (the last one belongs to the next round too: here it only supplies the
+// down-slope sum of filter 31 r + 30).  Which LANE an interval sits on is free, and so is the start of its padded run
+// inside the slack the round's trip count leaves: with bank_mod = 16 both are chosen (bipartite matching) so that the 16
+// lanes of each half-warp start on 16 different residues mod 16, which makes the 64-bit gathers of the mel stage
+// bank-conflict free for every step (all lanes advance together).  bank_mod = 0 keeps lane l on interval 31 r + l.
+// mlo word: bits 0..11 first bin of the run, 12..16 lane that holds the NEXT interval (its down-slope sum completes
+// this lane's filter), 17..24 filter index, bit 31 = this lane outputs a filter.
 int build_interval_table(const std::vector<float>& bank, int nm, int nb, int ld, float scale, std::vector<float2>& mw,
-                         std::vector<int>& mlo, int& rounds, int* cnt_out, int* base_out, std::string& why) {
+                         std::vector<int>& mlo, int& rounds, int* cnt_out, int* base_out, std::string& why,
+                         int bank_mod = 0) {
   mw.assign((size_t)kMelSlots * 32, make_float2(0.f, 0.f));
   mlo.assign(32 * kMelRounds, 1);
   auto W = [&](int m, int k) { return bank[(size_t)m * ld + k]; };
@@ -166,6 +175,7 @@ int build_interval_table(const std::vector<float>& bank, int nm, int nb, int ld,
     if (k != ilo[iv] + icnt[iv]) { why = "mel filterbank intervals are not contiguous"; return -1; }
     icnt[iv]++;
   }
+  if (nb > 4096 || nm > 255) { why = "mel filterbank does not fit the packed interval word"; return -1; }
   rounds = (nm + 30) / 31;
   int base = 0;
   for (int r = 0; r < rounds; ++r) {
@@ -177,15 +187,65 @@ int build_interval_table(const std::vector<float>& bank, int nm, int nb, int ld,
     cnt_out[r] = c;
     base_out[r] = base;
     if (base + c > kMelSlots) { why = "mel filterbank does not fit the sparse layout"; return -1; }
+    // items of the round and the run starts each may take
+    int n_items = 0, item_iv[32], lo_min[32], lo_max[32];
     for (int l = 0; l < 32; ++l) {
       const int iv = 31 * r + l;
-      int lo = (iv <= nm && icnt[iv]) ? ilo[iv] : 1;
-      if (lo + c > nb) lo = nb - c;                 // keep the padded run inside the spectrum
-      mlo[32 * r + l] = lo;
-      if (iv > nm) continue;
+      if (iv > nm) break;
+      item_iv[n_items] = iv;
+      if (icnt[iv]) {
+        lo_max[n_items] = ilo[iv] + c > nb ? nb - c : ilo[iv];
+        lo_min[n_items] = ilo[iv] + icnt[iv] - c < 0 ? 0 : ilo[iv] + icnt[iv] - c;
+        if (lo_min[n_items] > lo_max[n_items]) lo_min[n_items] = lo_max[n_items];
+      } else {            // no bins: all weights are zero, any run will do
+        lo_min[n_items] = 0;
+        lo_max[n_items] = nb - c;
+      }
+      ++n_items;
+    }
+    int lane_of[32], lo_of[32], slot_item[32];
+    for (int i = 0; i < 32; ++i) { lane_of[i] = -1; lo_of[i] = 0; slot_item[i] = -1; }
+    if (bank_mod == 16) {
+      // Kuhn's augmenting paths: item -> slot (half h, residue rho) = lane 16 h + rho
+      auto can = [&](int it, int slot) {
+        const int rho = slot & 15;
+        for (int lo = lo_max[it]; lo >= lo_min[it]; --lo)
+          if ((lo & 15) == rho) return lo;
+        return -1;
+      };
+      std::vector<char> seen(32);
+      std::function<bool(int)> aug = [&](int it) {
+        for (int slot = 0; slot < 32; ++slot) {
+          if (seen[slot] || can(it, slot) < 0) continue;
+          seen[slot] = 1;
+          if (slot_item[slot] < 0 || aug(slot_item[slot])) { slot_item[slot] = it; return true; }
+        }
+        return false;
+      };
+      // widest (least slack) items first
+      std::vector<int> order(n_items);
+      for (int i = 0; i < n_items; ++i) order[i] = i;
+      std::sort(order.begin(), order.end(), [&](int a, int b2) { return lo_max[a] - lo_min[a] < lo_max[b2] - lo_min[b2]; });
+      for (int it : order) { std::fill(seen.begin(), seen.end(), 0); aug(it); }
+      for (int slot = 0; slot < 32; ++slot)
+        if (slot_item[slot] >= 0) { lane_of[slot_item[slot]] = slot; lo_of[slot_item[slot]] = can(slot_item[slot], slot); }
+      for (int it = 0; it < n_items; ++it) {     // unmatched: any free lane, natural start (some conflicts remain)
+        if (lane_of[it] >= 0) continue;
+        for (int slot = 0; slot < 32; ++slot)
+          if (slot_item[slot] < 0) { slot_item[slot] = it; lane_of[it] = slot; lo_of[it] = lo_max[it]; break; }
+      }
+    } else {
+      for (int it = 0; it < n_items; ++it) { lane_of[it] = it; lo_of[it] = icnt[item_iv[it]] ? lo_max[it] : (1 + c > nb ? nb - c : 1); slot_item[it] = it; }
+    }
+    for (int l = 0; l < 32; ++l) mlo[32 * r + l] = (l << 12);   // idle lane: run at bin 0.., own lane as partner, no output
+    for (int it = 0; it < n_items; ++it) {
+      const int iv = item_iv[it], l = lane_of[it], lo = lo_of[it];
+      const bool outputs = iv < nm && iv <= 31 * r + 30;
+      const int partner = (it + 1 < n_items) ? lane_of[it + 1] : l;
+      mlo[32 * r + l] = lo | (partner << 12) | ((iv & 0xff) << 17) | (outputs ? (int)0x80000000u : 0);
       for (int q = 0; q < c; ++q) {
         const int k = lo + q;
-        if (iv_of[k] != iv) continue;               // padding slot: weight 0
+        if (k < 0 || k >= nb || iv_of[k] != iv) continue;   // padding slot: weight 0
         const float up = iv < nm ? W(iv, k) : 0.f;
         const float dn = iv >= 1 ? W(iv - 1, k) : 0.f;
         mw[(size_t)(base + q) * 32 + l] = make_float2(scale * up, scale * dn);
@@ -414,7 +474,6 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
 
   b200fe_handle* h = new b200fe_handle();
   h->cfg = *cfg;
-  { const char* ft = getenv("B200FE_FORCE_TILE"); h->force_tile = ft && ft[0] == '1'; }
   h->L = L; h->S = S; h->nfft = nfft;
   h->D = cfg->lfr_m * cfg->n_mels;
   h->rows_per_tile = (kFMax - cfg->lfr_m) / cfg->lfr_n + 1;
@@ -446,7 +505,7 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
   {
     std::string why;
     if (build_interval_table(h->mel_host, cfg->n_mels, nfft / 2, nfft / 2, 0.25f, mw, mlo, h->mel_rounds, h->mel_cnt,
-                             h->mel_base, why) != 0)
+                             h->mel_base, why, 16) != 0)
       return bail(B200FE_E_UNSUPPORTED, why);
     h->mel_paraformer = h->mel_rounds == MelShapeParaformer::kRounds;
     for (int r = 0; r < MelShapeParaformer::kRounds && h->mel_paraformer; ++r)

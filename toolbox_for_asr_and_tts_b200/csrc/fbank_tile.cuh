@@ -96,10 +96,12 @@ struct TileParams {
   const float2* twiddle;  // [kTw2Total]: table g, row k1-1, entry c = s(k1) * exp(-2*pi*i*(c - 16*g)*k1/512), s = 2 for
                           // k1 in {8, 16} else 1.  Table 1 undoes the one-row rotation group 1 applies to its sample
                           // loads.  Then the column-0 table: row t, entry c = 2 * exp(-2*pi*i*c*t/16), c < 8.
-  // sparse mel bank by interval between filter centres.  Round r: lane l <-> interval 31 r + l (the last lane's interval
-  // is the first of the next round: it only supplies the down-slope sum of filter 31 r + 30).  Every round has a
-  // warp-uniform trip count mel_cnt[r] = its widest interval; weights are zero-padded to it and stored lane-transposed:
-  // mel_w[(mel_base[r] + q) * 32 + lane] = (up, down) weight x 0.25 of bin mel_lo[32 r + lane] + q.  Read through L1.
+  // sparse mel bank by interval between filter centres.  Round r covers intervals 31 r .. 31 r + 31 (the last one is
+  // the first of the next round: here it only supplies the down-slope sum of filter 31 r + 30), one per lane, placed by
+  // build_interval_table so that the gathers are bank-conflict free.  Every round has a warp-uniform trip count
+  // mel_cnt[r] = its widest interval; weights are zero-padded to it and stored lane-transposed:
+  // mel_w[(mel_base[r] + q) * 32 + lane] = (up, down) weight x 0.25 of bin (mel_lo[32 r + lane] & 0xfff) + q; the rest
+  // of the mel_lo word names the partner lane, the filter index and whether the lane outputs.  Read through L1.
   const float2* mel_w;
   const int* mel_lo;      // [32 * mel_rounds]
   int mel_rounds;
@@ -184,8 +186,8 @@ template <int CNT, class EPI>
 __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, int base, const float2* pg, int lane, int M,
                                           float log_floor, EPI&& epi) {
   const int cnt = CNT >= 0 ? CNT : cnt_rt;
-  const int iv = lane + 31 * r;
-  const int lo = __ldg(mel.lo + 32 * r + lane);
+  const unsigned word = (unsigned)__ldg(mel.lo + 32 * r + lane);   // run start | partner lane | filter | outputs
+  const int lo = (int)(word & 0xfffu), partner = (int)((word >> 12) & 31u), iv = (int)((word >> 17) & 0xffu);
   const float2* wt = mel.w + (base * 32 + lane);
   const float2* p0 = pg + lo;
   float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -204,12 +206,12 @@ __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, 
 #pragma unroll 4
     for (int q = 0; q < cnt; ++q) body(q);
   }
-  // energy[filter iv] = up-slope sum of interval iv + down-slope sum of interval iv + 1 (the next lane)
-  const float ex = up.x + __shfl_down_sync(0xffffffffu, dn.x, 1);
-  const float ey = up.y + __shfl_down_sync(0xffffffffu, dn.y, 1);
-  const float ez = up.z + __shfl_down_sync(0xffffffffu, dn.z, 1);
-  const float ew = up.w + __shfl_down_sync(0xffffffffu, dn.w, 1);
-  if (lane < 31 && iv < M)
+  // energy[filter iv] = up-slope sum of interval iv + down-slope sum of interval iv + 1 (held by the partner lane)
+  const float ex = up.x + __shfl_sync(0xffffffffu, dn.x, partner);
+  const float ey = up.y + __shfl_sync(0xffffffffu, dn.y, partner);
+  const float ez = up.z + __shfl_sync(0xffffffffu, dn.z, partner);
+  const float ew = up.w + __shfl_sync(0xffffffffu, dn.w, partner);
+  if (word >> 31)
     epi(iv, fast_ln(fmaxf(ex, log_floor)), fast_ln(fmaxf(ey, log_floor)), fast_ln(fmaxf(ez, log_floor)),
         fast_ln(fmaxf(ew, log_floor)));
 }

@@ -163,7 +163,7 @@ tts_mel_kernel(const TtsParams p) {
         for (int t = 1; t < kMelRounds; ++t)
           if (r == t) { cnt = mel.cnt[t]; base = mel.base[t]; }
         const int iv = lane + 31 * r;
-        const int lo = __ldg(mel.lo + 32 * r + lane);
+        const int lo = __ldg(mel.lo + 32 * r + lane) & 0xfff;   // identity lane layout (build_interval_table, bank_mod 0)
         const float2* wt = mel.w + (base * 32 + lane);
         float up0 = 0.f, up1 = 0.f, dn0 = 0.f, dn1 = 0.f;
 #pragma unroll 4
