@@ -237,7 +237,13 @@ int build_interval_table(const std::vector<float>& bank, int nm, int nb, int ld,
     } else {
       for (int it = 0; it < n_items; ++it) { lane_of[it] = it; lo_of[it] = icnt[item_iv[it]] ? lo_max[it] : (1 + c > nb ? nb - c : 1); slot_item[it] = it; }
     }
-    for (int l = 0; l < 32; ++l) mlo[32 * r + l] = (l << 12);   // idle lane: run at bin 0.., own lane as partner, no output
+    // idle lanes read the same run as an active lane of their half-warp (a broadcast, not a conflict), partner = self
+    for (int l = 0; l < 32; ++l) {
+      int lo = 0;
+      for (int it = 0; it < n_items; ++it)
+        if ((lane_of[it] >> 4) == (l >> 4)) { lo = lo_of[it]; break; }
+      mlo[32 * r + l] = lo | (l << 12);
+    }
     for (int it = 0; it < n_items; ++it) {
       const int iv = item_iv[it], l = lane_of[it], lo = lo_of[it];
       const bool outputs = iv < nm && iv <= 31 * r + 30;
