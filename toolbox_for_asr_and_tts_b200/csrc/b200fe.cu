@@ -519,18 +519,17 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
   }
   // stage-2 twiddles of the packed real FFT (TileParams::twiddle) and the column-0 table, evaluated in double
   std::vector<float2> tw(kTw2Total, make_float2(0.f, 0.f));
-  for (int g = 0; g < 2; ++g)
-    for (int k1 = 1; k1 <= 16; ++k1)
-      for (int c = 0; c < 16; ++c) {
-        const int ph = (((c - 16 * g) * k1) % 512 + 512) % 512;
-        const double sc = (k1 == 8 || k1 == 16) ? 2.0 : 1.0;
-        tw[g * kTw2Table + (k1 - 1) * kXRow + c] =
-            make_float2((float)(sc * cos(2.0 * M_PI * ph / 512.0)), (float)(-sc * sin(2.0 * M_PI * ph / 512.0)));
-      }
+  for (int k1 = 1; k1 <= 16; ++k1)
+    for (int c = 0; c < 16; ++c) {
+      const int ph = (c * k1) % 512;
+      const double sc = (k1 == 8 || k1 == 16) ? 2.0 : 1.0;
+      tw[(k1 - 1) * kXRow + c] =
+          make_float2((float)(sc * cos(2.0 * M_PI * ph / 512.0)), (float)(-sc * sin(2.0 * M_PI * ph / 512.0)));
+    }
   for (int t = 0; t < 8; ++t)
     for (int c = 0; c < 8; ++c) {
       const int ph = (c * t) % 16;
-      tw[2 * kTw2Table + t * kC0Pitch + c] =
+      tw[kTw2Table + t * kC0Pitch + c] =
           make_float2((float)(2.0 * cos(2.0 * M_PI * ph / 16.0)), (float)(-2.0 * sin(2.0 * M_PI * ph / 16.0)));
     }
   CK(cudaMalloc(&h->d_window, 512 * sizeof(float)));

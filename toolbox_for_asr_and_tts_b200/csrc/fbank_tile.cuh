@@ -38,10 +38,10 @@ constexpr int kXGroupFloat2 = 32 * kXRow;
 constexpr int kYPitch = 17;
 constexpr int kYGroupF4 = 16 * kYPitch + 8;       // 280 float4 = 4480 B
 constexpr int kYWarpF4 = 2 * kYGroupF4;           // 8960 B per warp, aliased by the warp's 4 KB of power spectra
-// Twiddles of the packed FFT: [2 groups][16 rows k1 = 1..16][kXRow float2] then the column-0 table [8][kC0Pitch].
+// Twiddles of the packed FFT: [16 rows k1 = 1..16][kXRow float2] then the column-0 table [8][kC0Pitch].
 constexpr int kTw2Table = 16 * kXRow;
 constexpr int kC0Pitch = 10;                      // float2; 80 B rows: conflict-free 128-bit reads by 8 threads
-constexpr int kTw2Total = 2 * kTw2Table + 8 * kC0Pitch;   // float2
+constexpr int kTw2Total = kTw2Table + 8 * kC0Pitch;       // float2
 constexpr int kMaxMels = 128;
 constexpr int kMaxInt = kMaxMels + 1;  // intervals between consecutive filter centres
 constexpr int kMelRounds = (kMaxMels + 30) / 31;  // rounds of 31 filters: lane <-> interval, lane 31 only feeds lane 30
@@ -93,9 +93,8 @@ struct TileParams {
   float dither;
   unsigned long long seed;
   const float* window;    // [512] window * (2^15 if upscale), zero beyond L
-  const float2* twiddle;  // [kTw2Total]: table g, row k1-1, entry c = s(k1) * exp(-2*pi*i*(c - 16*g)*k1/512), s = 2 for
-                          // k1 in {8, 16} else 1.  Table 1 undoes the one-row rotation group 1 applies to its sample
-                          // loads.  Then the column-0 table: row t, entry c = 2 * exp(-2*pi*i*c*t/16), c < 8.
+  const float2* twiddle;  // [kTw2Total]: row k1-1, entry c = s(k1) * exp(-2*pi*i*c*k1/512), s = 2 for k1 in {8, 16}
+                          // else 1.  Then the column-0 table: row t, entry c = 2 * exp(-2*pi*i*c*t/16), c < 8.
   // sparse mel bank by interval between filter centres.  Round r covers intervals 31 r .. 31 r + 31 (the last one is
   // the first of the next round: here it only supplies the down-slope sum of filter 31 r + 30), one per lane, placed by
   // build_interval_table so that the gathers are bank-conflict free.  Every round has a warp-uniform trip count
@@ -116,7 +115,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int e_cap, int n_mels) {
   b += 2 * kFMax * 4;                               // raw first / last sample of each frame
   b += (size_t)kWarps * kYWarpF4 * 16;              // transpose buffers (aliased by the power spectra)
   b += (size_t)kFMax * n_mels * 4;                  // log-mel of the tile
-  b += kTw2Total * 8;                               // twiddles (one table per group of a warp + column 0)
+  b += kTw2Total * 8;                               // twiddles (stage 2 + column 0)
   return b;
 }
 
@@ -322,19 +321,20 @@ __device__ __forceinline__ void load_window_taps(float (&win)[NROWS + 1], const 
   }
 }
 
-// This thread's row of the stage-2 twiddle table: column j (16 for thread 0) of table g (the rotated group's table
-// when the frame leaves room for the rotation).
+// This thread's row of the stage-2 twiddle table: column j (16 for thread 0).  Both groups of a warp read the same
+// table (their loads coalesce into broadcasts): the one-row rotation of the second group only multiplies its column k1
+// by the unit-modulus constant W32^k1, which the power spectrum does not see.
 template <int NROWS>
 __device__ __forceinline__ const float2* fft_twiddle_row(const float2* tw_s, int j, int grp_in_warp) {
-  const int g = NROWS < 32 ? grp_in_warp : 0;
+  (void)grp_in_warp;
   const int col = j == 0 ? 16 : j;
-  return tw_s + g * kTw2Table + (col - 1) * kXRow;
+  return tw_s + (col - 1) * kXRow;
 }
 
 // ROT: the second 16-thread group of a warp loads its samples one 16-sample row late (register i holds row i-1).
 // Frames start 160 samples = 5*32 banks apart, so without this both groups of a warp would hit the same 16 banks on
-// every sample load (2-way conflict).  The rotation multiplies FFT32 output k1 by W32^k1, which twiddle table 1
-// undoes for free.
+// every sample load (2-way conflict).  The rotation multiplies FFT32 output k1 - hence the whole column k1 of the
+// spectrum - by W32^k1, a unit-modulus constant: the power spectrum is unchanged.
 //
 // Packed real FFT (tools/model_s2.py is the numpy model of this dataflow): lane .x of every f2 is frame A, .y frame B.
 //   stage 1  y[i] = windowed sample 16(i-g)+j;  z[m] = y[2m] + i y[2m+1];  Z = FFT16(z);  split -> Y[k1], k1 = 0..16
@@ -622,7 +622,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;   // this group's transpose buffer
   float4* pbuf4 = xbuf + warp * kYWarpF4;                          // this warp's power spectra (aliases both groups)
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = tw_s + 2 * kTw2Table + (j & 7) * kC0Pitch;
+  const float2* c0_row = tw_s + kTw2Table + (j & 7) * kC0Pitch;
 
   // tile descriptors are read one tile ahead so that no dependent global load sits in front of a tile
   TileDesc cur;

@@ -153,7 +153,7 @@ stream_push_kernel(const StreamParams p) {
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;
   float4* pbuf4 = xbuf + warp * kYWarpF4;
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = tw_s + 2 * kTw2Table + (j & 7) * kC0Pitch;
+  const float2* c0_row = tw_s + kTw2Table + (j & 7) * kC0Pitch;
   for (int quad = warp; 4 * quad < nf; quad += kWarps)
     fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s, x0_s, xl_s, nf, quad, S, L, win, yg, pbuf4, tw_row, c0_row, mel, M, p.preemph,
                                      p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)sid, (unsigned)t_seen,

@@ -32,7 +32,9 @@ def group_power(x, g):
     tw = np.zeros((17, 16), complex)
     for k1 in range(1, 17):
         for c in range(16):
-            tw[k1, c] = W(512, (c - 16 * g) * k1) * (2.0 if k1 in (8, 16) else 1.0)
+            # one table for both groups: the rotated group's column k1 is off by the unit-modulus factor W32^k1,
+            # which the power spectrum does not see
+            tw[k1, c] = W(512, c * k1) * (2.0 if k1 in (8, 16) else 1.0)
     P = np.full(257, np.nan)
     for j in range(16):
         col = 16 if j == 0 else j
