@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "fbank_tile.cuh"
+#include "fft512_complex.cuh"
 
 namespace b200fe {
 
