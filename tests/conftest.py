@@ -9,6 +9,19 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 GOLDEN = ROOT / "tests" / "golden" / "frontend_golden.npz"
+VARIANTS_GOLDEN = ROOT / "tests" / "golden" / "variants_golden.npz"
+# the Kaldi option sets of tests/golden/make_golden_variants.py, in WavFrontend keywords
+VARIANT_CONFS = {
+    "povey_32ms_40mel": dict(frame_length=32, frame_shift=10, n_mels=40, window="povey"),
+    "hanning_20ms_64mel_raw": dict(frame_length=20, frame_shift=10, n_mels=64, window="hanning",
+                                   preemphasis_coefficient=0.0, remove_dc_offset=False),
+    "blackman_band_100_7800": dict(frame_length=25, frame_shift=10, n_mels=80, window="blackman", low_freq=100.0,
+                                   high_freq=-200.0),
+    "rectangular_shift5": dict(frame_length=25, frame_shift=5, n_mels=80, window="rectangular"),
+    "hamming_shift20_24mel": dict(frame_length=25, frame_shift=20, n_mels=24, window="hamming"),
+    "subtract_mean_80mel": dict(frame_length=25, frame_shift=10, n_mels=80, window="hamming", subtract_mean=True),
+}
+VARIANT_SEED, VARIANT_LENS = 55, (16000, 4001)
 PARAFORMER = dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6)
 
 # Stated tolerances: log-mel max-abs <= 1e-3 against the float32 reference on broadband input;
@@ -40,6 +53,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     return dict(np.load(GOLDEN))
+
+
+@pytest.fixture(scope="session")
+def variants_golden():
+    return dict(np.load(VARIANTS_GOLDEN))
 
 
 @pytest.fixture(scope="session")

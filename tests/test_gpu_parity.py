@@ -6,7 +6,7 @@ import ctypes
 import numpy as np
 import pytest
 import torch
-from conftest import LOGMEL_ATOL, PARAFORMER, assert_logmel_close
+from conftest import LOGMEL_ATOL, PARAFORMER, VARIANT_CONFS, VARIANT_LENS, VARIANT_SEED, assert_logmel_close
 
 from oracle import kaldi_fbank_np as kf
 from oracle import wav_frontend_np as wf
@@ -596,3 +596,26 @@ def test_kaldi_option_variants_against_oracle(opts, kernel):
         assert k == ref.shape[0], (k, ref.shape)
         assert_logmel_close(feats[i, :k].cpu().numpy(), ref)
         assert not feats[i, k:].any()
+
+
+@pytest.mark.parametrize("name", sorted(VARIANT_CONFS))
+def test_kaldi_variants_against_torchaudio_golden(variants_golden, name):
+    """The CUDA path against torchaudio's own output (committed fixtures) for the option sets of
+    tests/golden/make_golden_variants.py, incl. subtract_mean."""
+    fe = WavFrontend(fs=16000, dither=0.0, **VARIANT_CONFS[name])
+    waves = [synth.uniform_pcm(VARIANT_SEED, i, n) for i, n in enumerate(VARIANT_LENS)]
+    feats, fl = fe.forward_fbank(dense_batch(waves), list(VARIANT_LENS))
+    for i, n in enumerate(VARIANT_LENS):
+        g = variants_golden[f"{name}_{n}"]
+        assert int(fl[i]) == g.shape[0]
+        assert_logmel_close(feats[i, :g.shape[0]].cpu().numpy(), g)
+
+
+def test_fsmn_vad_frontend_against_funasr_golden(variants_golden):
+    cm = variants_golden["vad_5_1_cmvn"]
+    fe = WavFrontend(cmvn=torch.from_numpy(cm), dither=0.0, **dict(PARAFORMER, lfr_m=5, lfr_n=1))
+    w = synth.uniform_pcm(63, 0, 48000)
+    feats, fl = fe(torch.from_numpy(w)[None].to(DEV), [48000])
+    g = variants_golden["vad_5_1_feats"]
+    assert int(fl[0]) == g.shape[0]
+    assert_feats_close(feats[0], g, cm)

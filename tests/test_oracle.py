@@ -5,7 +5,7 @@ import math
 
 import numpy as np
 import pytest
-from conftest import LOGMEL_ATOL, PARAFORMER
+from conftest import LOGMEL_ATOL, PARAFORMER, VARIANT_CONFS, VARIANT_LENS, VARIANT_SEED, assert_logmel_close
 from hypothesis import given, settings
 from hypothesis import strategies as st
 
@@ -180,3 +180,31 @@ def test_tts_mel_definition_against_torch():
         fb = melscale_fbanks(513, 0.0, 12000.0, 80, 24000, norm="slaney", mel_scale="slaney")
         ref_mel = torch.log(torch.clamp(fb.T @ mag, min=1e-5)).numpy()
         assert np.abs(mine - ref_mel).max() <= 2e-4
+
+
+@pytest.mark.parametrize("name", sorted(VARIANT_CONFS))
+def test_oracle_matches_golden_kaldi_variants(variants_golden, name):
+    """The restatement against torchaudio's own output for option sets away from the Paraformer values
+    (tests/golden/make_golden_variants.py): frame lengths / shifts, mel counts, windows, no pre-emphasis / DC removal,
+    band limits, subtract_mean."""
+    o = VARIANT_CONFS[name]
+    kw = dict(num_mel_bins=o["n_mels"], frame_length=float(o["frame_length"]), frame_shift=float(o["frame_shift"]),
+              dither=0.0, energy_floor=0.0, window_type=o["window"], sample_frequency=16000.0,
+              preemphasis_coefficient=o.get("preemphasis_coefficient", 0.97), remove_dc_offset=o.get("remove_dc_offset", True),
+              low_freq=o.get("low_freq", 20.0), high_freq=o.get("high_freq", 0.0), dtype=np.float32)
+    for i, n in enumerate(VARIANT_LENS):
+        x = synth.uniform_pcm(VARIANT_SEED, i, n)
+        got = kf.fbank(x * np.float32(32768.0), **kw)
+        if o.get("subtract_mean"):
+            got = wf.subtract_column_mean(got)
+        assert_logmel_close(got, variants_golden[f"{name}_{n}"])
+
+
+def test_oracle_matches_golden_fsmn_vad_frontend(variants_golden):
+    """LFR 5/1 + CMVN (the FSMN-VAD front-end) against the verbatim funasr WavFrontend's output."""
+    cm = variants_golden["vad_5_1_cmvn"]
+    w = synth.uniform_pcm(63, 0, 48000)
+    feats, lens = wf.frontend_forward([w], [48000], cmvn=cm, **dict(PARAFORMER, lfr_m=5, lfr_n=1))
+    g = variants_golden["vad_5_1_feats"]
+    assert int(lens[0]) == g.shape[0] == 298 and feats.shape[1:] == g.shape
+    assert np.abs(feats[0] - g).max() <= cmvn_atol(cm)
