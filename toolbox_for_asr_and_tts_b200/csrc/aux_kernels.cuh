@@ -142,8 +142,9 @@ __global__ void add_count_kernel(double* dst, double v) { *dst += v; }
 
 // Expands the per-utterance descriptors into the launch-wide tile list (one thread per tile).
 __global__ void build_tiles_kernel(const UttDesc* utts, int batch, int n_tiles, int rows_per_tile, int lfr_m, int lfr_n,
-                                   int S, TileDesc* tiles) {
+                                   int S, TileDesc* tiles, int* next_tile) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) *next_tile = 0;   // the tile kernel's work counter
   if (t >= n_tiles) return;
   int lo = 0, hi = batch - 1;   // last utterance whose tile_begin <= t (utterances without tiles share the next begin)
   while (lo < hi) {

@@ -686,7 +686,7 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
     h->launches++;
   } else if (pl.n_tiles > 0) {
     build_tiles_kernel<<<(pl.n_tiles + 255) / 256, 256, 0, st>>>(d_utts, batch, pl.n_tiles, h->rows_per_tile, h->cfg.lfr_m,
-                                                                 h->cfg.lfr_n, h->S, d_tiles);
+                                                                 h->cfg.lfr_n, h->S, d_tiles, d_counter);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
   }
@@ -720,6 +720,7 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   } else if (pl.n_tiles > 0) {
     TileParams p;
     p.wave = wave_dev; p.wave_total = wave_total; p.utts = d_utts; p.tiles = d_tiles; p.batch = batch; p.n_tiles = pl.n_tiles;
+    p.next_tile = d_counter;
     p.feats = feats_dev; p.rows_cap = rows_cap; p.stats = stats_dev;
     p.frame_len = h->L; p.frame_shift = h->S; p.n_mels = h->cfg.n_mels;
     p.lfr_m = h->cfg.lfr_m; p.lfr_n = h->cfg.lfr_n; p.rows_per_tile = h->rows_per_tile; p.e_cap = h->e_cap;

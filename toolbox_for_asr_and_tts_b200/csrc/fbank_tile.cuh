@@ -74,6 +74,7 @@ struct TileParams {
   long long wave_total;
   const UttDesc* utts;
   const TileDesc* tiles;  // [n_tiles], built on the device from utts
+  int* next_tile;         // work counter (zeroed by build_tiles_kernel): tiles beyond the first wave are claimed dynamically
   int batch;
   int n_tiles;
   float* feats;           // [batch, rows_cap, out_dim]
@@ -549,13 +550,14 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
   const float2* c0_row = tw_s + kTw2Table + (j & 7) * kC0Pitch;
 
-  // tile descriptors are read one tile ahead so that no dependent global load sits in front of a tile
+    // Work distribution: the first tile of every CTA is static, later ones are claimed from a global counter (thread 0,
+  // published through shared memory across the barrier that follows the staging).
+  __shared__ int next_tile_s;
   TileDesc cur;
-  if (blockIdx.x < p.n_tiles) cur = p.tiles[blockIdx.x];
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const int tile_next = tile + gridDim.x;
-    TileDesc nxt = cur;
-    if (tile_next < p.n_tiles) nxt = p.tiles[tile_next];
+  int tile = blockIdx.x;
+  if (tile < p.n_tiles) cur = p.tiles[tile];
+  while (tile < p.n_tiles) {
+    if (tid == 0) next_tile_s = (int)gridDim.x + atomicAdd(p.next_tile, 1);
     const int utt = cur.utt, row0 = cur.row0, nrow = cur.nrow, T = cur.T, f_lo = cur.f_lo, F = cur.F;
     const long long g0 = cur.g0;
     const int a_off = (int)((wave_mis + (unsigned)(g0 & 3)) & 3);
@@ -624,6 +626,9 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
       }
     }
     __syncthreads();
+    const int tile_next = next_tile_s;   // rewritten by thread 0 only after the next barrier
+    TileDesc nxt = cur;
+    if (tile_next < p.n_tiles) nxt = p.tiles[tile_next];
 
     // ---- pull the next tile's samples into L2 while this tile computes (one prefetch per 128-byte line)
     if (tile_next < p.n_tiles) {
@@ -669,6 +674,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
       }
     }
     cur = nxt;
+    tile = tile_next;
     // no barrier here: the next tile's staging only writes e_s / x0_s / xl_s, whose last readers finished before the
     // barrier above, and logmel_s is not written again before the barrier that follows the next staging.
   }
