@@ -11,20 +11,24 @@ namespace b200fe {
 
 // pad_sequence(padding_value=0.0) (VF:163-166): rows [n_rows[u], rows_cap) of every utterance are zeroed, and
 // feat_lens[u] = n_rows[u] (VF:160).  grid = (chunks, batch).
-__global__ void pad_rows_kernel(const UttDesc* utts, float* feats, long long rows_cap, int D, long long* feat_lens) {
-  const int u = blockIdx.y;
+__device__ __forceinline__ void pad_rows_block(const UttDesc* utts, float* feats, long long rows_cap, int D,
+                                               long long* feat_lens, int u, int bx, int nbx) {
   const int n_rows = utts[u].n_rows;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && feat_lens) feat_lens[u] = n_rows;
+  if (bx == 0 && threadIdx.x == 0 && feat_lens) feat_lens[u] = n_rows;
   float* base = feats + ((long long)u * rows_cap + n_rows) * D;
   const long long total = (rows_cap - n_rows) * (long long)D;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)nbx * blockDim.x;
+  const long long i0 = (long long)bx * blockDim.x + threadIdx.x;
   if ((D & 3) == 0) {  // row starts stay 16-byte aligned
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long i = i0; i < (total >> 2); i += stride) stg_stream4(base + 4 * i, z);
   } else {
     for (long long i = i0; i < total; i += stride) base[i] = 0.f;
   }
+}
+
+__global__ void pad_rows_kernel(const UttDesc* utts, float* feats, long long rows_cap, int D, long long* feat_lens) {
+  pad_rows_block(utts, feats, rows_cap, D, feat_lens, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 // WavFrontend.forward_lfr_cmvn (VF:198-218): out[u, i, j*M + d] = (in[u, clamp(n*i + j - left, 0, T-1), d] + shift) * scale
@@ -173,11 +177,8 @@ __global__ void pcm16_to_float_kernel(const short* src, int n, float* dst) {
 
 // Expands the per-utterance descriptors into the launch-wide quad list of the warp kernel: quad q of utterance u covers
 // frames 4 (q - quad_begin[u]) .. +3.  One thread per quad; utterances without frames own no quads.
-__global__ void build_quads_kernel(const UttDesc* utts, int batch, int n_quads, int S, int lfr_m, int lfr_n, int M,
-                                   QuadDesc* quads, int* next_quad) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q == 0) *next_quad = 0;   // the warp kernel's work counter
-  if (q >= n_quads) return;
+__device__ __forceinline__ void build_quad(const UttDesc* utts, int batch, int q, int S, int lfr_m, int lfr_n, int M,
+                                           QuadDesc* quads) {
   int lo = 0, hi = batch - 1;
   while (lo < hi) {   // last utterance whose quad_begin <= q (empty utterances share the next one's quad_begin)
     const int mid = (lo + hi + 1) >> 1;
@@ -200,6 +201,21 @@ __global__ void build_quads_kernel(const UttDesc* utts, int batch, int n_quads, 
   }
   d.nF = nF | (slow << 8);
   quads[q] = d;
+}
+
+// One launch in front of the warp kernel: blocks [0, quad_blocks) build the quad list (latency-bound: a binary search
+// per quad) while blocks [quad_blocks, quad_blocks + pad_bx * batch) clear the padding rows (bandwidth-bound).
+__global__ void prep_warp_kernel(const UttDesc* utts, int batch, int n_quads, int quad_blocks, int S, int lfr_m, int lfr_n,
+                                 int M, QuadDesc* quads, int* next_quad, float* feats, long long rows_cap,
+                                 long long* feat_lens, int pad_bx) {
+  if ((int)blockIdx.x < quad_blocks) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) *next_quad = 0;   // the warp kernel's work counter
+    if (q < n_quads) build_quad(utts, batch, q, S, lfr_m, lfr_n, M, quads);
+  } else {
+    const int b = blockIdx.x - quad_blocks;
+    pad_rows_block(utts, feats, rows_cap, lfr_m * M, feat_lens, b / pad_bx, b % pad_bx, pad_bx);
+  }
 }
 
 // Counter-based synthetic PCM, bit-identical to toolbox_for_asr_and_tts_b200/synth.py::uniform_pcm.

@@ -679,23 +679,25 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   if (pcm16 && !use_warp)
     return fail(h, B200FE_E_UNSUPPORTED, "int16 input is implemented in the warp kernel only (no statistics pass, "
                                          "frame shifts whose quad fits its buffer)");
+  const long long per_utt = rows_cap * (long long)h->D / 4;
+  int gx = (int)((per_utt + 256 * 8 - 1) / (256 * 8));
+  gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
   if (use_warp && pl.n_quads > 0) {
-    build_quads_kernel<<<(pl.n_quads + 255) / 256, 256, 0, st>>>(d_utts, batch, pl.n_quads, h->S, h->cfg.lfr_m,
-                                                                 h->cfg.lfr_n, h->cfg.n_mels, d_quads, d_counter);
+    // 1. one launch: quad list (+ work counter) and padding rows + feat_lens
+    const int qb = (pl.n_quads + 255) / 256;
+    prep_warp_kernel<<<qb + gx * batch, 256, 0, st>>>(d_utts, batch, pl.n_quads, qb, h->S, h->cfg.lfr_m, h->cfg.lfr_n,
+                                                      h->cfg.n_mels, d_quads, d_counter, feats_dev, rows_cap,
+                                                      (long long*)feat_lens_dev, gx);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
-  } else if (pl.n_tiles > 0) {
-    build_tiles_kernel<<<(pl.n_tiles + 255) / 256, 256, 0, st>>>(d_utts, batch, pl.n_tiles, h->rows_per_tile, h->cfg.lfr_m,
-                                                                 h->cfg.lfr_n, h->S, d_tiles, d_counter);
-    CUDA_TRY(h, cudaGetLastError());
-    h->launches++;
-  }
-
-  // 1. padding rows + feat_lens
-  {
-    const long long per_utt = rows_cap * (long long)h->D / 4;
-    int gx = (int)((per_utt + 256 * 8 - 1) / (256 * 8));
-    gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
+  } else {
+    if (pl.n_tiles > 0) {
+      build_tiles_kernel<<<(pl.n_tiles + 255) / 256, 256, 0, st>>>(d_utts, batch, pl.n_tiles, h->rows_per_tile, h->cfg.lfr_m,
+                                                                   h->cfg.lfr_n, h->S, d_tiles, d_counter);
+      CUDA_TRY(h, cudaGetLastError());
+      h->launches++;
+    }
+    // 1. padding rows + feat_lens
     pad_rows_kernel<<<dim3(gx, batch), 256, 0, st>>>(d_utts, feats_dev, rows_cap, h->D, (long long*)feat_lens_dev);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
