@@ -166,6 +166,15 @@ size_t b200fe_audio_stats_workspace(int batch);
 int b200fe_audio_stats(const float* wave_dev, const int64_t* offsets_dev, int64_t row_stride, const int64_t* lengths_dev,
                        int batch, int64_t max_length, float clip_level, double* out_dev, void* workspace_dev,
                        size_t workspace_bytes, void* stream);
+/* base64_to_audio_np after the WAV header (R:voice_interface.py:1004-1034): wire PCM (sample_width 1 = uint8, 2 = int16,
+ * 4 = int32; interleaved channels) -> float32 mono at dst_rate: width normalisation, channel mean and - when the rates
+ * differ - the linear-interpolation resampling of its numpy branch (np.interp over np.linspace), in float64 and the
+ * reference's operation order, so the float32 output is bit-identical to numpy's.  (The scipy.signal.resample branch is
+ * a whole-signal FFT of arbitrary length and is not implemented.)  n_frames_in counts sample FRAMES (all channels);
+ * b200fe_ingest_length gives the output length, int(n * dst_rate / src_rate). */
+int64_t b200fe_ingest_length(int64_t n_frames_in, int src_rate, int dst_rate);
+int b200fe_ingest_pcm(const void* pcm_dev, int sample_width, int channels, int64_t n_frames_in, int src_rate, int dst_rate,
+                      float* out_dev, int64_t out_capacity, void* stream);
 /* Kaldi subtract_mean (TA:642-644, _subtract_column_mean), i.e. the utterance mean normalisation of the CAM++
  * speaker-verification features (R:voice_interface.py:2430,2520,2558), in place on [batch, rows_cap, dim] features:
  * feats[u, t, :] -= mean over t < n_rows[u]. */

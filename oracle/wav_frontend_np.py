@@ -241,3 +241,25 @@ def audio_statistics(audio: np.ndarray, clip_level: float = 0.999) -> np.ndarray
 def subtract_column_mean(feats: np.ndarray) -> np.ndarray:
     """TA:642-644 (_subtract_column_mean): mean over frames, per mel bin."""
     return (feats - feats.mean(axis=0, keepdims=True)).astype(feats.dtype)
+
+
+def ingest_pcm(raw: np.ndarray, channels: int, src_rate: int, dst_rate: int = 16000) -> np.ndarray:
+    """R:voice-service/app/services/voice_interface.py:1004-1034 (base64_to_audio_np after the WAV header), with the numpy
+    (np.interp) resampling branch of :1029-1034.  raw: uint8 / int16 / int32 interleaved samples."""
+    if raw.dtype == np.uint8:
+        audio = (raw - 128) / 128.0          # :1007, uint8 arithmetic wraps exactly as upstream's does
+    elif raw.dtype == np.int16:
+        audio = raw / 32768.0                # :1010
+    elif raw.dtype == np.int32:
+        audio = raw / 2147483648.0           # :1013
+    else:
+        raise ValueError(f"unsupported sample width: {raw.dtype}")
+    if channels > 1:
+        audio = np.mean(audio.reshape(-1, channels), axis=1)     # :1019
+    if src_rate != dst_rate:
+        old_length = len(audio)
+        new_length = int(old_length * dst_rate / src_rate)
+        old_indices = np.linspace(0, old_length - 1, old_length)
+        new_indices = np.linspace(0, old_length - 1, new_length)
+        audio = np.interp(new_indices, old_indices, audio)        # :1031-1034
+    return audio.astype(np.float32)                                # :1045

@@ -619,3 +619,19 @@ def test_fsmn_vad_frontend_against_funasr_golden(variants_golden):
     g = variants_golden["vad_5_1_feats"]
     assert int(fl[0]) == g.shape[0]
     assert_feats_close(feats[0], g, cm)
+
+
+@pytest.mark.parametrize("dtype,channels,src", [(np.int16, 1, 16000), (np.int16, 2, 48000), (np.int16, 1, 8000),
+                                                (np.int16, 1, 44100), (np.int32, 2, 22050), (np.uint8, 1, 16000),
+                                                (np.uint8, 3, 32000)])
+def test_ingest_pcm_is_bit_identical_to_numpy(dtype, channels, src):
+    """wire PCM -> float32 mono 16 kHz (R:voice_interface.py:1004-1034, numpy resampling branch)."""
+    rng = np.random.default_rng(int(src) + channels)
+    info = np.iinfo(dtype)
+    for n in (1, 2, 7, 1600, 44101):
+        raw = rng.integers(info.min, info.max, size=n * channels, dtype=dtype, endpoint=True)
+        ref = wf.ingest_pcm(raw, channels, src)
+        t = torch.from_numpy(raw.view(np.uint8) if dtype == np.uint8 else raw).to(DEV)
+        got = WavFrontend.ingest_pcm(t, channels=channels, src_rate=src).cpu().numpy()
+        assert got.dtype == np.float32 and got.shape == ref.shape, (n, got.shape, ref.shape)
+        assert np.array_equal(got, ref), (n, np.abs(got - ref).max() if got.size else 0)

@@ -1,6 +1,8 @@
 // By-products of the front-end pass that the reference computes on the host around its funasr calls:
 //   * audio_stats_kernel   _log_audio_statistics / the per-chunk energy gate (R:voice-service/app/services/
 //                          voice_interface.py:873-939, 1298-1300, 1569-1570): max, min, mean |x|, RMS, clipping ratio
+//   * ingest_pcm_kernel    base64_to_audio_np after the WAV header (R:voice_interface.py:1004-1034): sample width
+//                          normalisation, channel mean, linear-interpolation resampling (its numpy branch), float32
 //   * column_mean_kernel   Kaldi subtract_mean (TA:642-644, _subtract_column_mean) = the utterance mean
 //                          normalisation of the CAM++ speaker-verification features (R:voice_interface.py:2430,2520,2558)
 #pragma once
@@ -86,6 +88,46 @@ __global__ void audio_stats_final_kernel(const AudioStatsAcc* acc, const long lo
   o[3] = sqrt(acc[u].sum_sq / (double)n);
   o[4] = (double)acc[u].n_clip / (double)n;
   o[5] = fmax(fabs(mx), fabs(mn));
+}
+
+// Wire PCM -> float32 mono at the target rate, in the reference's float64 arithmetic and operation order so that the
+// float32 result is bit-identical to numpy's (R:voice_interface.py:1004-1034):
+//   width 1: ((u8 - 128) mod 256) / 128.0   (uint8 arithmetic wraps in numpy, :1007)      width 2: s16 / 32768.0
+//   width 4: s32 / 2147483648.0             channels: np.mean(x.reshape(-1, ch), axis=1) = sequential sum / ch
+//   resample: np.interp(np.linspace(0, n-1, m), np.arange(n), x): x_i = i * step, last = n - 1 exactly,
+//             y = (x[j+1] - x[j]) * (x_i - j) + x[j] with separate multiply and add (no contraction).
+__device__ __forceinline__ double ingest_mono(const void* pcm, int width, int channels, long long k) {
+  double acc = 0.0;
+  for (int c = 0; c < channels; ++c) {
+    const long long i = k * channels + c;
+    double v;
+    if (width == 1) v = (double)(unsigned char)(static_cast<const unsigned char*>(pcm)[i] - 128u) / 128.0;
+    else if (width == 2) v = (double)static_cast<const short*>(pcm)[i] / 32768.0;
+    else v = (double)static_cast<const int*>(pcm)[i] / 2147483648.0;
+    acc = c == 0 ? v : __dadd_rn(acc, v);
+  }
+  return channels > 1 ? acc / (double)channels : acc;
+}
+
+__global__ void ingest_pcm_kernel(const void* pcm, int width, int channels, long long n_in, long long n_out, double step,
+                                  float* out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (long long)gridDim.x * blockDim.x) {
+    double y;
+    if (n_out == n_in && step == 1.0) {
+      y = ingest_mono(pcm, width, channels, i);
+    } else {
+      // np.linspace: the last point is `stop` exactly - unless it is the only point, which is `start`
+      const double x = (i == n_out - 1 && n_out > 1) ? (double)(n_in - 1) : __dmul_rn((double)i, step);
+      long long j = (long long)x;                 // x >= 0: truncation = floor
+      if (j >= n_in - 1) {
+        y = ingest_mono(pcm, width, channels, n_in - 1);
+      } else {
+        const double f0 = ingest_mono(pcm, width, channels, j), f1 = ingest_mono(pcm, width, channels, j + 1);
+        y = (double)j == x ? f0 : __dadd_rn(__dmul_rn(__dadd_rn(f1, -f0), __dadd_rn(x, -(double)j)), f0);
+      }
+    }
+    out[i] = (float)y;
+  }
 }
 
 // feats[u, t, d] -= mean_t feats[u, :T_u, d]  (TA:642-644).  One CTA per (utterance, 32 columns): 8 row-lanes x 32

@@ -20,6 +20,29 @@ int b200fe_audio_stats(const float* wave_dev, const int64_t* offsets_dev, int64_
   return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
 }
 
+int64_t b200fe_ingest_length(int64_t n_frames_in, int src_rate, int dst_rate) {
+  if (n_frames_in < 0 || src_rate <= 0 || dst_rate <= 0) return B200FE_E_INVALID;
+  if (src_rate == dst_rate) return n_frames_in;
+  return (int64_t)((double)(n_frames_in * (int64_t)dst_rate) / (double)src_rate);   // int(len * 16000 / orig_sr), :1026
+}
+
+int b200fe_ingest_pcm(const void* pcm_dev, int sample_width, int channels, int64_t n_frames_in, int src_rate, int dst_rate,
+                      float* out_dev, int64_t out_capacity, void* stream) {
+  if (!pcm_dev || !out_dev || channels < 1 || (sample_width != 1 && sample_width != 2 && sample_width != 4))
+    return B200FE_E_INVALID;
+  const int64_t n_out = b200fe_ingest_length(n_frames_in, src_rate, dst_rate);
+  if (n_out < 0 || n_out > out_capacity) return B200FE_E_INVALID;
+  if (n_out == 0) return B200FE_OK;
+  if (n_frames_in < 1) return B200FE_E_INVALID;
+  // np.linspace(0, n-1, m): step = (n-1)/(m-1) (m == 1: the single point is 0)
+  const double step = src_rate == dst_rate ? 1.0 : (n_out > 1 ? (double)(n_frames_in - 1) / (double)(n_out - 1) : 0.0);
+  long long blocks = (n_out + 255) / 256;
+  blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
+  ingest_pcm_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pcm_dev, sample_width, channels, n_frames_in,
+                                                                         src_rate == dst_rate ? n_frames_in : n_out, step, out_dev);
+  return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
+}
+
 int b200fe_subtract_column_mean(float* feats_dev, int64_t rows_cap, int dim, const int64_t* n_rows_dev, int batch,
                                 void* stream) {
   if (batch == 0) return B200FE_OK;

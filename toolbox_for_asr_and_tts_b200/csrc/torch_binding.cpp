@@ -312,6 +312,28 @@ at::Tensor fe_audio_stats(const at::Tensor& wave, const c10::optional<at::Tensor
   return out;
 }
 
+// pcm: CUDA uint8 / int16 / int32, interleaved channels -> float32 mono at dst_rate
+at::Tensor fe_ingest_pcm(const at::Tensor& pcm, int64_t channels, int64_t src_rate, int64_t dst_rate) {
+  TORCH_CHECK(pcm.is_cuda(), "b200fe.ingest_pcm: PCM must be a CUDA tensor");
+  int width = 0;
+  if (pcm.scalar_type() == at::kByte) width = 1;
+  else if (pcm.scalar_type() == at::kShort) width = 2;
+  else if (pcm.scalar_type() == at::kInt) width = 4;
+  TORCH_CHECK(width != 0, "b200fe.ingest_pcm: PCM must be uint8, int16 or int32");
+  TORCH_CHECK(channels >= 1 && pcm.numel() % channels == 0, "b200fe.ingest_pcm: element count is not a multiple of the channel count");
+  c10::cuda::CUDAGuard guard(pcm.device());
+  auto x = pcm.contiguous();
+  const int64_t n_in = x.numel() / channels;
+  const int64_t n_out = b200fe_ingest_length(n_in, (int)src_rate, (int)dst_rate);
+  TORCH_CHECK(n_out >= 0, "b200fe.ingest_pcm: bad sample rates");
+  auto out = at::empty({n_out}, x.options().dtype(at::kFloat));
+  if (n_out == 0) return out;
+  int rc = b200fe_ingest_pcm(x.data_ptr(), width, (int)channels, n_in, (int)src_rate, (int)dst_rate, out.data_ptr<float>(),
+                             n_out, cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_ingest_pcm failed (", rc, ")");
+  return out;
+}
+
 void fe_subtract_column_mean(at::Tensor feats, const at::Tensor& n_rows) {
   TORCH_CHECK(feats.is_cuda() && feats.scalar_type() == at::kFloat && feats.dim() == 3 && feats.is_contiguous(),
               "b200fe.subtract_column_mean: features must be a contiguous CUDA float32 [B, T, D] tensor");
@@ -360,6 +382,7 @@ TORCH_LIBRARY(b200fe, m) {
   m.def("tts_forward(int t, Tensor wave, Tensor? offsets, Tensor lengths, int hop, int n_mels) -> (Tensor, Tensor)", tts_forward);
   m.def("audio_stats(Tensor wave, Tensor? offsets, Tensor lengths, float clip_level) -> Tensor", fe_audio_stats);
   m.def("subtract_column_mean(Tensor(a!) feats, Tensor n_rows) -> ()", fe_subtract_column_mean);
+  m.def("ingest_pcm(Tensor pcm, int channels, int src_rate, int dst_rate) -> Tensor", fe_ingest_pcm);
   m.def("launch_count(int h) -> int", fe_launch_count);
   m.def("select_kernel(int h, int which) -> ()", fe_select_kernel);
   m.def("profile_enable(int h, bool on) -> ()", fe_profile_enable);

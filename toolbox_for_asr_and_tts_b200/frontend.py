@@ -209,6 +209,15 @@ class WavFrontend(nn.Module):
         return _native.ops().audio_stats(wave.to(torch.float32), None if offsets is None else _as_length_tensor(offsets),
                                          _as_length_tensor(lengths), float(clip_level))
 
+    @staticmethod
+    def ingest_pcm(pcm: torch.Tensor, channels: int = 1, src_rate: int = 16000, dst_rate: int = 16000) -> torch.Tensor:
+        """Wire PCM (CUDA uint8 / int16 / int32, interleaved channels) -> float32 mono at dst_rate, exactly as the
+        reference's base64_to_audio_np does after the WAV header (R:voice_interface.py:1004-1034: width normalisation,
+        channel mean, np.interp resampling - its numpy branch), bit-identical to numpy."""
+        WavFrontend._check_cuda(pcm, "pcm")
+        from . import _native
+        return _native.ops().ingest_pcm(pcm, int(channels), int(src_rate), int(dst_rate))
+
     # ------------------------------------------------------------------ extras used by tests / tools
     def frame_counts(self, input_lengths) -> Tuple[torch.Tensor, torch.Tensor]:
         """(frames, LFR rows) per utterance, as the reference would produce (TA:65-70, VF:43)."""
