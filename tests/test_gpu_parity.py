@@ -635,3 +635,15 @@ def test_ingest_pcm_is_bit_identical_to_numpy(dtype, channels, src):
         got = WavFrontend.ingest_pcm(t, channels=channels, src_rate=src).cpu().numpy()
         assert got.dtype == np.float32 and got.shape == ref.shape, (n, got.shape, ref.shape)
         assert np.array_equal(got, ref), (n, np.abs(got - ref).max() if got.size else 0)
+
+
+def test_handles_follow_the_tensor_device(cmvn):
+    """One front-end object used from two GPUs of a box: the native tables are per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fe = make_fe(cmvn)
+    x = torch.from_numpy(synth.uniform_pcm(SEED, 16000, 16000))[None]
+    a, la = fe(x.to("cuda:0"), [16000])
+    b, lb = fe(x.to("cuda:1"), [16000])
+    assert b.device.index == 1 and lb.device.index == 1
+    assert torch.equal(a.cpu(), b.cpu()) and torch.equal(la.cpu(), lb.cpu())

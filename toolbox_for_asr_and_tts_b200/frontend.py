@@ -106,22 +106,32 @@ class WavFrontend(nn.Module):
         return self.n_mels * self.lfr_m
 
     # ------------------------------------------------------------------ native handles
-    def _handle(self, lfr: bool, cmvn: bool, fbank_only_cfg: bool = False) -> _Handle:
-        key = (lfr, cmvn, fbank_only_cfg)
+    def _handle(self, lfr: bool, cmvn: bool, fbank_only_cfg: bool = False, device=None) -> _Handle:
+        """One native handle per (configuration, CUDA device): its tables live on the device it was created on."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: the B200 front-end has no CPU fallback")
+        dev = torch.cuda.current_device() if device is None else torch.device(device).index
+        if dev is None:
+            dev = torch.cuda.current_device()
+        key = (lfr, cmvn, fbank_only_cfg, dev)
         if key not in self._handles:
-            self._handles[key] = _Handle(
-                fs=int(self.fs), frame_length=float(self.frame_length), frame_shift=float(self.frame_shift),
-                n_mels=int(self.n_mels), window_type=WINDOW_TYPES[self.window],
-                lfr_m=int(self.lfr_m) if lfr else 1, lfr_n=int(self.lfr_n) if lfr else 1,
-                dither=float(self.dither), snip_edges=bool(self.snip_edges),
-                upscale=True if fbank_only_cfg else bool(self.upsacle_samples),
-                preemph=self.preemphasis_coefficient, remove_dc=self.remove_dc_offset, low_freq=self.low_freq,
-                high_freq=self.high_freq, blackman_coeff=self.blackman_coeff,
-                cmvn=self.cmvn if (cmvn and self.cmvn is not None) else None)
+            with torch.cuda.device(dev):
+                self._handles[key] = self._new_handle(lfr, cmvn, fbank_only_cfg)
             code = getattr(self, "_kernel_code", 0)
             if code:
                 self._handles[key].ops.select_kernel(self._handles[key].h, code)
         return self._handles[key]
+
+    def _new_handle(self, lfr: bool, cmvn: bool, fbank_only_cfg: bool) -> _Handle:
+        return _Handle(
+            fs=int(self.fs), frame_length=float(self.frame_length), frame_shift=float(self.frame_shift),
+            n_mels=int(self.n_mels), window_type=WINDOW_TYPES[self.window],
+            lfr_m=int(self.lfr_m) if lfr else 1, lfr_n=int(self.lfr_n) if lfr else 1,
+            dither=float(self.dither), snip_edges=bool(self.snip_edges),
+            upscale=True if fbank_only_cfg else bool(self.upsacle_samples),
+            preemph=self.preemphasis_coefficient, remove_dc=self.remove_dc_offset, low_freq=self.low_freq,
+            high_freq=self.high_freq, blackman_coeff=self.blackman_coeff,
+            cmvn=self.cmvn if (cmvn and self.cmvn is not None) else None)
 
     def launch_count(self) -> int:
         return sum(int(h.ops.launch_count(h.h)) for h in self._handles.values())
@@ -154,7 +164,7 @@ class WavFrontend(nn.Module):
         """VF:128-168.  input: float32 [B, Nmax] in [-1, 1]; returns ([B, max T_lfr, n_mels*lfr_m], int64 [B])."""
         self._check_cuda(input, "input")
         lens = _as_length_tensor(input_lengths)
-        h = self._handle(lfr=True, cmvn=True)
+        h = self._handle(lfr=True, cmvn=True, device=input.device)
         self._calls += 1
         feats, feat_lens = h.ops.forward(h.h, self._pcm(input), None, lens, 0, kwargs.get("stats"),
                                          int(self.dither_seed + self._calls))
@@ -174,7 +184,7 @@ class WavFrontend(nn.Module):
         Same outputs as `forward`.  `stats` (CUDA float64 [2*D+1]) accumulates global CMVN statistics of the
         un-normalised LFR features."""
         self._check_cuda(wave, "wave")
-        h = self._handle(lfr=True, cmvn=True)
+        h = self._handle(lfr=True, cmvn=True, device=wave.device)
         self._calls += 1
         return h.ops.forward(h.h, self._pcm(wave), _as_length_tensor(offsets), _as_length_tensor(lengths), int(rows_cap),
                              stats, int(self.dither_seed + self._calls))
@@ -182,7 +192,7 @@ class WavFrontend(nn.Module):
     def forward_fbank(self, input: torch.Tensor, input_lengths) -> Tuple[torch.Tensor, torch.Tensor]:
         """VF:170-196: Kaldi fbank only (always upscaled by 2^15 upstream), zero-padded, lengths int64."""
         self._check_cuda(input, "input")
-        h = self._handle(lfr=False, cmvn=False, fbank_only_cfg=True)
+        h = self._handle(lfr=False, cmvn=False, fbank_only_cfg=True, device=input.device)
         self._calls += 1
         feats, feat_lens = h.ops.forward(h.h, self._pcm(input), None, _as_length_tensor(input_lengths), 0, None,
                                          int(self.dither_seed + self._calls))
@@ -194,7 +204,7 @@ class WavFrontend(nn.Module):
         """VF:198-218: LFR + CMVN of given [B, T, n_mels] features."""
         self._check_cuda(input, "input")
         lens = _as_length_tensor(input_lengths)
-        h = self._handle(lfr=True, cmvn=True)
+        h = self._handle(lfr=True, cmvn=True, device=input.device)
         feats, feat_lens = h.ops.lfr_cmvn(h.h, input.to(torch.float32), lens)
         rows = int(-(-int(lens.max()) // self.lfr_n)) if lens.numel() else 0
         return feats[:, :rows], feat_lens
