@@ -27,7 +27,7 @@ class StreamPool:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("StreamPool state must live on a CUDA device (no CPU fallback)")
-        self._h = frontend._handle(lfr=True, cmvn=True)
+        self._h = frontend._handle(lfr=True, cmvn=True, device=self.device)
         ops = self._h.ops
         self.state = ops.stream_state(self._h.h, self.n_streams, self.max_chunk, self.device)
         self.rows_cap = int(ops.stream_max_rows(self._h.h, self.max_chunk))

@@ -22,20 +22,24 @@ class TtsLogMel(nn.Module):
         self.sample_rate, self.n_fft, self.hop_length, self.n_mels = sample_rate, n_fft, hop_length, n_mels
         self.f_min, self.f_max = f_min, f_max
         self._ops = None
-        self._h = 0
+        self._hs = {}      # one native handle per CUDA device (its tables live there)
 
-    def _handle(self):
-        if not self._h:
+    def _handle(self, device):
+        dev = torch.device(device).index
+        if dev is None:
+            dev = torch.cuda.current_device()
+        if dev not in self._hs:
             self._ops = _native.ops()
-            self._h = self._ops.tts_create(self.sample_rate, self.n_fft, self.hop_length, self.n_mels, float(self.f_min),
-                                           float(self.f_max))
-        return self._h
+            with torch.cuda.device(dev):
+                self._hs[dev] = self._ops.tts_create(self.sample_rate, self.n_fft, self.hop_length, self.n_mels,
+                                                     float(self.f_min), float(self.f_max))
+        return self._hs[dev]
 
     def __del__(self):
         try:
-            if self._h:
-                self._ops.tts_destroy(self._h)
-                self._h = 0
+            for h in self._hs.values():
+                self._ops.tts_destroy(h)
+            self._hs = {}
         except Exception:
             pass
 
@@ -46,6 +50,6 @@ class TtsLogMel(nn.Module):
         """waveform: CUDA float32 [B, Nmax] in [-1, 1]; returns (mel [B, n_mels, max_frames], frames int64 [B])."""
         if not isinstance(waveform, torch.Tensor) or not waveform.is_cuda:
             raise RuntimeError("waveform must be a CUDA tensor: the B200 front-end has no CPU fallback")
-        h = self._handle()
+        h = self._handle(waveform.device)
         return self._ops.tts_forward(h, waveform.to(torch.float32), None, _as_length_tensor(lengths), self.hop_length,
                                      self.n_mels)
