@@ -647,3 +647,46 @@ def test_handles_follow_the_tensor_device(cmvn):
     b, lb = fe(x.to("cuda:1"), [16000])
     assert b.device.index == 1 and lb.device.index == 1
     assert torch.equal(a.cpu(), b.cpu()) and torch.equal(la.cpu(), lb.cpu())
+
+
+def test_ten_minute_utterance_matches_oracle_on_excerpts(cmvn):
+    """Large indices: one 10-minute utterance (59 998 frames, 10 000 rows) next to a short one.  Frames depend on local
+    samples only and LFR rows on 7 neighbouring frames, so an excerpt that starts on a multiple of 6 frames reproduces
+    the interior rows of the long utterance: compared with the oracle on three excerpts (start, middle, end)."""
+    fe = make_fe(cmvn)
+    n = 9_600_000
+    w = synth.uniform_pcm(101, 0, n)
+    feats, fl = fe(dense_batch([w, w[:16000]]), [n, 16000])
+    T = 1 + (n - 400) // 160
+    assert int(fl[0]) == -(-T // 6) == 10000 and int(fl[1]) == 17
+    assert not feats[1, 17:].any()
+    for row0 in (0, 5000, 10000 - 40):
+        f0 = 6 * row0                                   # first frame of the excerpt = a multiple of lfr_n
+        a = f0 * 160
+        ex = w[a:a + 6 * 40 * 160 + 400 + 6 * 160]      # 46 rows worth of frames
+        ref, rl = wf.frontend_forward([ex], [len(ex)], cmvn=cmvn, **PARAFORMER)
+        lo = 1 if row0 > 0 else 0                       # the excerpt's first row replicates ITS first frame
+        hi = 38                                         # ... and its last rows replicate its last frame
+        if row0 + hi > 10000:
+            hi = 10000 - row0
+        assert_feats_close(feats[0, row0 + lo:row0 + hi], ref[0, lo:hi], cmvn)
+    # the very last rows of the long utterance (right replication) against an excerpt that ends where it ends
+    tail_frames = 6 * 30 + (T - 1) % 6 + 1
+    a = (T - tail_frames) * 160
+    assert (T - tail_frames) % 6 == 0
+    ref, rl = wf.frontend_forward([w[a:]], [n - a], cmvn=cmvn, **PARAFORMER)
+    k = int(rl[0])
+    assert_feats_close(feats[0, 10000 - k + 1:10000], ref[0, 1:k], cmvn)
+
+
+def test_empty_and_degenerate_batches(cmvn):
+    fe = make_fe(cmvn)
+    with pytest.raises(RuntimeError, match="empty list of sequences"):      # pad_sequence's error upstream (VF:163)
+        fe(torch.zeros(0, 16000, device=DEV), [])
+    # a batch made only of utterances shorter than one frame, and one with a single frame exactly
+    lens = [399, 320, 400]
+    waves = [synth.uniform_pcm(7, i, k) for i, k in enumerate(lens)]
+    got, gl = fe(dense_batch(waves), lens)
+    ref, rl = wf.frontend_forward(waves, lens, cmvn=cmvn, **PARAFORMER)
+    assert np.array_equal(gl.cpu().numpy(), rl) and got.shape == ref.shape
+    assert_feats_close(got, ref, cmvn)

@@ -87,6 +87,7 @@ std::tuple<at::Tensor, at::Tensor> fe_forward(int64_t h, const at::Tensor& wave,
   auto w = wave.contiguous();
   auto len = lengths.to(at::kCPU, at::kLong).contiguous();
   const int b = (int)len.numel();
+  TORCH_CHECK(b > 0, "received an empty list of sequences");   // what pad_sequence raises upstream (VF:163)
   at::Tensor off;
   const int64_t* off_ptr = nullptr;
   int64_t row_stride = 0;
