@@ -128,16 +128,40 @@ __device__ __forceinline__ void stg_stream4(float* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// counter-based N(0,1) for dither: one value per (utterance, absolute frame, sample-in-frame), cf. TA:179-181
-__device__ __forceinline__ float dither_normal(unsigned long long seed, unsigned utt, unsigned frame, unsigned n) {
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)utt + 1) +
-                         0xD1B54A32D192ED03ull * ((unsigned long long)frame * 1024ull + n);
+// Counter-based N(0,1) for dither, cf. TA:179-181 (independent noise per (frame, sample)): one Box-Muller pair per
+// (utterance, frame PAIR, sample-in-frame) - the cosine branch belongs to the even frame 2k, the sine branch to 2k+1 -
+// so a thread that transforms frames (fa, fa+1) needs one hash / log / sqrt / sincos per sample when fa is even.
+__device__ __forceinline__ unsigned mix32(unsigned x) {   // 32-bit avalanche (two multiply / xorshift rounds)
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+// salt of one (seed, utterance): the 64-bit mixing is done once per call site, not per sample
+__device__ __forceinline__ unsigned dither_salt(unsigned long long seed, unsigned utt) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)utt + 1);
   z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
   z ^= z >> 27; z *= 0x94D049BB133111EBull;
   z ^= z >> 31;
-  const float u1 = ((unsigned)(z >> 40) + 1u) * (1.0f / 16777216.0f);  // (0, 1]
-  const float u2 = (unsigned)(z & 0xFFFFFFu) * (1.0f / 16777216.0f);  // [0, 1)
-  return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530717958647692f * u2);
+  return (unsigned)z ^ (unsigned)(z >> 32);
+}
+__device__ __forceinline__ float2 dither_bm(unsigned salt, unsigned frame_pair, unsigned n) {
+  const unsigned k1 = mix32((frame_pair * 1024u + n) ^ salt);
+  const unsigned k2 = mix32(k1 ^ 0x9E3779B9u);
+  const float u1 = ((k1 >> 8) + 1u) * (1.0f / 16777216.0f);  // (0, 1]
+  const float u2 = (k2 >> 8) * (1.0f / 16777216.0f);         // [0, 1)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+  float sn, cs;
+  __sincosf(6.28318530717958647692f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+// noise of frames (fa, fa + 1) at sample n, as the two lanes of an f2
+__device__ __forceinline__ float2 dither_pair(unsigned salt, unsigned fa, unsigned n) {
+  const float2 p0 = dither_bm(salt, fa >> 1, n);
+  if ((fa & 1u) == 0u) return p0;                       // warp-uniform: fa is the same for the whole group
+  const float2 p1 = dither_bm(salt, (fa >> 1) + 1u, n);
+  return make_float2(p0.y, p1.x);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -315,20 +339,33 @@ __device__ __forceinline__ void quad_stage1(const float* eA, f2 x0, f2 xl, bool 
       }
     }
     if constexpr (DITHER) {
-      // x'[n] = x[n] + dither*g(frame, n)  (TA:179-181: independent noise per (frame, sample));
-      // the pre-emphasised value picks up dither*(g(n) - preemph*g(n-1))
+      // x'[n] = x[n] + dither*g(frame, n)  (TA:179-181); the pre-emphasised value picks up
+      // dither*(g(n) - preemph*g(n-1)).  Every thread draws the noise of its own samples once; g(n-1) is the previous
+      // lane's value of the same row (lane 15's value of the previous row for lane 0), fetched with one shuffle.
       const unsigned fa = frame_abs_a;
+      const unsigned salt = dither_salt(seed, utt);
+      const int src = (threadIdx.x & 16) | ((j + 15) & 15);
+      f2 rot_prev = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int n = 16 * (i - g) + j;
-        if (n >= 0 && n < L) {
-          const int nm = n > 0 ? n - 1 : 0;
-          if (vA) y[i].x += dither * (dither_normal(seed, utt, fa, n) - preemph * dither_normal(seed, utt, fa, nm));
-          if (vB) y[i].y += dither * (dither_normal(seed, utt, fa + 1, n) - preemph * dither_normal(seed, utt, fa + 1, nm));
+        const bool live = n >= 0 && n < L;
+        f2 gn = make_float2(0.f, 0.f);
+        if (live) gn = dither_pair(salt, fa, (unsigned)n);
+        f2 rot;
+        rot.x = __shfl_sync(0xffffffffu, gn.x, src);
+        rot.y = __shfl_sync(0xffffffffu, gn.y, src);
+        const f2 prev = n == 0 ? gn : (j == 0 ? rot_prev : rot);   // n = 0: replicate rule, g(-1) := g(0)
+        rot_prev = rot;
+        if (live) {
+          const f2 d = mul2s(fma2s(prev, -preemph, gn), dither);
+          if (vA) y[i].x += d.x;
+          if (vB) y[i].y += d.y;
         }
       }
-      if (vA) { x0.x += dither * dither_normal(seed, utt, fa, 0); xl.x += dither * dither_normal(seed, utt, fa, L - 1); }
-      if (vB) { x0.y += dither * dither_normal(seed, utt, fa + 1, 0); xl.y += dither * dither_normal(seed, utt, fa + 1, L - 1); }
+      const f2 g0 = dither_pair(salt, fa, 0u), gl = dither_pair(salt, fa, (unsigned)(L - 1));
+      if (vA) { x0.x += dither * g0.x; xl.x += dither * gl.x; }
+      if (vB) { x0.y += dither * g0.y; xl.y += dither * gl.y; }
     }
     if (j == 0) {  // replicate rule at the frame start: y[0] = x[0] - preemph * x[0]  (TA:193-198)
       const f2 yf = fma2s(x0, -preemph, x0);
