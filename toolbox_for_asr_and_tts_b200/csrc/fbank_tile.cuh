@@ -211,14 +211,15 @@ __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, 
   const int lo = (int)(word & 0xfffu), partner = (int)((word >> 12) & 31u), iv = (int)((word >> 17) & 0xffu);
   const float2* wt = mel.w + (base * 32 + lane);
   const float2* p0 = pg + lo;
-  float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = make_float4(0.f, 0.f, 0.f, 0.f);
+  // packed accumulators: (frame A, frame B) of group 0 and of group 1, as the spectra are stored
+  f2 up0 = make_float2(0.f, 0.f), up1 = up0, dn0 = up0, dn1 = up0;
   auto body = [&](int q) {
     const float2 w = __ldg(wt + 32 * q);
     const float2 s0 = p0[q], s1 = p0[256 + q];
-    up.x = fmaf(w.x, s0.x, up.x); up.y = fmaf(w.x, s0.y, up.y);
-    up.z = fmaf(w.x, s1.x, up.z); up.w = fmaf(w.x, s1.y, up.w);
-    dn.x = fmaf(w.y, s0.x, dn.x); dn.y = fmaf(w.y, s0.y, dn.y);
-    dn.z = fmaf(w.y, s1.x, dn.z); dn.w = fmaf(w.y, s1.y, dn.w);
+    up0 = fma2s(s0, w.x, up0);
+    up1 = fma2s(s1, w.x, up1);
+    dn0 = fma2s(s0, w.y, dn0);
+    dn1 = fma2s(s1, w.y, dn1);
   };
   if constexpr (CNT >= 0) {
 #pragma unroll
@@ -228,10 +229,10 @@ __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, 
     for (int q = 0; q < cnt; ++q) body(q);
   }
   // energy[filter iv] = up-slope sum of interval iv + down-slope sum of interval iv + 1 (held by the partner lane)
-  const float ex = up.x + __shfl_sync(0xffffffffu, dn.x, partner);
-  const float ey = up.y + __shfl_sync(0xffffffffu, dn.y, partner);
-  const float ez = up.z + __shfl_sync(0xffffffffu, dn.z, partner);
-  const float ew = up.w + __shfl_sync(0xffffffffu, dn.w, partner);
+  const float ex = up0.x + __shfl_sync(0xffffffffu, dn0.x, partner);
+  const float ey = up0.y + __shfl_sync(0xffffffffu, dn0.y, partner);
+  const float ez = up1.x + __shfl_sync(0xffffffffu, dn1.x, partner);
+  const float ew = up1.y + __shfl_sync(0xffffffffu, dn1.y, partner);
   if (word >> 31)
     epi(iv, fast_ln(fmaxf(ex, log_floor)), fast_ln(fmaxf(ey, log_floor)), fast_ln(fmaxf(ez, log_floor)),
         fast_ln(fmaxf(ew, log_floor)));
