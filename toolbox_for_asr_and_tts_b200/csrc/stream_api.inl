@@ -10,21 +10,22 @@ int stream_layout(const b200fe_handle* h, int n_streams, int max_chunk, StreamLa
   lay.n_mels = h->cfg.n_mels;
   nf_max = (max_chunk - 1) / h->S + 1;
   e_cap = ((h->L - 1 + max_chunk + 8) + 3) & ~3;
-  smem = stream_smem_bytes(e_cap, nf_max, lay.cache_cap, h->cfg.n_mels);
+  smem = stream_smem_bytes(e_cap, nf_max, lay.cache_cap, h->cfg.n_mels, warp_kernel_fits(h->L, h->S));
   return 0;
 }
 
 template <int NROWS, bool EXACT, class MELS>
 int launch_stream(b200fe_handle* h, const StreamParams& p, size_t smem, bool dither, cudaStream_t st) {
-  if (dither) {
-    auto k = stream_push_kernel<NROWS, EXACT, true, MELS>;
-    CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<p.n, kCtaThreads, smem, st>>>(p);
-  } else {
-    auto k = stream_push_kernel<NROWS, EXACT, false, MELS>;
-    CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<p.n, kCtaThreads, smem, st>>>(p);
-  }
+#define LAUNCHS(DI, PQ)                                                                               \
+  do {                                                                                                \
+    auto k = stream_push_kernel<NROWS, EXACT, DI, MELS, PQ>;                                          \
+    CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k<<<p.n, kCtaThreads, smem, st>>>(p);                                                             \
+  } while (0)
+  const bool per_quad = warp_kernel_fits(h->L, h->S);   // every warp fetches its own quads (3 CTAs per SM)
+  if (per_quad) { if (dither) LAUNCHS(true, true); else LAUNCHS(false, true); }
+  else          { if (dither) LAUNCHS(true, false); else LAUNCHS(false, false); }
+#undef LAUNCHS
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
   return 0;
