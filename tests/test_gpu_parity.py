@@ -690,3 +690,29 @@ def test_empty_and_degenerate_batches(cmvn):
     ref, rl = wf.frontend_forward(waves, lens, cmvn=cmvn, **PARAFORMER)
     assert np.array_equal(gl.cpu().numpy(), rl) and got.shape == ref.shape
     assert_feats_close(got, ref, cmvn)
+
+
+def test_digital_silence_and_level_changes(cmvn):
+    """Real streams contain digital silence and abrupt level changes: all-zero frames must hit the log floor exactly
+    (log(FLT_EPSILON), TA:633), frames that straddle silence / signal boundaries and very quiet segments must match the
+    oracle, and nothing may turn into NaN / Inf."""
+    rng = np.random.default_rng(3)
+    t = np.arange(8000) / 16000.0
+    parts = [np.zeros(8000), 0.001 * rng.standard_normal(8000), 0.5 * np.sin(2 * np.pi * (200 + 3000 * t) * t),
+             np.zeros(4000), (rng.integers(-3, 4, 8000) / 32768.0), np.zeros(8000)]
+    x = np.concatenate(parts).astype(np.float32)
+    fe = make_fe(cmvn)
+    feats, fl = fe(torch.from_numpy(x)[None].to(DEV), [len(x)])
+    ref, rl = wf.frontend_forward([x], [len(x)], cmvn=cmvn, **PARAFORMER)
+    got = feats[0].cpu().numpy()
+    assert int(fl[0]) == int(rl[0]) and np.isfinite(got).all()
+    sh, sc = cmvn[0].astype(np.float64), cmvn[1].astype(np.float64)
+    lg = (got.astype(np.float64) / sc - sh).reshape(-1, 7, 80)
+    lr = (ref[0].astype(np.float64) / sc - sh).reshape(-1, 7, 80)
+    floor = float(np.log(np.finfo(np.float32).eps))
+    silent = lr <= floor + 1e-6
+    assert silent.any() and np.abs(lg[silent] - floor).max() <= 1e-5      # exact zeros -> the floor on both sides
+    # everything else: the stated tolerance, except bins within a hair of the floor where log is ill-conditioned
+    ok = ~silent & (lr > floor + 3.0)
+    err = np.abs(lg - lr)
+    assert err[ok].max() <= 3e-3 and err[ok].mean() <= 2e-5
