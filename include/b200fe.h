@@ -175,6 +175,20 @@ int b200fe_audio_stats(const float* wave_dev, const int64_t* offsets_dev, int64_
 int64_t b200fe_ingest_length(int64_t n_frames_in, int src_rate, int dst_rate);
 int b200fe_ingest_pcm(const void* pcm_dev, int sample_width, int channels, int64_t n_frames_in, int src_rate, int dst_rate,
                       float* out_dev, int64_t out_capacity, void* stream);
+/* Sliding audio windows per stream, resident in HBM: replaces `buf = np.concatenate([buf, chunk])[-target:]` of the KWS
+ * window (1.6 s) and the pre-speech guard (0.4 s) (R:voice_interface.py:1304-1311, 1742-1746).  One slab holds a circular
+ * buffer of capacity_samples per stream.  push appends chunk b ([n, chunk_stride] float32, chunk_lens_dev[b] samples) to
+ * stream stream_ids_dev[b] (distinct ids within one call); window writes the newest min(total, capacity) samples of each
+ * requested stream, oldest first, to out_dev [n, capacity_samples] (zero tail) and their count to lens_dev [n] - the
+ * array the reference would hand to the model after its slice. */
+size_t b200fe_ring_state_bytes(int n_streams, int capacity_samples);
+int b200fe_ring_reset(void* state_dev, int n_streams, int capacity_samples, const int32_t* stream_ids_dev_or_null, int n,
+                      void* stream);
+int b200fe_ring_push(void* state_dev, int n_streams, int capacity_samples, const float* chunks_dev, int64_t chunk_stride,
+                     const int32_t* chunk_lens_dev, const int32_t* stream_ids_dev, int n, int max_chunk_samples,
+                     void* stream);
+int b200fe_ring_window(const void* state_dev, int n_streams, int capacity_samples, const int32_t* stream_ids_dev, int n,
+                       float* out_dev, int64_t* lens_dev, void* stream);
 /* Kaldi subtract_mean (TA:642-644, _subtract_column_mean), i.e. the utterance mean normalisation of the CAM++
  * speaker-verification features (R:voice_interface.py:2430,2520,2558), in place on [batch, rows_cap, dim] features:
  * feats[u, t, :] -= mean over t < n_rows[u]. */

@@ -716,3 +716,39 @@ def test_digital_silence_and_level_changes(cmvn):
     ok = ~silent & (lr > floor + 3.0)
     err = np.abs(lg - lr)
     assert err[ok].max() <= 3e-3 and err[ok].mean() <= 2e-5
+
+
+def test_audio_ring_reproduces_the_reference_sliding_window(cmvn):
+    """`buf = np.concatenate([buf, chunk])[-target:]` (R:voice_interface.py:1304-1311) for several
+    sessions at once on the device, then the KWS-style front-end call on the window."""
+    from toolbox_for_asr_and_tts_b200 import AudioRing
+    cap, n_streams = 25600, 5                     # 1.6 s at 16 kHz
+    ring = AudioRing(n_streams, cap, DEV)
+    rng = np.random.default_rng(11)
+    bufs = [np.zeros(0, dtype=np.float32) for _ in range(n_streams)]
+    fe = make_fe(cmvn)
+    for tick in range(9):
+        ids = [s for s in range(n_streams) if (tick + s) % 3 != 0]            # not every session speaks every tick
+        lens = [int(rng.integers(1, 6401)) if tick != 4 else 30000 for _ in ids]   # tick 4: a chunk longer than the window
+        maxlen = max(lens)
+        chunks = np.zeros((len(ids), maxlen), dtype=np.float32)
+        for k, (s, n) in enumerate(zip(ids, lens)):
+            c = (0.3 * rng.standard_normal(n)).astype(np.float32)
+            chunks[k, :n] = c
+            bufs[s] = np.concatenate([bufs[s], c])[-cap:]                       # the reference's update
+        ring.push(torch.from_numpy(chunks).to(DEV), lens, ids)
+        win, wl = ring.window(list(range(n_streams)))
+        win, wl = win.cpu().numpy(), wl.cpu().numpy()
+        for s in range(n_streams):
+            assert wl[s] == len(bufs[s])
+            assert np.array_equal(win[s, :wl[s]], bufs[s]) and not win[s, wl[s]:].any()
+    ring.reset([1])
+    win, wl = ring.window([1, 2])
+    assert int(wl[0]) == 0 and not win[0].any() and int(wl[1]) == len(bufs[2])
+    # the window goes straight into the front-end, like kws_model.generate(input=self.kws_audio_buffer) at :1370-1374
+    win, wl = ring.window([0, 2, 3])
+    feats, fl = fe(win, wl)
+    ref, rl = wf.frontend_forward([bufs[0], bufs[2], bufs[3]], [len(bufs[0]), len(bufs[2]), len(bufs[3])], cmvn=cmvn, **PARAFORMER)
+    assert np.array_equal(fl.cpu().numpy(), rl)
+    for i, k in enumerate(rl):
+        assert_feats_close(feats[i, :k], ref[i, :k], cmvn)

@@ -7,7 +7,7 @@ The native code (libb200fe.so + _b200fe_torch.so) is loaded lazily; there is no 
 """
 from .cmvn import load_cmvn, stats_to_cmvn, write_cmvn  # noqa: F401
 from .frontend import WavFrontend  # noqa: F401
-from .online import StreamPool, WavFrontendOnline  # noqa: F401
+from .online import AudioRing, StreamPool, WavFrontendOnline  # noqa: F401
 from .tts_mel import TtsLogMel  # noqa: F401
 
-__all__ = ["WavFrontend", "WavFrontendOnline", "StreamPool", "TtsLogMel", "load_cmvn", "write_cmvn", "stats_to_cmvn"]
+__all__ = ["WavFrontend", "WavFrontendOnline", "StreamPool", "AudioRing", "TtsLogMel", "load_cmvn", "write_cmvn", "stats_to_cmvn"]

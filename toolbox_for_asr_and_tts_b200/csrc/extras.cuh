@@ -3,6 +3,9 @@
 //                          voice_interface.py:873-939, 1298-1300, 1569-1570): max, min, mean |x|, RMS, clipping ratio
 //   * ingest_pcm_kernel    base64_to_audio_np after the WAV header (R:voice_interface.py:1004-1034): sample width
 //                          normalisation, channel mean, linear-interpolation resampling (its numpy branch), float32
+//   * ring_push / ring_window   the per-session sliding audio buffers (KWS 1.6 s window, 0.4 s pre-speech guard:
+//                          buffer = np.concatenate([buffer, chunk])[-target:], R:voice_interface.py:1304-1311,1742-1746)
+//                          as a device-resident circular buffer per stream
 //   * column_mean_kernel   Kaldi subtract_mean (TA:642-644, _subtract_column_mean) = the utterance mean
 //                          normalisation of the CAM++ speaker-verification features (R:voice_interface.py:2430,2520,2558)
 #pragma once
@@ -128,6 +131,65 @@ __global__ void ingest_pcm_kernel(const void* pcm, int width, int channels, long
     }
     out[i] = (float)y;
   }
+}
+
+// Sliding audio windows, one circular buffer of `cap` samples per stream in one slab: [n_streams] int64 totals (samples
+// ever pushed) followed by [n_streams][cap] float32.  Sample number t of a stream lives at slot t % cap, so a push never
+// moves old data and the window of the newest min(total, cap) samples is a gather.
+struct RingLayout {
+  int n_streams;
+  int cap;
+  __host__ __device__ size_t totals_bytes() const { return ((size_t)n_streams * sizeof(long long) + 255) & ~(size_t)255; }
+  __host__ __device__ size_t total_bytes() const { return totals_bytes() + (size_t)n_streams * cap * sizeof(float); }
+  __host__ __device__ long long* totals(void* base) const { return reinterpret_cast<long long*>(base); }
+  __host__ __device__ float* data(void* base) const { return reinterpret_cast<float*>((char*)base + totals_bytes()); }
+};
+
+__global__ void ring_reset_kernel(void* state, RingLayout lay, const int* ids, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = ids ? ids[i] : i;
+  if (s >= 0 && s < lay.n_streams) lay.totals(state)[s] = 0;
+}
+
+// grid = (chunks of the copy, n): appends chunk b to stream ids[b]; only the newest `cap` samples of a long chunk land.
+// Stream ids must be distinct within one call.  The total is advanced by a second tiny kernel (ring_commit_kernel) so
+// that every block of this one sees the same starting total.
+__global__ void ring_push_kernel(void* state, RingLayout lay, const float* chunks, long long chunk_stride,
+                                 const int* chunk_lens, const int* ids, int max_chunk) {
+  const int b = blockIdx.y, s = ids[b];
+  if (s < 0 || s >= lay.n_streams) return;
+  const int len = min(max(chunk_lens[b], 0), max_chunk);
+  const long long total = lay.totals(state)[s];
+  const int skip = len > lay.cap ? len - lay.cap : 0;       // older part of an over-long chunk never becomes visible
+  float* ring = lay.data(state) + (size_t)s * lay.cap;
+  const float* src = chunks + (long long)b * chunk_stride;
+  for (int i = skip + blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x)
+    ring[(total + i) % lay.cap] = src[i];
+}
+__global__ void ring_commit_kernel(void* state, RingLayout lay, const int* chunk_lens, const int* ids, int n, int max_chunk) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const int s = ids[b];
+  if (s >= 0 && s < lay.n_streams) lay.totals(state)[s] += min(max(chunk_lens[b], 0), max_chunk);
+}
+
+// out[b, 0 : m] = the newest m = min(total, cap) samples of stream ids[b], oldest first; out[b, m : cap] = 0; lens[b] = m.
+__global__ void ring_window_kernel(const void* state, RingLayout lay, const int* ids, float* out, long long* lens) {
+  const int b = blockIdx.y, s = ids[b];
+  float* dst = out + (size_t)b * lay.cap;
+  if (s < 0 || s >= lay.n_streams) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lay.cap; i += gridDim.x * blockDim.x) dst[i] = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) lens[b] = 0;
+    return;
+  }
+  const long long total = lay.totals(const_cast<void*>(state))[s];
+  const int m = (int)(total < lay.cap ? total : lay.cap);
+  const long long first = total - m;
+  const float* ring = lay.data(const_cast<void*>(state)) + (size_t)s * lay.cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lay.cap; i += gridDim.x * blockDim.x)
+    dst[i] = i < m ? ring[(first + i) % lay.cap] : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) lens[b] = m;
 }
 
 // feats[u, t, d] -= mean_t feats[u, :T_u, d]  (TA:642-644).  One CTA per (utterance, 32 columns): 8 row-lanes x 32

@@ -43,6 +43,51 @@ int b200fe_ingest_pcm(const void* pcm_dev, int sample_width, int channels, int64
   return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
 }
 
+size_t b200fe_ring_state_bytes(int n_streams, int capacity_samples) {
+  if (n_streams <= 0 || capacity_samples <= 0) return 0;
+  RingLayout lay{n_streams, capacity_samples};
+  return lay.total_bytes();
+}
+
+int b200fe_ring_reset(void* state_dev, int n_streams, int capacity_samples, const int32_t* stream_ids_dev_or_null, int n,
+                      void* stream) {
+  if (!state_dev || n_streams <= 0 || capacity_samples <= 0 || n < 0) return B200FE_E_INVALID;
+  if (n == 0) return B200FE_OK;
+  RingLayout lay{n_streams, capacity_samples};
+  ring_reset_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(state_dev, lay, stream_ids_dev_or_null, n);
+  return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
+}
+
+int b200fe_ring_push(void* state_dev, int n_streams, int capacity_samples, const float* chunks_dev, int64_t chunk_stride,
+                     const int32_t* chunk_lens_dev, const int32_t* stream_ids_dev, int n, int max_chunk_samples,
+                     void* stream) {
+  if (!state_dev || !chunks_dev || !chunk_lens_dev || !stream_ids_dev || n_streams <= 0 || capacity_samples <= 0 || n < 0 ||
+      max_chunk_samples <= 0)
+    return B200FE_E_INVALID;
+  if (n == 0) return B200FE_OK;
+  RingLayout lay{n_streams, capacity_samples};
+  int gx = (max_chunk_samples + 1023) / 1024;
+  gx = gx < 1 ? 1 : (gx > 32 ? 32 : gx);
+  cudaStream_t st = (cudaStream_t)stream;
+  ring_push_kernel<<<dim3(gx, n), 256, 0, st>>>(state_dev, lay, chunks_dev, chunk_stride, chunk_lens_dev, stream_ids_dev,
+                                                max_chunk_samples);
+  ring_commit_kernel<<<(n + 255) / 256, 256, 0, st>>>(state_dev, lay, chunk_lens_dev, stream_ids_dev, n, max_chunk_samples);
+  return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
+}
+
+int b200fe_ring_window(const void* state_dev, int n_streams, int capacity_samples, const int32_t* stream_ids_dev, int n,
+                       float* out_dev, int64_t* lens_dev, void* stream) {
+  if (!state_dev || !stream_ids_dev || !out_dev || !lens_dev || n_streams <= 0 || capacity_samples <= 0 || n < 0)
+    return B200FE_E_INVALID;
+  if (n == 0) return B200FE_OK;
+  RingLayout lay{n_streams, capacity_samples};
+  int gx = (capacity_samples + 1023) / 1024;
+  gx = gx < 1 ? 1 : (gx > 32 ? 32 : gx);
+  ring_window_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)stream>>>(state_dev, lay, stream_ids_dev, out_dev,
+                                                                     (long long*)lens_dev);
+  return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
+}
+
 int b200fe_subtract_column_mean(float* feats_dev, int64_t rows_cap, int dim, const int64_t* n_rows_dev, int batch,
                                 void* stream) {
   if (batch == 0) return B200FE_OK;

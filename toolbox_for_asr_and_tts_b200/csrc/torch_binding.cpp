@@ -335,6 +335,47 @@ at::Tensor fe_ingest_pcm(const at::Tensor& pcm, int64_t channels, int64_t src_ra
   return out;
 }
 
+at::Tensor ring_state(int64_t n_streams, int64_t capacity, c10::Device device) {
+  TORCH_CHECK(device.is_cuda(), "the audio ring lives on a CUDA device");
+  const size_t bytes = b200fe_ring_state_bytes((int)n_streams, (int)capacity);
+  TORCH_CHECK(bytes > 0, "bad ring geometry");
+  c10::cuda::CUDAGuard guard(device);
+  auto st = at::empty({(int64_t)bytes}, at::TensorOptions().dtype(at::kByte).device(device));
+  int rc = b200fe_ring_reset(st.data_ptr(), (int)n_streams, (int)capacity, nullptr, (int)n_streams, cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_ring_reset failed");
+  return st;
+}
+
+void ring_reset(at::Tensor state, int64_t n_streams, int64_t capacity, const at::Tensor& ids) {
+  c10::cuda::CUDAGuard guard(state.device());
+  auto i = ids.to(state.device(), at::kInt).contiguous();
+  int rc = b200fe_ring_reset(state.data_ptr(), (int)n_streams, (int)capacity, i.data_ptr<int32_t>(), (int)i.numel(), cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_ring_reset failed");
+}
+
+void ring_push(at::Tensor state, int64_t n_streams, int64_t capacity, const at::Tensor& chunks, const at::Tensor& lens,
+               const at::Tensor& ids) {
+  TORCH_CHECK(chunks.is_cuda() && chunks.scalar_type() == at::kFloat && chunks.dim() == 2, "chunks must be CUDA float32 [n, len]");
+  c10::cuda::CUDAGuard guard(state.device());
+  auto c = chunks.contiguous();
+  auto l = lens.to(state.device(), at::kInt).contiguous(), i = ids.to(state.device(), at::kInt).contiguous();
+  TORCH_CHECK(l.numel() == c.size(0) && i.numel() == c.size(0), "one length and one stream id per chunk");
+  int rc = b200fe_ring_push(state.data_ptr(), (int)n_streams, (int)capacity, c.data_ptr<float>(), c.size(1),
+                            l.data_ptr<int32_t>(), i.data_ptr<int32_t>(), (int)c.size(0), (int)c.size(1), cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_ring_push failed");
+}
+
+std::tuple<at::Tensor, at::Tensor> ring_window(const at::Tensor& state, int64_t n_streams, int64_t capacity, const at::Tensor& ids) {
+  c10::cuda::CUDAGuard guard(state.device());
+  auto i = ids.to(state.device(), at::kInt).contiguous();
+  auto out = at::empty({i.numel(), capacity}, at::TensorOptions().dtype(at::kFloat).device(state.device()));
+  auto lens = at::empty({i.numel()}, at::TensorOptions().dtype(at::kLong).device(state.device()));
+  int rc = b200fe_ring_window(state.data_ptr(), (int)n_streams, (int)capacity, i.data_ptr<int32_t>(), (int)i.numel(),
+                              out.data_ptr<float>(), lens.data_ptr<int64_t>(), cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_ring_window failed");
+  return {out, lens};
+}
+
 void fe_subtract_column_mean(at::Tensor feats, const at::Tensor& n_rows) {
   TORCH_CHECK(feats.is_cuda() && feats.scalar_type() == at::kFloat && feats.dim() == 3 && feats.is_contiguous(),
               "b200fe.subtract_column_mean: features must be a contiguous CUDA float32 [B, T, D] tensor");
@@ -384,6 +425,10 @@ TORCH_LIBRARY(b200fe, m) {
   m.def("audio_stats(Tensor wave, Tensor? offsets, Tensor lengths, float clip_level) -> Tensor", fe_audio_stats);
   m.def("subtract_column_mean(Tensor(a!) feats, Tensor n_rows) -> ()", fe_subtract_column_mean);
   m.def("ingest_pcm(Tensor pcm, int channels, int src_rate, int dst_rate) -> Tensor", fe_ingest_pcm);
+  m.def("ring_state(int n_streams, int capacity, Device device) -> Tensor", ring_state);
+  m.def("ring_reset(Tensor(a!) state, int n_streams, int capacity, Tensor ids) -> ()", ring_reset);
+  m.def("ring_push(Tensor(a!) state, int n_streams, int capacity, Tensor chunks, Tensor lens, Tensor ids) -> ()", ring_push);
+  m.def("ring_window(Tensor state, int n_streams, int capacity, Tensor ids) -> (Tensor, Tensor)", ring_window);
   m.def("launch_count(int h) -> int", fe_launch_count);
   m.def("select_kernel(int h, int which) -> ()", fe_select_kernel);
   m.def("profile_enable(int h, bool on) -> ()", fe_profile_enable);

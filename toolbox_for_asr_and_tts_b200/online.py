@@ -53,6 +53,36 @@ class StreamPool:
         self.state.copy_(snap)
 
 
+class AudioRing:
+    """Sliding audio windows for many sessions, resident in HBM: what the reference keeps per session with
+    `buf = np.concatenate([buf, chunk])[-target:]` (KWS window 1.6 s, pre-speech guard 0.4 s;
+    R:voice_interface.py:1304-1311, 1742-1746).  `window(ids)` returns what the reference would hand to the model after
+    its slice: the newest min(total, capacity) samples per stream, oldest first, as a dense [k, capacity] tensor with a
+    zero tail, plus their counts - ready for `WavFrontend.forward(window, lens)`."""
+
+    def __init__(self, n_streams: int, capacity_samples: int, device="cuda"):
+        from . import _native
+        self.n_streams, self.capacity = int(n_streams), int(capacity_samples)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("AudioRing state must live on a CUDA device (no CPU fallback)")
+        self._ops = _native.ops()
+        self.state = self._ops.ring_state(self.n_streams, self.capacity, self.device)
+
+    def reset(self, stream_ids) -> None:
+        self._ops.ring_reset(self.state, self.n_streams, self.capacity, torch.as_tensor(stream_ids, dtype=torch.int32))
+
+    def push(self, chunks: torch.Tensor, chunk_lens, stream_ids) -> None:
+        """chunks: CUDA float32 [k, <=max_len]; stream ids must be distinct within one call."""
+        if not chunks.is_cuda:
+            raise RuntimeError("chunks must be a CUDA tensor: the B200 front-end has no CPU fallback")
+        self._ops.ring_push(self.state, self.n_streams, self.capacity, chunks, torch.as_tensor(chunk_lens, dtype=torch.int32),
+                            torch.as_tensor(stream_ids, dtype=torch.int32))
+
+    def window(self, stream_ids) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._ops.ring_window(self.state, self.n_streams, self.capacity, torch.as_tensor(stream_ids, dtype=torch.int32))
+
+
 class WavFrontendOnline(WavFrontend):
     """Chunked front-end with upstream's call shape (batch size 1, state in the caller's `cache` dict)."""
 
