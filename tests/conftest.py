@@ -25,11 +25,15 @@ VARIANT_SEED, VARIANT_LENS = 55, (16000, 4001)
 PARAFORMER = dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6)
 
 # Stated tolerances: log-mel max-abs <= 1e-3 against the float32 reference on broadband input;
-# after CMVN the bound scales with the largest Rescale entry.  Bins more than 12 nepers (52 dB) below the frame's
-# strongest mel bin sit at the float32 noise floor of ANY 512-point float32 FFT (the reference's own float32 result is
-# 2-5e-4 away from float64 there, tests/parity_report.py): they get 3e-3, and the mean error is bounded separately.
+# after CMVN the bound scales with the largest Rescale entry.  Bins far below the frame's strongest mel bin sit at the
+# float32 noise floor of ANY 512-point float32 FFT: the absolute spectrum error is ~3e-7 of the frame's norm, so the
+# relative error of a bin d nepers below the peak grows like e^(d/2) (the reference's own float32 result is 2-5e-4 away
+# from float64 at d = 15, tests/parity_report.py; two kernels of this repository that only pair frames differently
+# differ by 0.18 at d = 25, tools/fuzz_gpu.py).  Hence: 1e-3 within 12 nepers of the peak, below that
+# max(3e-3, 2e-6 * e^(d/2)), and the mean error is bounded separately.
 LOGMEL_ATOL = 1e-3
 LOGMEL_ATOL_DEEP = 3e-3
+LOGMEL_FLOOR_COEF = 2e-6
 LOGMEL_MEAN_ATOL = 2e-5
 DEEP_BIN_NEPERS = 12.0
 
@@ -40,9 +44,11 @@ def assert_logmel_close(got, ref):
     ref = np.asarray(ref, dtype=np.float64)
     assert got.shape == ref.shape
     err = np.abs(got - ref)
-    deep = ref < ref.max(axis=-1, keepdims=True) - DEEP_BIN_NEPERS
+    depth = ref.max(axis=-1, keepdims=True) - ref
+    deep = depth > DEEP_BIN_NEPERS
     assert err[~deep].max() <= LOGMEL_ATOL, err[~deep].max()
-    assert err.max() <= LOGMEL_ATOL_DEEP, err.max()
+    tol_deep = np.maximum(LOGMEL_ATOL_DEEP, LOGMEL_FLOOR_COEF * np.exp(np.minimum(depth, 60.0) / 2.0))
+    assert (err <= tol_deep)[deep].all(), float((err - tol_deep)[deep].max())
     assert err.mean() <= LOGMEL_MEAN_ATOL, err.mean()
 
 
