@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-from toolbox_for_asr_and_tts_b200 import WavFrontend, synth  # noqa: E402
+from toolbox_for_asr_and_tts_b200 import StreamPool, WavFrontend, synth  # noqa: E402
 
 
 def close(a, b, cm, m):
@@ -30,14 +30,73 @@ def close(a, b, cm, m):
     return float(err[~deep].max()), excess, float(err.mean())
 
 
+def fuzz_streaming(a, rng, dev):
+    """Random chunking of random-length streams (up to 24 at a time, chunk lengths 1..9600 per tick, some ticks skipped),
+    LFR 7/6 and 5/1: the concatenated rows must equal the offline rows (same kernels, frames paired differently)."""
+    t0, it, worst = time.time(), 0, 0.0
+    pools = {}
+    for m, n in ((7, 6), (5, 1)):
+        cm = np.stack([rng.normal(-8.0, 1.0, m * 80), rng.uniform(0.2, 0.5, m * 80)]).astype(np.float32)
+        fe = WavFrontend(cmvn=torch.from_numpy(cm), fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10,
+                         lfr_m=m, lfr_n=n, dither=0.0)
+        pools[(m, n)] = (fe, StreamPool(fe, 24, 9600, dev), cm)
+    while time.time() - t0 < a.seconds:
+        m, n = ((7, 6), (5, 1))[int(rng.integers(2))]
+        fe, pool, cm = pools[(m, n)]
+        ns = int(rng.integers(1, 25))
+        lens = rng.integers(1, 60000, ns)
+        waves = [(0.3 * rng.standard_normal(int(k))).astype(np.float32) for k in lens]
+        pool.reset(torch.arange(24, dtype=torch.int32, device=dev))
+        pos, got = [0] * ns, [[] for _ in range(ns)]
+        while any(p < k for p, k in zip(pos, lens)):
+            ids, chunks, clens, fins = [], [], [], []
+            for s in range(ns):
+                if pos[s] < lens[s] and rng.random() < 0.8:
+                    c = int(min(rng.integers(1, 9601), lens[s] - pos[s]))
+                    buf = np.zeros(9600, dtype=np.float32)
+                    buf[:c] = waves[s][pos[s]:pos[s] + c]
+                    pos[s] += c
+                    ids.append(s); chunks.append(buf); clens.append(c); fins.append(1 if pos[s] >= lens[s] else 0)
+            if not ids:
+                continue
+            f, r = pool.push(torch.from_numpy(np.stack(chunks)).to(dev), torch.tensor(clens, dtype=torch.int32),
+                             torch.tensor(ids, dtype=torch.int32), torch.tensor(fins, dtype=torch.uint8))
+            r = r.cpu().tolist()
+            for k, s in enumerate(ids):
+                if r[k]:
+                    got[s].append(f[k, :r[k]].cpu())
+        nmax = int(lens.max())
+        dense = torch.zeros(ns, nmax)
+        for s in range(ns):
+            dense[s, :lens[s]] = torch.from_numpy(waves[s])
+        keep = [s for s in range(ns) if lens[s] >= 400]     # shorter streams never complete a frame
+        if keep:
+            off, ol = fe(dense[keep].to(dev), [int(lens[s]) for s in keep])
+            for k, s in enumerate(keep):
+                cat = torch.cat(got[s]) if got[s] else torch.zeros(0, m * 80)
+                assert cat.shape[0] == int(ol[k]), (it, s, int(lens[s]), cat.shape[0], int(ol[k]))
+                mx, ex, mean = close(cat.numpy(), off[k, :cat.shape[0]].cpu().numpy(), cm, m)
+                worst = max(worst, mx)
+                assert mx <= 2e-3 and ex <= 0.0 and mean <= 2e-5, (it, s, mx, ex, mean)
+        for s in range(ns):
+            if lens[s] < 400:
+                assert not got[s], (it, s, "rows from a stream shorter than one frame")
+        it += 1
+    print(f"streaming fuzz ok: {it} random sessions-sets in {time.time() - t0:.0f} s, worst stream-vs-offline difference {worst:.2e}")
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--streaming", action="store_true", help="fuzz the chunked-streaming path instead")
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--only", type=int, default=-1, help="replay the random draws and run just this iteration, with diagnostics")
     a = ap.parse_args()
     rng = np.random.default_rng(a.seed)
     dev = "cuda:0"
+    if a.streaming:
+        fuzz_streaming(a, rng, dev)
+        return
     confs = [(7, 6), (5, 1), (1, 1), (3, 2)]
     fes = {}
     for m, n in confs:
