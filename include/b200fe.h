@@ -215,10 +215,12 @@ int b200fe_lfr_targets(int frame, int n_frames, int n_rows, int lfr_m, int lfr_n
  * 1 = always the tile kernel (the one that also accumulates CMVN statistics).  Results are identical. */
 int b200fe_select_kernel(b200fe_handle* h, int which);
 
-/* Roofline support: while enabled, every launch of the dominant (fused) kernel is bracketed by CUDA events
- * recorded on the launching stream.  b200fe_profile_collect synchronises those events, returns the summed kernel
- * time and the number of launches since the last collect, and clears the list. */
-int b200fe_profile_enable(b200fe_handle* h, int on);
+/* Roofline support: while enabled (every > 0), every `every`-th launch of the dominant (fused) kernel is bracketed by
+ * CUDA events recorded on the launching stream (1 = all of them; an event pair costs a few microseconds of stream
+ * time and keeps that launch from overlapping the tail of the kernel in front of it, so a throughput loop samples).
+ * b200fe_profile_collect synchronises those events, returns the summed kernel time and the number of TIMED launches
+ * since the last collect, and clears the list. */
+int b200fe_profile_enable(b200fe_handle* h, int every);
 int b200fe_profile_collect(b200fe_handle* h, double* total_ms, int64_t* n_launches);
 
 #ifdef __cplusplus

@@ -752,3 +752,46 @@ def test_audio_ring_reproduces_the_reference_sliding_window(cmvn):
     assert np.array_equal(fl.cpu().numpy(), rl)
     for i, k in enumerate(rl):
         assert_feats_close(feats[i, :k], ref[i, :k], cmvn)
+
+
+def test_one_frontend_from_several_host_threads_on_their_own_streams(cmvn):
+    """SURVEY 8(b) threading clause: one handle may be shared by host threads that use distinct streams / workspaces.
+    Four threads push different ragged batches through ONE WavFrontend concurrently; every result must be bit-identical
+    to the same batch run alone."""
+    import threading
+    fe = make_fe(cmvn)
+    rng = np.random.default_rng(77)
+    jobs = []
+    for t in range(4):
+        lens = [int(v) for v in rng.integers(400, 60000, size=6)]
+        waves = [synth.uniform_pcm(SEED + t, i, n) for i, n in enumerate(lens)]
+        jobs.append((dense_batch(waves), lens))
+    alone = []
+    for x, lens in jobs:
+        f, l = fe(x, lens)
+        alone.append((f.clone(), l.clone()))
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(t):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream(device=DEV)
+            x, lens = jobs[t]
+            st.wait_stream(torch.cuda.default_stream(torch.device(DEV)))
+            with torch.cuda.stream(st):
+                for _ in range(25):
+                    f, l = fe(x, lens)
+                    st.synchronize()
+                    if not (torch.equal(f, alone[t][0]) and torch.equal(l, alone[t][1])):
+                        errors.append(f"thread {t}: result differs from the serial run")
+                        return
+        except Exception as e:   # surfaced below: an exception in a thread must fail the test
+            errors.append(f"thread {t}: {type(e).__name__}: {e}")
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

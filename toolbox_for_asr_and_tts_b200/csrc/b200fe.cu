@@ -61,9 +61,10 @@ struct b200fe_handle {
   PinnedSlot slots[4];
   int next_slot = 0;
   long long launches = 0;
-  bool profile = false;
+  int profile_every = 0, profile_tick = 0;   // b200fe_profile_enable: time every n-th fused-kernel launch
   bool force_tile = false;           // b200fe_select_kernel(h, 1): keep the tile kernel (A/B measurements, tests)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  UttTable utt_tab;                  // staging for the prep launch's by-value utterance table (under mu)
   mutable std::string err;
 };
 
@@ -368,7 +369,8 @@ int launch_tile(b200fe_handle* h, const TileParams& p, int grid, bool dither, bo
     k<<<grid, kCtaThreads, h->smem_bytes, st>>>(p);                                                             \
   } while (0)
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->profile) {
+  const bool timed = h->profile_every > 0 && (h->profile_tick++ % h->profile_every) == 0;
+  if (timed) {
     CUDA_TRY(h, cudaEventCreate(&e0));
     CUDA_TRY(h, cudaEventCreate(&e1));
     CUDA_TRY(h, cudaEventRecord(e0, st));
@@ -376,7 +378,7 @@ int launch_tile(b200fe_handle* h, const TileParams& p, int grid, bool dither, bo
   if (dither) { if (stats) LAUNCH(true, true); else LAUNCH(true, false); }
   else        { if (stats) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
-  if (h->profile) {
+  if (timed) {
     CUDA_TRY(h, cudaEventRecord(e1, st));
     h->prof_events.emplace_back(e0, e1);
   }
@@ -392,17 +394,24 @@ int launch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cu
   do {                                                                                                \
     auto k = fbank_warp_kernel<NROWS, EXACT, DI, MELS, SR, SampleT>;                                             \
     CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    k<<<grid, kCtaThreads, smem, st>>>(p);                                                            \
+    cudaLaunchConfig_t lc = {};                                                                       \
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kCtaThreads); lc.dynamicSmemBytes = smem; lc.stream = st; \
+    cudaLaunchAttribute at[1];                                                                        \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                    \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                                             \
+    lc.attrs = at; lc.numAttrs = timed ? 0 : 1;                                                                 \
+    CUDA_TRY(h, cudaLaunchKernelEx(&lc, k, p));                                                       \
   } while (0)
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->profile) {
+  const bool timed = h->profile_every > 0 && (h->profile_tick++ % h->profile_every) == 0;
+  if (timed) {
     CUDA_TRY(h, cudaEventCreate(&e0));
     CUDA_TRY(h, cudaEventCreate(&e1));
     CUDA_TRY(h, cudaEventRecord(e0, st));
   }
   if (dither) LAUNCHW(true); else LAUNCHW(false);
 #undef LAUNCHW
-  if (h->profile) {
+  if (timed) {
     CUDA_TRY(h, cudaEventRecord(e1, st));
     h->prof_events.emplace_back(e0, e1);
   }
@@ -584,10 +593,11 @@ int b200fe_select_kernel(b200fe_handle* h, int which) {
   return B200FE_OK;
 }
 
-int b200fe_profile_enable(b200fe_handle* h, int on) {
+int b200fe_profile_enable(b200fe_handle* h, int every) {
   if (!h) return B200FE_E_INVALID;
   std::lock_guard<std::mutex> lock(h->mu);
-  h->profile = on != 0;
+  h->profile_every = every > 0 ? every : 0;
+  h->profile_tick = 0;
   return B200FE_OK;
 }
 
@@ -672,10 +682,13 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   ShortDesc* d_shorts = reinterpret_cast<ShortDesc*>((char*)d_utts + align256((size_t)batch * sizeof(UttDesc)));
   TileDesc* d_tiles = reinterpret_cast<TileDesc*>((char*)d_shorts + align256((size_t)batch * sizeof(ShortDesc)));
   QuadDesc* d_quads = reinterpret_cast<QuadDesc*>(d_tiles);   // same region: a launch uses one of the two lists
-  if ((rc = upload(h, pl.utts.data(), (size_t)batch * sizeof(UttDesc), d_utts, st))) return rc;
   // the warp kernel does everything except the CMVN statistics (which need the row-major tile pass)
   const bool use_warp = stats_dev == nullptr && warp_kernel_fits(h->L, h->S) && (!h->force_tile || pcm16) &&
                         pl.max_rows * (long long)h->D < (1ll << kTargetOffBits) - 1;
+  // utterance table: inside the prep launch's parameters when it fits (warp path, no short utterances, which read
+  // d_utts-independent descriptors of their own), else one pinned-buffer upload
+  const bool utts_in_params = use_warp && pl.n_quads > 0 && batch <= kParamUtts;
+  if (!utts_in_params && (rc = upload(h, pl.utts.data(), (size_t)batch * sizeof(UttDesc), d_utts, st))) return rc;
   if (pcm16 && !use_warp)
     return fail(h, B200FE_E_UNSUPPORTED, "int16 input is implemented in the warp kernel only (no statistics pass, "
                                          "frame shifts whose quad fits its buffer)");
@@ -685,9 +698,18 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   if (use_warp && pl.n_quads > 0) {
     // 1. one launch: quad list (+ work counter) and padding rows + feat_lens
     const int qb = (pl.n_quads + 255) / 256;
-    prep_warp_kernel<<<qb + gx * batch, 256, 0, st>>>(d_utts, batch, pl.n_quads, qb, h->S, h->cfg.lfr_m, h->cfg.lfr_n,
-                                                      h->cfg.n_mels, d_quads, d_counter, feats_dev, rows_cap,
-                                                      (long long*)feat_lens_dev, gx);
+    if (utts_in_params) {
+      static_assert(sizeof(UttTable) <= 16384, "kernel parameters");
+      UttTable& tab = h->utt_tab;
+      memcpy(tab.u, pl.utts.data(), (size_t)batch * sizeof(UttDesc));
+      prep_warp_kernel_tab<<<qb + gx * batch, 256, 0, st>>>(tab, batch, pl.n_quads, qb, h->S, h->cfg.lfr_m, h->cfg.lfr_n,
+                                                            h->cfg.n_mels, d_quads, d_counter, feats_dev, rows_cap,
+                                                            (long long*)feat_lens_dev, gx);
+    } else {
+      prep_warp_kernel<<<qb + gx * batch, 256, 0, st>>>(d_utts, batch, pl.n_quads, qb, h->S, h->cfg.lfr_m, h->cfg.lfr_n,
+                                                        h->cfg.n_mels, d_quads, d_counter, feats_dev, rows_cap,
+                                                        (long long*)feat_lens_dev, gx);
+    }
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
   } else {

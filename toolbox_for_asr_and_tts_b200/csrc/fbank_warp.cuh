@@ -250,6 +250,10 @@ fbank_warp_kernel(const QuadParams p) {
   float win[NROWS + 1];
   load_window_taps<NROWS>(win, p.window, j, grp_in_warp);
   __syncthreads();   // the only CTA-wide barrier: the twiddle tables
+  // Launched as a programmatic dependent of prep_warp_kernel (b200fe.cu: launch_warp): everything above reads
+  // per-handle constants only and overlaps the tail of that kernel; the quad list and the work counter are its
+  // output.  (A no-op when the launch carries no such attribute.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   float* buf = bufs + warp * kQuadBuf;
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;

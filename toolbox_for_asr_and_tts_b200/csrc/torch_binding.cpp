@@ -391,7 +391,7 @@ int64_t fe_launch_count(int64_t h) { return b200fe_launch_count(H(h)); }
 
 void fe_select_kernel(int64_t h, int64_t which) { check(b200fe_select_kernel(H(h), (int)which), H(h), "b200fe_select_kernel"); }
 
-void fe_profile_enable(int64_t h, bool on) { check(b200fe_profile_enable(H(h), on), H(h), "b200fe_profile_enable"); }
+void fe_profile_enable(int64_t h, int64_t every) { check(b200fe_profile_enable(H(h), (int)every), H(h), "b200fe_profile_enable"); }
 
 std::tuple<double, int64_t> fe_profile_collect(int64_t h) {
   double ms = 0.0;
@@ -431,6 +431,6 @@ TORCH_LIBRARY(b200fe, m) {
   m.def("ring_window(Tensor state, int n_streams, int capacity, Tensor ids) -> (Tensor, Tensor)", ring_window);
   m.def("launch_count(int h) -> int", fe_launch_count);
   m.def("select_kernel(int h, int which) -> ()", fe_select_kernel);
-  m.def("profile_enable(int h, bool on) -> ()", fe_profile_enable);
+  m.def("profile_enable(int h, int every) -> ()", fe_profile_enable);
   m.def("profile_collect(int h) -> (float, int)", fe_profile_collect);
 }

@@ -143,10 +143,11 @@ class WavFrontend(nn.Module):
         for h in self._handles.values():
             h.ops.select_kernel(h.h, self._kernel_code)
 
-    def profile(self, on: bool) -> None:
-        """Bracket every launch of the fused kernel with CUDA events on its stream (bench.py roofline)."""
+    def profile(self, every) -> None:
+        """Bracket every `every`-th launch of the fused kernel with CUDA events on its stream (bench.py roofline);
+        True / 1 = every launch, False / 0 = off."""
         h = self._handle(lfr=True, cmvn=True)
-        h.ops.profile_enable(h.h, bool(on))
+        h.ops.profile_enable(h.h, int(every))
 
     def profile_collect(self):
         """(summed kernel milliseconds, launches) since the last collect."""
