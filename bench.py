@@ -32,6 +32,7 @@ sys.path.insert(0, str(ROOT))
 
 CONF = dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6)
 BATCH = 256
+E2E_REPS = 3          # end-to-end loop: median of three runs
 PROFILE_EVERY = 4     # roofline sample: one fused-kernel launch in four is bracketed by CUDA events
 WORKLOAD = "paraformer-zh front-end, 256 synthetic utterances 1-30 s @16 kHz, length-packed (BASELINE.json configs[1])"
 METRIC = "audio_seconds_per_second"
@@ -247,16 +248,25 @@ def run_ours(args, rank, world, local_rank):
         t_end.synchronize()
         return t_begin.elapsed_time(t_end), last, lens_pin[(n_steps - 1) & 1]
 
-    e2e_loop(host, 3)
-    barrier()
+    def e2e_measure(host_buf):
+        """E2E_REPS runs of e2e_steps steps each (every run: barrier, max over ranks); the MEDIAN run is reported and
+        all of them are listed - the loop is PCIe-bound and a shared host shows transients of tens of percent."""
+        e2e_loop(host_buf, 3)
+        runs, out = [], None
+        for _ in range(E2E_REPS):
+            barrier()
+            ms, l_dev, l_host = e2e_loop(host_buf, e2e_steps)
+            barrier()
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            runs.append(float(t[0]))
+            out = (l_dev, l_host)
+        return sorted(runs)[len(runs) // 2], [r / e2e_steps for r in runs], out[0], out[1]
+
     sampler.start()
-    e2e_ms, l2, lens_host = e2e_loop(host, e2e_steps)
-    barrier()
+    e2e_ms, e2e_runs, l2, lens_host = e2e_measure(host)
     sampler.stop()
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t[0])
     e2e_value = audio_s * world * e2e_steps / (e2e_ms * 1e-3)
     assert torch.equal(l2.cpu(), flens.cpu()) and torch.equal(lens_host, flens.cpu())
 
@@ -264,14 +274,7 @@ def run_ours(args, rank, world, local_rank):
     #                  SURVEY.md 8(f)2): reported beside `e2e`, never mixed into it
     host16 = torch.empty(total + 8, dtype=torch.int16).pin_memory()
     host16.copy_((wave.cpu() * 32768.0).round().clamp_(-32768, 32767).to(torch.int16))
-    e2e_loop(host16, 3)
-    barrier()
-    e2e16_ms, l3, _ = e2e_loop(host16, e2e_steps)
-    barrier()
-    t = torch.tensor([e2e16_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e16_ms = float(t[0])
+    e2e16_ms, e2e16_runs, l3, _ = e2e_measure(host16)
     e2e16_value = audio_s * world * e2e_steps / (e2e16_ms * 1e-3)
     assert torch.equal(l3.cpu(), flens.cpu())
 
@@ -332,11 +335,12 @@ def run_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
                     "d2h_bytes_per_step": int(lens_host.numel() * 8), "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps, "runs_ms_per_step": e2e_runs, "reported": "median run",
                     "note": "double-buffered serving loop (step k+1's H2D overlaps step k's kernels); features stay in HBM "
                             "for the acoustic model, only feature lengths return to the host"},
             "e2e_pcm16": {"value": e2e16_value, "unit": UNIT, "h2d_bytes_per_step": int(host16.numel() * 2),
                           "d2h_bytes_per_step": int(lens_host.numel() * 8), "ms_per_step": e2e16_ms / e2e_steps,
+                          "runs_ms_per_step": e2e16_runs,
                           "note": "side measurement: int16 PCM in, converted inside the kernel's loads (bit-identical "
                                   "features); the headline e2e above takes the reference's float32 input"},
             "gpu_launches": int(launches),
