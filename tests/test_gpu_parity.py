@@ -795,3 +795,23 @@ def test_one_frontend_from_several_host_threads_on_their_own_streams(cmvn):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_batches_beyond_the_parameter_table_match_small_batches_bitwise(cmvn):
+    """Up to 256 utterances travel in the prep launch's parameters, larger batches through a pinned-buffer copy: the two
+    routes must give the same rows.  300 short utterances in one call against the same utterances in calls of 100."""
+    fe = make_fe(cmvn)
+    rng = np.random.default_rng(5)
+    lens = [int(v) for v in rng.integers(300, 9000, size=300)]
+    waves = [synth.uniform_pcm(SEED + 9, i, n) for i, n in enumerate(lens)]
+    big, big_l = fe(dense_batch(waves), lens)
+    for a in range(0, 300, 100):
+        part, part_l = fe(dense_batch(waves[a:a + 100]), lens[a:a + 100])
+        assert torch.equal(part_l, big_l[a:a + 100])
+        k = part.shape[1]
+        assert torch.equal(part, big[a:a + 100, :k])
+        assert not big[a:a + 100, k:].any()
+    ref, rl = wf.frontend_forward(waves[:8], lens[:8], cmvn=cmvn, **dict(PARAFORMER, dither=0.0))
+    assert np.array_equal(big_l[:8].cpu().numpy(), rl)
+    for i in range(8):
+        assert_feats_close(big[i, :rl[i]], ref[i, :rl[i]], cmvn)
