@@ -815,3 +815,30 @@ def test_batches_beyond_the_parameter_table_match_small_batches_bitwise(cmvn):
     assert np.array_equal(big_l[:8].cpu().numpy(), rl)
     for i in range(8):
         assert_feats_close(big[i, :rl[i]], ref[i, :rl[i]], cmvn)
+
+
+def test_forward_is_capturable_in_a_cuda_graph(cmvn):
+    """A fixed-shape serving loop captures the call once and replays it (the batch's utterance table travels inside the
+    launch parameters, so the capture holds no host -> device copy): replays on new PCM equal the eager call bitwise."""
+    fe = make_fe(cmvn)
+    lens = [16000, 52000, 9000, 31000, 400, 48000, 7777, 23456]
+
+    def batch(seed):
+        return dense_batch([synth.uniform_pcm(seed, i, n) for i, n in enumerate(lens)])
+
+    static_in = batch(1)
+    side = torch.cuda.Stream(device=DEV)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fe(static_in, lens)                      # warm-up outside the capture (handle, kernel attributes)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out, out_lens = fe(static_in, lens)
+    for seed in (2, 3):
+        x = batch(seed)
+        static_in.copy_(x)
+        graph.replay()
+        torch.cuda.synchronize()
+        ref, ref_lens = fe(x, lens)
+        assert torch.equal(out, ref) and torch.equal(out_lens, ref_lens)
