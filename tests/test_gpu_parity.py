@@ -842,3 +842,38 @@ def test_forward_is_capturable_in_a_cuda_graph(cmvn):
         torch.cuda.synchronize()
         ref, ref_lens = fe(x, lens)
         assert torch.equal(out, ref) and torch.equal(out_lens, ref_lens)
+
+
+def test_stream_tick_is_capturable_in_a_cuda_graph(cmvn):
+    """The per-tick push of a StreamPool takes device tensors only: captured once, replayed every tick (chunk contents,
+    chunk lengths and final flags change in place) it must equal an eagerly driven pool bitwise."""
+    fe = make_fe(cmvn)
+    n_streams, chunk, ticks = 16, 9600, 5
+    rng = np.random.default_rng(3)
+    eager = StreamPool(fe, n_streams=n_streams, max_chunk_samples=chunk, device=DEV)
+    graphed = StreamPool(fe, n_streams=n_streams, max_chunk_samples=chunk, device=DEV)
+    ids = torch.arange(n_streams, dtype=torch.int32, device=DEV)
+    s_chunks = torch.zeros(n_streams, chunk, device=DEV)
+    s_lens = torch.full((n_streams,), chunk, dtype=torch.int32, device=DEV)
+    s_fin = torch.zeros(n_streams, dtype=torch.uint8, device=DEV)
+    side = torch.cuda.Stream(device=DEV)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        warm = StreamPool(fe, n_streams=n_streams, max_chunk_samples=chunk, device=DEV)
+        warm.push(s_chunks, s_lens, ids, s_fin)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_feats, g_rows = graphed.push(s_chunks, s_lens, ids, s_fin)
+    for t in range(ticks):
+        x = torch.from_numpy(rng.uniform(-0.3, 0.3, (n_streams, chunk)).astype(np.float32)).to(DEV)
+        lens = torch.from_numpy(rng.integers(1, chunk + 1, n_streams).astype(np.int32)).to(DEV)
+        fin = torch.full((n_streams,), 1 if t == ticks - 1 else 0, dtype=torch.uint8, device=DEV)
+        s_chunks.copy_(x); s_lens.copy_(lens); s_fin.copy_(fin)
+        graph.replay()
+        e_feats, e_rows = eager.push(x, lens, ids, fin)
+        torch.cuda.synchronize()
+        assert torch.equal(g_rows, e_rows), t
+        for s in range(n_streams):
+            k = int(e_rows[s])
+            assert torch.equal(g_feats[s, :k], e_feats[s, :k]), (t, s)
