@@ -532,7 +532,7 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
     for (int c = 0; c < 16; ++c) {
       const int ph = (c * k1) % 512;
       const double sc = (k1 == 8 || k1 == 16) ? 2.0 : 1.0;
-      tw[(k1 - 1) * kXRow + c] =
+      tw[(k1 - 1) * kTwPitch + c] =
           make_float2((float)(sc * cos(2.0 * M_PI * ph / 512.0)), (float)(-sc * sin(2.0 * M_PI * ph / 512.0)));
     }
   for (int t = 0; t < 8; ++t)

@@ -38,7 +38,8 @@ constexpr int kYPitch = 17;
 constexpr int kYGroupF4 = 16 * kYPitch + 8;       // 280 float4 = 4480 B
 constexpr int kYWarpF4 = 2 * kYGroupF4;           // 8960 B per warp, aliased by the warp's 4 KB of power spectra
 // Twiddles of the packed FFT: [16 rows k1 = 1..16][kXRow float2] then the column-0 table [8][kC0Pitch].
-constexpr int kTw2Table = 16 * kXRow;
+constexpr int kTwPitch = 17;         // float2 per row: 136 B, so the 16 lanes of a group read 32 distinct banks with 64-bit loads
+constexpr int kTw2Table = 16 * kTwPitch;
 constexpr int kC0Pitch = 10;                      // float2; 80 B rows: conflict-free 128-bit reads by 8 threads
 constexpr int kTw2Total = kTw2Table + 8 * kC0Pitch;       // float2
 constexpr int kMaxMels = 128;
@@ -279,7 +280,7 @@ template <int NROWS>
 __device__ __forceinline__ const float2* fft_twiddle_row(const float2* tw_s, int j, int grp_in_warp) {
   (void)grp_in_warp;
   const int col = j == 0 ? 16 : j;
-  return tw_s + (col - 1) * kXRow;
+  return tw_s + (col - 1) * kTwPitch;
 }
 
 // ROT: the second 16-thread group of a warp loads its samples one 16-sample row late (register i holds row i-1).
@@ -434,10 +435,12 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
   f2 ar[16], ai[16];
   {
     const float4* rowp = yg + (col - 1) * kYPitch;
-    const float4* tw4 = reinterpret_cast<const float4*>(tw_row);
     static_for<0, 8>([&](auto ic) {
       constexpr int h = decltype(ic)::value;
-      const float4 t = tw4[h];
+      // 64-bit loads: both groups of the warp read the same 16 words, one wavefront (a 128-bit load is served per
+      // half-warp: two wavefronts per group)
+      const float2 ta = tw_row[2 * h], tb = tw_row[2 * h + 1];
+      const float4 t = make_float4(ta.x, ta.y, tb.x, tb.y);
       const float4 v0 = rowp[2 * h], v1 = rowp[2 * h + 1];
       constexpr bool sw = 2 * h >= 8;   // slots 8..15 are stored (im, re)
       {
