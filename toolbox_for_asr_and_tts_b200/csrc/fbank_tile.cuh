@@ -35,8 +35,12 @@ constexpr int kXRow = 18;           // float2 per twiddle row: 16 + 2 pad -> 144
 // Transpose buffer of the packed real FFT, per 16-thread group: rows k1 = 1..16 of 16 float4 (re A, re B, im A, im B),
 // pitch 17 float4 (272 B: 128-bit row reads by 16 threads are conflict-free), then row 0 as 16 float2 (real bins).
 constexpr int kYPitch = 17;
-constexpr int kYGroupF4 = 16 * kYPitch + 8;       // 280 float4 = 4480 B
-constexpr int kYWarpF4 = 2 * kYGroupF4;           // 8960 B per warp, aliased by the warp's 4 KB of power spectra
+// The group pitch is 16 banks (mod 32) so that a quarter-warp reading 4 columns of BOTH groups (stage 2 assigns lanes
+// 2c, 2c+1 to column c of group 0 / group 1) touches 32 distinct banks.
+constexpr int kYGroupF4 = 16 * kYPitch + 12;      // 284 float4 = 4544 B
+constexpr int kYWarpF4 = 2 * kYGroupF4;           // 9088 B per warp, aliased by the warp's power spectra
+constexpr int kSpecPitch = 256 + 8;               // float2 between the two groups' power spectra: again 16 banks apart
+constexpr int kSpecF4 = kSpecPitch;               // float4 taken by both spectra (2 * kSpecPitch float2)
 // Twiddles of the packed FFT: [16 rows k1 = 1..16][kXRow float2] then the column-0 table [8][kC0Pitch].
 constexpr int kTwPitch = 17;         // float2 per row: 136 B, so the 16 lanes of a group read 32 distinct banks with 64-bit loads
 constexpr int kTw2Table = 16 * kTwPitch;
@@ -216,7 +220,7 @@ __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, 
   f2 up0 = make_float2(0.f, 0.f), up1 = up0, dn0 = up0, dn1 = up0;
   auto body = [&](int q) {
     const float2 w = __ldg(wt + 32 * q);
-    const float2 s0 = p0[q], s1 = p0[256 + q];
+    const float2 s0 = p0[q], s1 = p0[kSpecPitch + q];
     up0 = fma2s(s0, w.x, up0);
     up1 = fma2s(s1, w.x, up1);
     dn0 = fma2s(s0, w.y, dn0);
@@ -273,14 +277,19 @@ __device__ __forceinline__ void load_window_taps(float (&win)[NROWS + 1], const 
   }
 }
 
-// This thread's row of the stage-2 twiddle table: column j (16 for thread 0).  Both groups of a warp read the same
-// table (their loads coalesce into broadcasts): the one-row rotation of the second group only multiplies its column k1
-// by the unit-modulus constant W32^k1, which the power spectrum does not see.
+// This thread's row of the stage-2 twiddle table.  Stage 2 is assigned across the warp (quad_stage2): lanes 2c and 2c+1
+// transform column c (16 for c = 0) of group 0 and of group 1 and read the same row.  One table serves both groups: the
+// one-row rotation of the second group only multiplies its column k1 by the unit-modulus constant W32^k1, which the
+// power spectrum does not see.
 template <int NROWS>
 __device__ __forceinline__ const float2* fft_twiddle_row(const float2* tw_s, int j, int grp_in_warp) {
-  (void)grp_in_warp;
-  const int col = j == 0 ? 16 : j;
+  const int c = ((grp_in_warp << 4) | j) >> 1;
+  const int col = c == 0 ? 16 : c;
   return tw_s + (col - 1) * kTwPitch;
+}
+// This thread's row of the column-0 table: lanes 2t and 2t+1 of a half-warp both compute bin 32 t of their own group.
+__device__ __forceinline__ const float2* fft_c0_row(const float2* tw_s, int j) {
+  return tw_s + kTw2Table + ((j >> 1) & 7) * kC0Pitch;
 }
 
 // ROT: the second 16-thread group of a warp loads its samples one 16-sample row late (register i holds row i-1).
@@ -431,14 +440,18 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
   reinterpret_cast<float2*>(yg + 16 * kYPitch)[j] = y0;
   __syncwarp();
 
-  const int col = j == 0 ? 16 : j;
+  // Stage 2 is assigned across the warp, not per group: lanes 2c and 2c+1 transform column c (16 for c = 0) of group 0
+  // and of group 1.  Both read the same twiddle row, and a shared load merges identical addresses of adjacent lanes
+  // (profiles/r1_microbench_smem_wavefronts.txt), so the tables are read once per warp instead of once per group.
+  const int lane = (grp_in_warp << 4) | j;
+  const int c = lane >> 1, g2 = lane & 1;
+  const int col = c == 0 ? 16 : c;
+  float4* const ywarp = yg - grp_in_warp * kYGroupF4;
   f2 ar[16], ai[16];
   {
-    const float4* rowp = yg + (col - 1) * kYPitch;
+    const float4* rowp = ywarp + g2 * kYGroupF4 + (col - 1) * kYPitch;
     static_for<0, 8>([&](auto ic) {
       constexpr int h = decltype(ic)::value;
-      // 64-bit loads: both groups of the warp read the same 16 words, one wavefront (a 128-bit load is served per
-      // half-warp: two wavefronts per group)
       const float2 ta = tw_row[2 * h], tb = tw_row[2 * h + 1];
       const float4 t = make_float4(ta.x, ta.y, tb.x, tb.y);
       const float4 v0 = rowp[2 * h], v1 = rowp[2 * h + 1];
@@ -457,12 +470,14 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
       }
     });
   }
-  // ---- column 0: thread t = j & 7 sums the 16 real bins Y_c[0] against W16^(c t), folded to 8 terms
+  // ---- column 0 of the lane's OWN group (half-warp): lanes 2t and 2t+1 both sum the 16 real bins Y_c[0] against
+  //      W16^(c t), folded to 8 terms (the pair's identical loads merge; the even lane stores)
+  const int t0 = (lane >> 1) & 7;
   f2 p0;
   {
     const float4* u4 = reinterpret_cast<const float4*>(yg + 16 * kYPitch);   // 16 x (A, B)
-    const float4* w4 = reinterpret_cast<const float4*>(c0_row);
-    const float sgn = (j & 1) ? -1.f : 1.f;
+    const float4* w4 = reinterpret_cast<const float4*>(c0_row);   // fft_c0_row: row t0
+    const float sgn = (t0 & 1) ? -1.f : 1.f;
     f2 cr = make_float2(0.f, 0.f), ci = make_float2(0.f, 0.f);
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
@@ -477,16 +492,17 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
     p0 = fma2(cr, cr, mul2(ci, ci));
   }
   fft_dit2<16>(ar, ai);
-  __syncwarp();   // every lane has consumed the transpose buffer: the spectra may overwrite it
+  __syncwarp();   // every lane has consumed the transpose buffers: the spectra may overwrite them
   {
-    float2* pb2 = reinterpret_cast<float2*>(pbuf4) + grp_in_warp * 256;
+    float2* pb2 = reinterpret_cast<float2*>(pbuf4) + g2 * kSpecPitch;
     static_for<0, 16>([&](auto ic) {
       constexpr int k2 = decltype(ic)::value;
       const f2 pw = fma2(ar[k2], ar[k2], mul2(ai[k2], ai[k2]));
       if constexpr (k2 < 8) pb2[col + 32 * k2] = pw;
-      else if (j != 0) pb2[(32 - col) + 32 * (15 - k2)] = pw;
+      else if (c != 0) pb2[(32 - col) + 32 * (15 - k2)] = pw;
     });
-    if (j < 8) pb2[32 * j] = p0;   // bin 0 carries no mel weight
+    // bin 0 carries no mel weight
+    if ((lane & 1) == 0) reinterpret_cast<float2*>(pbuf4)[grp_in_warp * kSpecPitch + 32 * t0] = p0;
   }
   __syncwarp();
 }
@@ -589,7 +605,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;   // this group's transpose buffer
   float4* pbuf4 = xbuf + warp * kYWarpF4;                          // this warp's power spectra (aliases both groups)
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = tw_s + kTw2Table + (j & 7) * kC0Pitch;
+  const float2* c0_row = fft_c0_row(tw_s, j);
 
     // Work distribution: the first tile of every CTA is static, later ones are claimed from a global counter (thread 0,
   // published through shared memory across the barrier that follows the staging).

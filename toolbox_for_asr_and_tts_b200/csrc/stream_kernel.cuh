@@ -210,7 +210,7 @@ stream_push_kernel(const StreamParams p) {
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;
   float4* pbuf4 = xbuf + warp * kYWarpF4;
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = tw_s + kTw2Table + (j & 7) * kC0Pitch;
+  const float2* c0_row = fft_c0_row(tw_s, j);
   if constexpr (PERQUAD) {
     // every warp fetches, transforms and mel-projects its own quads: no CTA-wide staging
     float* buf = e_s + warp * kQuadBuf;
