@@ -33,7 +33,7 @@ sys.path.insert(0, str(ROOT))
 CONF = dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6)
 BATCH = 256
 E2E_REPS = 3          # end-to-end loop: median of three runs
-PROFILE_EVERY = 4     # roofline sample: one fused-kernel launch in four is bracketed by CUDA events
+PROFILE_EVERY = 8     # roofline sample: one fused-kernel launch in eight is bracketed by CUDA events
 WORKLOAD = "paraformer-zh front-end, 256 synthetic utterances 1-30 s @16 kHz, length-packed (BASELINE.json configs[1])"
 METRIC = "audio_seconds_per_second"
 UNIT = "audio-s/s"
