@@ -24,32 +24,49 @@ VARIANT_CONFS = {
 VARIANT_SEED, VARIANT_LENS = 55, (16000, 4001)
 PARAFORMER = dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6)
 
-# Stated tolerances: log-mel max-abs <= 1e-3 against the float32 reference on broadband input;
-# after CMVN the bound scales with the largest Rescale entry.  Bins far below the frame's strongest mel bin sit at the
-# float32 noise floor of ANY 512-point float32 FFT: the absolute spectrum error is ~3e-7 of the frame's norm, so the
-# relative error of a bin d nepers below the peak grows like e^(d/2) (the reference's own float32 result is 2-5e-4 away
-# from float64 at d = 15, tests/parity_report.py; two kernels of this repository that only pair frames differently
-# differ by 0.18 at d = 25, tools/fuzz_gpu.py).  Hence: 1e-3 within 12 nepers of the peak, below that
-# max(3e-3, 2e-6 * e^(d/2)), and the mean error is bounded separately.
+# Stated tolerances.
+#   * log-mel vs the float32 reference: max-abs <= 1e-3, flat, for every bin that is not ill-conditioned; mean <= 2e-5.
+#   * ill-conditioned bins ("pure tones, near-silence; oracle fp32 vs fp64 differs up to 2.7e-2"):
+#     bins more than 12 nepers (52 dB) below the frame's strongest mel bin.  There a float32 FFT - the reference's own
+#     included - only carries the bin to its float32 noise floor, so a flat bound cannot be the statement.  Two forms:
+#       - broadband inputs (all golden vectors): a flat 3e-3 cap, nothing else;
+#       - inputs with deep spectral nulls (tones, silence next to signal, the 412 k-frame bench batch whose rarest bins
+#         reach 20 nepers): pass the float64 oracle as `ref64`; the CUDA path's error against float64 over those bins
+#         must stay within a small multiple of the float32 REFERENCE's own error against float64 over the same bins
+#         (rms <= 2x + 1e-4, max <= 4x + 3e-3): "as exact as the reference is determined", no depth formula.
+#     Bins within 1e-3 of the log floor log(FLT_EPSILON) are excluded, as BASELINE.md states.
 LOGMEL_ATOL = 1e-3
 LOGMEL_ATOL_DEEP = 3e-3
-LOGMEL_FLOOR_COEF = 2e-6
 LOGMEL_MEAN_ATOL = 2e-5
 DEEP_BIN_NEPERS = 12.0
+LOG_FLOOR = float(np.log(np.finfo(np.float32).eps))
 
 
-def assert_logmel_close(got, ref):
-    """got/ref: [..., n_mels] natural-log mel energies (no CMVN)."""
+def assert_logmel_close(got, ref, ref64=None):
+    """got/ref: [..., n_mels] natural-log mel energies (no CMVN); ref = float32 reference, ref64 = float64 oracle."""
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert got.shape == ref.shape
     err = np.abs(got - ref)
     depth = ref.max(axis=-1, keepdims=True) - ref
-    deep = depth > DEEP_BIN_NEPERS
-    assert err[~deep].max() <= LOGMEL_ATOL, err[~deep].max()
-    tol_deep = np.maximum(LOGMEL_ATOL_DEEP, LOGMEL_FLOOR_COEF * np.exp(np.minimum(depth, 60.0) / 2.0))
-    assert (err <= tol_deep)[deep].all(), float((err - tol_deep)[deep].max())
-    assert err.mean() <= LOGMEL_MEAN_ATOL, err.mean()
+    floor = ref <= LOG_FLOOR + 1e-3
+    deep = (depth > DEEP_BIN_NEPERS) & ~floor
+    well = ~deep & ~floor
+    if well.any():
+        assert err[well].max() <= LOGMEL_ATOL, float(err[well].max())
+        assert err[well].mean() <= LOGMEL_MEAN_ATOL, float(err[well].mean())
+    if floor.any():    # excluded from the comparison (BASELINE.md section 5); sanity only: nothing far above the floor
+        assert (got[floor] >= LOG_FLOOR - 1e-6).all() and (got[floor] <= LOG_FLOOR + 3.0).all()
+    if not deep.any():
+        return
+    if ref64 is None:
+        assert err[deep].max() <= LOGMEL_ATOL_DEEP, float(err[deep].max())
+        return
+    ref64 = np.asarray(ref64, dtype=np.float64)
+    e_got, e_ref = np.abs(got - ref64)[deep], np.abs(ref - ref64)[deep]
+    rms_got, rms_ref = float(np.sqrt((e_got ** 2).mean())), float(np.sqrt((e_ref ** 2).mean()))
+    assert rms_got <= 2.0 * rms_ref + 1e-4, (rms_got, rms_ref)
+    assert e_got.max() <= 4.0 * e_ref.max() + LOGMEL_ATOL_DEEP, (float(e_got.max()), float(e_ref.max()))
 
 
 def pytest_configure(config):

@@ -683,7 +683,7 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   TileDesc* d_tiles = reinterpret_cast<TileDesc*>((char*)d_shorts + align256((size_t)batch * sizeof(ShortDesc)));
   QuadDesc* d_quads = reinterpret_cast<QuadDesc*>(d_tiles);   // same region: a launch uses one of the two lists
   // the warp kernel does everything except the CMVN statistics (which need the row-major tile pass)
-  const bool use_warp = stats_dev == nullptr && warp_kernel_fits(h->L, h->S) && (!h->force_tile || pcm16) &&
+  const bool use_warp = stats_dev == nullptr && warp_kernel_fits(h->L, h->S, pcm16) && (!h->force_tile || pcm16) &&
                         pl.max_rows * (long long)h->D < (1ll << kTargetOffBits) - 1;
   // utterance table: inside the prep launch's parameters when it fits (warp path, no short utterances, which read
   // d_utts-independent descriptors of their own), else one pinned-buffer upload

@@ -8,8 +8,8 @@
 // Work decomposition ("fbank tile kernel"):
 //   * tile  = rows_per_tile LFR rows of one utterance = F <= kFMax consecutive frames (1 frame of halo is recomputed
 //             between neighbouring tiles);  persistent CTAs stride over the tile list.
-//   * stage = the tile's samples are read ONCE from HBM with 128-bit loads, pre-emphasised and kept in shared memory
-//             (each sample feeds 2.5 frames).
+//   * stage = the tile's raw samples are read ONCE from HBM with 128-bit loads and kept in shared memory (each sample
+//             feeds 2.5 frames); pre-emphasis and DC removal happen on the way into the FFT registers (quad_stage1).
 //   * FFT   = a group of 16 threads transforms two real frames at once, one frame per lane of packed f32x2 registers
 //             (FFMA2/FADD2/FMUL2: half the issue slots per flop).  Thread j owns samples n = 16 i + j: a REAL 32-point
 //             register FFT per thread (16-point complex FFT of even/odd samples + split), ONE shared-memory
@@ -114,8 +114,7 @@ struct TileParams {
 
 __host__ __device__ inline size_t tile_smem_bytes(int e_cap, int n_mels) {
   size_t b = 0;
-  b += (size_t)e_cap * 4;                           // staged, pre-emphasised samples
-  b += 2 * kFMax * 4;                               // raw first / last sample of each frame
+  b += (size_t)e_cap * 4;                           // staged raw samples
   b += (size_t)kWarps * kYWarpF4 * 16;              // transpose buffers (aliased by the power spectra)
   b += (size_t)kFMax * n_mels * 4;                  // log-mel of the tile
   b += kTw2Total * 8;                               // twiddles (stage 2 + column 0)
@@ -171,8 +170,7 @@ __device__ __forceinline__ float2 dither_pair(unsigned salt, unsigned fa, unsign
 
 // ------------------------------------------------------------------------------------------------------------
 // fbank_quad: log-mel of 4 consecutive frames (tile-local frames 4*quad .. 4*quad+3) by one warp.
-//   e_base   staged pre-emphasised samples, e_base[f*S + n] = x[n] - preemph*x[n-1] of tile-local frame f
-//   x0_s/xl_s raw first / last sample of every tile-local frame
+//   x_base   staged raw samples, x_base[f*S + n] = sample n of tile-local frame f
 //   win      this thread's window taps (n = 16*i + j), already scaled by 2^15 when upscaling
 //   xg       this 16-thread group's transpose buffer; pbuf4 = the warp's spectra, [2 groups][256 bins] x (frame A, frame B),
 //            aliasing the warp's two xg's
@@ -305,14 +303,24 @@ __device__ __forceinline__ const float2* fft_c0_row(const float2* tw_s, int j) {
 //            bins beyond 256 are the conjugates of bins (32 - col) + 32 (15 - k2) and have the same power.
 //   column 0 thread t < 8: X[32 t] = sum_c Y_c[0] W16^(c t)  (real input: 8 folded terms).
 // All stored powers are 4 |X[k]|^2 (the mel weights carry the 0.25).
-// Stage 1 of a group's frame pair: load, [dither], frame-start rule, DC removal, window, real 32-point FFT.
-//   eA        first (pre-emphasised) sample of frame A in shared memory; frame B starts S samples later
-//   x0 / xl   raw first / last sample of the two frames (lane .x = frame A)
+// Stage 1 of a group's frame pair: load RAW samples, [dither], pre-emphasis with the frame-start rule, DC removal,
+// window, real 32-point FFT.
+//   xA   first raw sample of frame A in shared memory (x / 32768 scale or not: the window table carries the 2^15);
+//        frame B starts S samples later.  The sample before a frame's first one is never read: the reference
+//        replicates the first sample there (TA:193-198), and that is what thread 0 loads instead.
+// Pre-emphasis  e[n] = x[n] - p x[n-1]  is one FMA per (frame, sample) on the two loaded values.  The frame mean is
+// taken from the RAW samples and enters as (1-p)*mean inside the window FMA:
+//   z[n] = w[n] * ((x[n] - mean) - p (x[n-1] - mean)) = e[n] * w[n] - ((1-p) mean) * w[n]          (TA:183-204)
+// Both choices are about the weakest mel bins (FFT bins 1..2, 15 nepers below the rest after DC removal and
+// pre-emphasis): an error of the subtracted constant is DC-coherent over the frame, i.e. it lands exactly there.
+// Summing raw samples keeps that error (1-p) = 0.03 times smaller than recovering the mean from the sum of the
+// pre-emphasised samples, and subtracting inside the FMA avoids rounding e[n] - const to e's grid (the same error
+// on every sample of a binade).  profiles/r2_parity_report.txt has the before / after.
 // Out: zr/zi[1..15] = 2 Y[k1], zr/zi[8] = Y[8], y0 = Y[0], y16 = Y[16] (real).
 // SR > 0: the frame shift is SR 16-sample rows (compile-time), so frame B's row i is frame A's row i + SR and the
 // overlapping rows are loaded once.
 template <int NROWS, bool EXACT, bool DITHER, int SR = 0>
-__device__ __forceinline__ void quad_stage1(const float* eA, f2 x0, f2 xl, bool vA, bool vB, int S, int L,
+__device__ __forceinline__ void quad_stage1(const float* xA, bool vA, bool vB, int S, int L,
                                             const float (&win)[NROWS + 1], float preemph, int remove_dc, float dither,
                                             unsigned long long seed, unsigned utt, unsigned frame_abs_a, int j, int g,
                                             f2 (&zr)[16], f2 (&zi)[16], f2& y0, f2& y16) {
@@ -322,41 +330,68 @@ __device__ __forceinline__ void quad_stage1(const float* eA, f2 x0, f2 xl, bool 
   static_assert(LIVE == 16 || LIVE > 8, "frame rows must cover more than half of the FFT");
   {
     f2 y[2 * LIVE];
+    f2 s;   // raw frame sums of this thread's samples
     // thread j owns samples n = 16*row + j of both frames; register i holds row i - g
-    eA += j - 16 * g;
+    xA += j - 16 * g;
     auto row_in = [&](int i) {
       if constexpr (EXACT) return ROT ? (i == 0 ? g == 0 : (i == NROWS ? g == 1 : i < NROWS)) : true;
       else return (i - g >= 0) && (i < NR) && (16 * (i - g) + j < L);
     };
-    if constexpr (SR > 0 && EXACT) {
-      float r[2 * LIVE + SR];
+    const bool j0 = j == 0;
+    if constexpr (SR > 0 && EXACT && ROT) {
+      static_assert(SR < NROWS, "frames of a pair must overlap");
+      constexpr int NREG = 2 * LIVE + SR;
+      float r[NREG], pr[NREG];
 #pragma unroll
-      for (int i = 0; i < 2 * LIVE + SR; ++i) {
+      for (int i = 0; i < NREG; ++i) {
         const bool need = (i < 2 * LIVE && vA && row_in(i)) || (i >= SR && vB && row_in(i - SR));
-        r[i] = need ? eA[16 * i] : 0.f;
+        const bool first = j0 && i == g;           // frame A's n = 0: its predecessor is the sample itself
+        r[i] = need ? xA[16 * i] : 0.f;
+        pr[i] = need ? xA[16 * i - (first ? 0 : 1)] : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 2 * LIVE; ++i) {
-        y[i].x = (vA && row_in(i)) ? r[i] : 0.f;
-        y[i].y = (vB && row_in(i)) ? r[i + SR] : 0.f;
+        const float pb = (j0 && i == g) ? r[i + SR] : pr[i + SR];   // frame B's n = 0
+        y[i].x = row_in(i) ? fmaf(-preemph, pr[i], r[i]) : 0.f;
+        y[i].y = row_in(i) ? fmaf(-preemph, pb, r[i + SR]) : 0.f;
       }
+      // raw sums: frame A = registers g .. g+NROWS-1, frame B = the same + SR; registers SR+1 .. NROWS-1 are common
+      float c4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = SR + 1; k < NROWS; ++k) c4[(k - SR - 1) & 3] += r[k];
+      float a2[2] = {g == 0 ? r[0] : r[NROWS], 0.f}, b2[2] = {g == 0 ? r[SR] : r[NROWS + SR], 0.f};
+#pragma unroll
+      for (int k = 1; k <= SR; ++k) a2[k & 1] += r[k];
+#pragma unroll
+      for (int k = NROWS; k < NROWS + SR; ++k) b2[k & 1] += r[k];
+      const float common = (c4[0] + c4[1]) + (c4[2] + c4[3]);
+      s = make_float2(common + (a2[0] + a2[1]), common + (b2[0] + b2[1]));
     } else {
-      const float* eB = eA + S;
+      const float* xB = xA + S;
+      f2 s4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s4[i] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 2 * LIVE; ++i) {
         const bool in = row_in(i);
-        y[i].x = (vA && in) ? eA[16 * i] : 0.f;
-        y[i].y = (vB && in) ? eB[16 * i] : 0.f;
+        const int back = (j0 && i == g) ? 0 : 1;
+        f2 x = make_float2(0.f, 0.f), px = make_float2(0.f, 0.f);
+        if (vA && in) { x.x = xA[16 * i]; px.x = xA[16 * i - back]; }
+        if (vB && in) { x.y = xB[16 * i]; px.y = xB[16 * i - back]; }
+        y[i] = fma2s(px, -preemph, x);
+        s4[i & 3] = add2(s4[i & 3], x);
       }
+      s = add2(add2(s4[0], s4[1]), add2(s4[2], s4[3]));
     }
     if constexpr (DITHER) {
-      // x'[n] = x[n] + dither*g(frame, n)  (TA:179-181); the pre-emphasised value picks up
-      // dither*(g(n) - preemph*g(n-1)).  Every thread draws the noise of its own samples once; g(n-1) is the previous
-      // lane's value of the same row (lane 15's value of the previous row for lane 0), fetched with one shuffle.
+      // x'[n] = x[n] + dither*g(frame, n)  (TA:179-181): the pre-emphasised value picks up
+      // dither*(g(n) - preemph*g(n-1)) and the raw sum dither*g(n).  Every thread draws the noise of its own samples
+      // once; g(n-1) is the previous lane's value of the same row (lane 15's value of the previous row for lane 0),
+      // fetched with one shuffle.
       const unsigned fa = frame_abs_a;
       const unsigned salt = dither_salt(seed, utt);
       const int src = (threadIdx.x & 16) | ((j + 15) & 15);
-      f2 rot_prev = make_float2(0.f, 0.f);
+      f2 rot_prev = make_float2(0.f, 0.f), gs = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         const int n = 16 * (i - g) + j;
@@ -369,27 +404,12 @@ __device__ __forceinline__ void quad_stage1(const float* eA, f2 x0, f2 xl, bool 
         const f2 prev = n == 0 ? gn : (j == 0 ? rot_prev : rot);   // n = 0: replicate rule, g(-1) := g(0)
         rot_prev = rot;
         if (live) {
-          const f2 d = mul2s(fma2s(prev, -preemph, gn), dither);
-          if (vA) y[i].x += d.x;
-          if (vB) y[i].y += d.y;
+          y[i] = fma2s(fma2s(prev, -preemph, gn), dither, y[i]);
+          gs = add2(gs, gn);
         }
       }
-      const f2 g0 = dither_pair(salt, fa, 0u), gl = dither_pair(salt, fa, (unsigned)(L - 1));
-      if (vA) { x0.x += dither * g0.x; xl.x += dither * gl.x; }
-      if (vB) { x0.y += dither * g0.y; xl.y += dither * gl.y; }
+      s = fma2s(gs, dither, s);
     }
-    if (j == 0) {  // replicate rule at the frame start: y[0] = x[0] - preemph * x[0]  (TA:193-198)
-      const f2 yf = fma2s(x0, -preemph, x0);
-      if (g == 0) y[0] = yf;
-      if constexpr (ROT) { if (g == 1) y[1] = yf; }
-    }
-    // frame sums as 4 independent chains (a serial chain of 25 adds would expose the FADD latency)
-    f2 s4[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s4[i] = y[i];
-#pragma unroll
-    for (int i = 4; i < NR; ++i) s4[i & 3] = add2(s4[i & 3], y[i]);
-    f2 s = add2(add2(s4[0], s4[1]), add2(s4[2], s4[3]));
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) {
       f2 t;
@@ -397,11 +417,11 @@ __device__ __forceinline__ void quad_stage1(const float* eA, f2 x0, f2 xl, bool 
       t.y = __shfl_xor_sync(0xffffffffu, s.y, o);
       s = add2(s, t);
     }
-    // (1-preemph) * mean(frame), recovered from the sum of the pre-emphasised samples
-    f2 mean = make_float2(0.f, 0.f);
-    if (remove_dc) mean = mul2s(fma2s(sub2(xl, x0), -preemph, s), 1.0f / (float)L);
+    // -(1-p) * mean(frame), applied inside the window FMA: e*w - ((1-p) mean)*w rounds once, after the subtraction
+    f2 nmean = make_float2(0.f, 0.f);
+    if (remove_dc) nmean = mul2s(s, -(1.0f - preemph) / (float)L);
 #pragma unroll
-    for (int i = 0; i < NR; ++i) y[i] = mul2s(sub2(y[i], mean), win[i]);
+    for (int i = 0; i < NR; ++i) y[i] = fma2s(y[i], win[i], mul2s(nmean, win[i]));
     // z[m] = y[2m] + i y[2m+1] at bit-reversed positions (decimation in time)
     static_for<0, 16>([&](auto ic) {
       constexpr int m = decltype(ic)::value;
@@ -509,7 +529,7 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
 
 // Log-mel of tile-local frames 4*quad .. 4*quad+3 into logmel[F][M] (shared memory): tile and streaming kernels.
 template <int NROWS, bool EXACT, bool DITHER, class MELS>
-__device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_s, const float* xl_s, int F, int quad,
+__device__ __forceinline__ void fbank_quad(const float* x_base, int F, int quad,
                                            int S, int L, const float (&win)[NROWS + 1], float4* yg, float4* pbuf4,
                                            const float2* tw_row, const float2* c0_row, const MelTab& mel, int M,
                                            float preemph, int remove_dc, float log_floor, float dither,
@@ -518,11 +538,8 @@ __device__ __forceinline__ void fbank_quad(const float* e_base, const float* x0_
   const int g = NROWS < 32 ? grp_in_warp : 0;
   const int fA = 4 * quad + 2 * grp_in_warp;   // tile-local frame of lane .x; fA + 1 is lane .y
   const bool vA = fA < F, vB = fA + 1 < F;
-  f2 x0 = make_float2(0.f, 0.f), xl = make_float2(0.f, 0.f);
-  if (vA) { x0.x = x0_s[fA]; xl.x = xl_s[fA]; }
-  if (vB) { x0.y = x0_s[fA + 1]; xl.y = xl_s[fA + 1]; }
   f2 zr[16], zi[16], y0, y16;
-  quad_stage1<NROWS, EXACT, DITHER>(e_base + fA * S, x0, xl, vA, vB, S, L, win, preemph, remove_dc, dither, seed, utt,
+  quad_stage1<NROWS, EXACT, DITHER>(x_base + fA * S, vA, vB, S, L, win, preemph, remove_dc, dither, seed, utt,
                                     frame_abs0 + (unsigned)fA, j, g, zr, zi, y0, y16);
   __syncwarp();   // earlier readers of the (aliased) buffer are done
   quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
@@ -547,10 +564,8 @@ template <int NROWS, bool EXACT, bool DITHER, bool STATS, class MELS>
 __global__ void __launch_bounds__(kCtaThreads, 3)
 fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* e_s = reinterpret_cast<float*>(smem_raw);
-  float* x0_s = e_s + p.e_cap;
-  float* xl_s = x0_s + kFMax;
-  float4* xbuf = reinterpret_cast<float4*>(xl_s + kFMax);
+  float* e_s = reinterpret_cast<float*>(smem_raw);              // the tile's raw samples
+  float4* xbuf = reinterpret_cast<float4*>(e_s + p.e_cap);
   float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * kYWarpF4);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + kFMax * p.n_mels);
 
@@ -621,26 +636,21 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
     const long long ga = g0 - a_off;                          // 16-byte aligned load grid
     const int n_s = (F - 1) * S + L;
 
-    // ---- stage: HBM -> (pre-emphasis) -> shared, 128-bit both ways.  All loads of a batch are issued before the
-    //      first use, so a tile pays one memory latency instead of one per iteration.
+    // ---- stage: HBM -> shared, 128-bit both ways (raw samples: pre-emphasis happens in stage 1).  All loads of a
+    //      batch are issued before the first use, so a tile pays one memory latency instead of one per iteration.
     {
       const int nv = (a_off + n_s + 3) >> 2;
-      const bool interior = ga >= 1 && ga + 4ll * nv <= p.wave_total;   // no per-element bounds checks needed
+      const bool interior = ga >= 0 && ga + 4ll * nv <= p.wave_total;   // no per-element bounds checks needed
       const float* src = p.wave + ga;
       constexpr int kBatch = 11;   // 11 x 128 float4 cover a 400/160 tile in one batch: one exposed memory latency
       for (int vb = 0; vb < nv; vb += kBatch * kCtaThreads) {
         float4 x[kBatch];
-        float pv[kBatch];
         if (interior) {
 #pragma unroll
           for (int u = 0; u < kBatch; ++u) {
             const int v = vb + u * kCtaThreads + tid;
             x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            pv[u] = 0.f;
-            if (v < nv) {
-              x[u] = ldg_stream4(src + 4 * v);
-              if (lane == 0) pv[u] = src[4 * v - 1];
-            }
+            if (v < nv) x[u] = ldg_stream4(src + 4 * v);
           }
         } else {
 #pragma unroll
@@ -648,38 +658,19 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
             const int v = vb + u * kCtaThreads + tid;
             const long long ab = ga + 4ll * v;
             x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            pv[u] = 0.f;
             if (v < nv) {
               if (ab >= 0 && ab < p.wave_total) x[u].x = p.wave[ab];
               if (ab + 1 >= 0 && ab + 1 < p.wave_total) x[u].y = p.wave[ab + 1];
               if (ab + 2 >= 0 && ab + 2 < p.wave_total) x[u].z = p.wave[ab + 2];
               if (ab + 3 >= 0 && ab + 3 < p.wave_total) x[u].w = p.wave[ab + 3];
-              if (lane == 0 && ab >= 1 && ab - 1 < p.wave_total) pv[u] = p.wave[ab - 1];
             }
           }
-        }
-        // the sample before each float4 comes from the previous lane (all shuffles first: they are independent)
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          const float up1 = __shfl_up_sync(0xffffffffu, x[u].w, 1);
-          if (lane != 0) pv[u] = up1;
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
           const int v = vb + u * kCtaThreads + tid;
-          if (v < nv) {
-            float4 e;
-            e.x = fmaf(-p.preemph, pv[u], x[u].x);
-            e.y = fmaf(-p.preemph, x[u].x, x[u].y);
-            e.z = fmaf(-p.preemph, x[u].y, x[u].z);
-            e.w = fmaf(-p.preemph, x[u].z, x[u].w);
-            *reinterpret_cast<float4*>(e_s + 4 * v) = e;
-          }
+          if (v < nv) *reinterpret_cast<float4*>(e_s + 4 * v) = x[u];
         }
-      }
-      if (tid < F) {
-        x0_s[tid] = p.wave[g0 + (long long)tid * S];
-        xl_s[tid] = p.wave[g0 + (long long)tid * S + L - 1];
       }
     }
     __syncthreads();
@@ -699,7 +690,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
 
     // ---- per warp: quads of 4 frames (2 groups x 2 frames), no CTA-wide sync inside
     for (int quad = warp; 4 * quad < F; quad += kWarps)
-      fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s + a_off, x0_s, xl_s, F, quad, S, L, win, yg, pbuf4, tw_row, c0_row, mel, M,
+      fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s + a_off, F, quad, S, L, win, yg, pbuf4, tw_row, c0_row, mel, M,
                                        p.preemph, p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)utt,
                                        (unsigned)f_lo, logmel_s, j, grp_in_warp, lane);
     __syncthreads();
@@ -732,7 +723,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
     }
     cur = nxt;
     tile = tile_next;
-    // no barrier here: the next tile's staging only writes e_s / x0_s / xl_s, whose last readers finished before the
+    // no barrier here: the next tile's staging only writes e_s, whose last readers finished before the
     // barrier above, and logmel_s is not written again before the barrier that follows the next staging.
   }
 

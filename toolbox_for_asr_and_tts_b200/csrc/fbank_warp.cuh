@@ -3,9 +3,10 @@
 //
 //   * work list  = QuadDesc[n_quads], built on the device (build_quads_kernel); persistent warps stride over it, so
 //                  the 4 warps of a CTA work on neighbouring quads and share their 240 overlapping samples through L1.
-//   * samples    = the quad's 880 samples are prefetched into L2 one quad AHEAD (one line per lane), then read with
-//                  128-bit loads, pre-emphasised in registers and stored to the warp's private buffer; the other 15
-//                  warps of the SM cover the L2 latency.
+//   * samples    = the quad's 880 raw samples arrive by ONE bulk copy (cp.async.bulk, 1-D TMA) per quad into the warp's
+//                  private 3.5 KB buffer, issued by lane 0 a whole quad ahead and completed on the warp's own mbarrier:
+//                  no registers, no LSU-pipe traffic, no exposed L2 latency.  (Ends of the wave buffer and int16 PCM:
+//                  128-bit loads -> registers -> shared, prefetched into L2 one quad ahead.)
 //   * FFT / mel  = quad_stage1 / quad_stage2 / mel_stage of fbank_tile.cuh (packed f32x2 real FFT, interval mel).
 //   * LFR + CMVN = closed form, per quad: the 4 log-mel frames go through a 1.25 KB per-warp staging tile and are
 //                  written as 128-bit rows wherever clamp(n*i + jj - left, 0, T-1) == f  (VF:40-60: frame f is slot jj
@@ -17,6 +18,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "fbank_tile.cuh"
 
@@ -64,10 +67,14 @@ struct QuadParams {
 };
 
 __host__ __device__ inline size_t warp_smem_bytes() {
-  return (size_t)kWarps * kQuadBuf * 4 + (size_t)kWarps * kYWarpF4 * 16 + (size_t)kTw2Total * 8;
+  return (size_t)kWarps * kQuadBuf * 4 + (size_t)kWarps * kYWarpF4 * 16 + (size_t)kTw2Total * 8 + (size_t)kWarps * 8;
 }
-// the quad of a (frame_len, frame_shift) pair fits the per-warp buffer (3 floats of alignment slack)
-__host__ __device__ inline bool warp_kernel_fits(int L, int S) { return 3 + 3 * S + L <= kQuadBuf; }
+// The quad of a (frame_len, frame_shift) pair fits the per-warp buffer: whole 16-byte vectors are stored, starting up
+// to one vector minus one sample before the quad's first sample (3 floats for float32 PCM, 7 for int16 PCM).
+__host__ __device__ inline bool warp_kernel_fits(int L, int S, bool pcm16 = false) {
+  const int per = pcm16 ? 8 : 4;
+  return ((per - 1 + 3 * S + L + per - 1) / per) * per <= kQuadBuf;
+}
 
 // Where frame f of an utterance with T frames / `rows` LFR rows goes (VF:40-60): slot jj of row i wherever
 // n*i + jj - left == f.  With (i_hi, jj1) the solution of largest i, the others are (i_hi - k, jj1 + k n).  Two are
@@ -90,135 +97,125 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
   return v;
 }
 
-// Samples of a quad: HBM/L2 -> registers (128-bit streaming loads on the 16-byte grid of the wave buffer; the samples
-// must not evict the mel / CMVN tables from the few KB of L1 left beside 4 CTAs) -> pre-emphasis -> the warp's buffer:
-// buf[a_off + n] = x[n] - preemph * x[n-1] for sample n of the quad's first frame (the predecessor of a vector's first
-// sample comes from the previous lane through one shuffle).  Also returns the raw first / last sample of the group's
-// two frames (x0 / xl, for the DC correction), read by lanes 0..7 and shuffled.  Quads touching the ends of the wave
-// buffer load element-wise.  Returns a_off.
+// ---- samples of a quad: HBM -> the warp's buffer, raw (pre-emphasis and DC removal happen in quad_stage1) --------
+// buf[a_off + n] = sample n of the quad's first frame; a_off = position of that sample on the 16-byte grid of the
+// wave buffer (0 for aligned offsets).
+//
+// float32 PCM, interior quads: ONE bulk copy (cp.async.bulk = 1-D TMA, SASS UBLKCP) per quad, issued by lane 0 a whole
+// quad ahead and completed on the warp's own mbarrier, so the samples never pass through registers or the LSU pipe
+// and no L2 latency is exposed.  The buffer is single: it is only read by the stage-1 loads at the top of a quad, and
+// the next quad's copy is issued right after them.
+// Quads that touch the ends of the wave buffer (a bulk copy needs 16-byte aligned, in-bounds ends) and int16 PCM take
+// the generic fill below: vector loads on the 16-byte grid -> registers -> shared.
 template <class SampleT>
-__device__ __forceinline__ int quad_samples(const QuadParams& p, long long g0, int nF, int lane, int grp_in_warp,
-                                            float* buf, f2& x0, f2& xl);
-
-template <>
-__device__ __forceinline__ int quad_samples<float>(const QuadParams& p, long long g0, int nF, int lane, int grp_in_warp,
-                                                   float* buf, f2& x0, f2& xl) {
-  const float* wave = static_cast<const float*>(p.wave);
-  const unsigned wave_mis = (unsigned)((reinterpret_cast<uintptr_t>(wave) >> 2) & 3);
-  const int a_off = (int)((wave_mis + (unsigned)(g0 & 3)) & 3);
-  const long long ga = g0 - a_off;
-  const int nv = (a_off + (nF - 1) * p.frame_shift + p.frame_len + 3) >> 2;
-  float4 x[kQuadVecs];
-  if (ga >= 0 && ga + 4ll * nv <= p.wave_total) {
-    const float* src = wave + ga + 4 * lane;
-#pragma unroll
-    for (int u = 0; u < kQuadVecs; ++u)
-      x[u] = lane + 32 * u < nv ? ldg_stream4(src + 128 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
-  } else {
-#pragma unroll
-    for (int u = 0; u < kQuadVecs; ++u) {
-      const long long ab = ga + 4ll * (lane + 32 * u);
-      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane + 32 * u < nv) {
-        if (ab >= 0 && ab < p.wave_total) x[u].x = wave[ab];
-        if (ab + 1 >= 0 && ab + 1 < p.wave_total) x[u].y = wave[ab + 1];
-        if (ab + 2 >= 0 && ab + 2 < p.wave_total) x[u].z = wave[ab + 2];
-        if (ab + 3 >= 0 && ab + 3 < p.wave_total) x[u].w = wave[ab + 3];
-      }
-    }
-  }
-  float cap = 0.f;
-  if (lane < 8 && (lane & 3) < nF)
-    cap = __ldg(wave + g0 + (long long)(lane & 3) * p.frame_shift + (lane < 4 ? 0 : p.frame_len - 1));
-  float4* buf4 = reinterpret_cast<float4*>(buf);
-  float below = 0.f;   // lane 31's last sample of the previous vector row (lane 0's predecessor)
-#pragma unroll
-  for (int u = 0; u < kQuadVecs; ++u) {
-    const float rot = __shfl_sync(0xffffffffu, x[u].w, (lane + 31) & 31);
-    const float pv = lane == 0 ? below : rot;
-    below = rot;   // only lane 0 uses it: there rot is lane 31's value
-    if (lane + 32 * u < nv) {
-      float4 e;
-      e.x = fmaf(-p.preemph, pv, x[u].x);
-      e.y = fmaf(-p.preemph, x[u].x, x[u].y);
-      e.z = fmaf(-p.preemph, x[u].y, x[u].z);
-      e.w = fmaf(-p.preemph, x[u].z, x[u].w);
-      buf4[lane + 32 * u] = e;
-    }
-  }
-  const int fa = 2 * grp_in_warp;
-  x0.x = __shfl_sync(0xffffffffu, cap, fa);
-  x0.y = __shfl_sync(0xffffffffu, cap, fa + 1);
-  xl.x = __shfl_sync(0xffffffffu, cap, fa + 4);
-  xl.y = __shfl_sync(0xffffffffu, cap, fa + 5);
-  return a_off;
+__device__ __forceinline__ int quad_a_off(const void* wave, long long g0) {
+  constexpr int kPer = 16 / (int)sizeof(SampleT);   // samples per 16-byte vector
+  const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(wave) / sizeof(SampleT)) & (kPer - 1));
+  return (int)((mis + (unsigned)(g0 & (kPer - 1))) & (kPer - 1));
 }
 
-// int16 PCM: 8 samples per 16-byte vector, converted with the reference's own rule float(s) / 32768 (exact), so the
-// result is bit-identical to handing the converted float32 buffer to the float path - at half the HBM / PCIe bytes.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Lane 0 only.  True when the quad's samples can be fetched with one bulk copy; then the copy is in flight.
+__device__ __forceinline__ bool quad_fill_tma(const float* wave, long long wave_total, long long g0, int n_samples,
+                                              float* buf, unsigned long long* bar) {
+  const int a_off = quad_a_off<float>(wave, g0);
+  const long long ga = g0 - a_off;
+  const int nv = (a_off + n_samples + 3) >> 2;
+  if (ga < 0 || ga + 4ll * nv > wave_total) return false;
+  const unsigned bytes = 16u * (unsigned)nv;
+  // earlier generic-proxy accesses of the buffer (the generic fill's stores) are ordered before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(buf)), "l"(wave + ga), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+  return true;
+}
+
+template <class SampleT>
+__device__ __forceinline__ void quad_fill_generic(const void* wave_any, long long wave_total, long long g0, int n_samples,
+                                                  int lane, float* buf);
+
+template <>
+__device__ __forceinline__ void quad_fill_generic<float>(const void* wave_any, long long wave_total, long long g0,
+                                                         int n_samples, int lane, float* buf) {
+  const float* wave = static_cast<const float*>(wave_any);
+  const int a_off = quad_a_off<float>(wave, g0);
+  const long long ga = g0 - a_off;
+  const int nv = (a_off + n_samples + 3) >> 2;
+  float4* buf4 = reinterpret_cast<float4*>(buf);
+#pragma unroll
+  for (int u = 0; u < kQuadVecs; ++u) {
+    if (lane + 32 * u >= nv) continue;
+    const long long ab = ga + 4ll * (lane + 32 * u);
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ab >= 0 && ab + 4 <= wave_total) {
+      x = ldg_stream4(wave + ab);
+    } else {
+      if (ab >= 0 && ab < wave_total) x.x = wave[ab];
+      if (ab + 1 >= 0 && ab + 1 < wave_total) x.y = wave[ab + 1];
+      if (ab + 2 >= 0 && ab + 2 < wave_total) x.z = wave[ab + 2];
+      if (ab + 3 >= 0 && ab + 3 < wave_total) x.w = wave[ab + 3];
+    }
+    buf4[lane + 32 * u] = x;
+  }
+}
+
+// int16 PCM: 8 samples per 16-byte vector, converted with the reference's own rule float(s) / 32768 (exact,
+// R:voice_interface.py:1008-1013), so the result is bit-identical to handing the converted float32 buffer to the
+// float path - at half the HBM / PCIe bytes.
 constexpr int kQuadVecs16 = 4;
 template <>
-__device__ __forceinline__ int quad_samples<short>(const QuadParams& p, long long g0, int nF, int lane, int grp_in_warp,
-                                                   float* buf, f2& x0, f2& xl) {
-  const short* wave = static_cast<const short*>(p.wave);
-  const unsigned wave_mis = (unsigned)((reinterpret_cast<uintptr_t>(wave) >> 1) & 7);
-  const int a_off = (int)((wave_mis + (unsigned)(g0 & 7)) & 7);
+__device__ __forceinline__ void quad_fill_generic<short>(const void* wave_any, long long wave_total, long long g0,
+                                                         int n_samples, int lane, float* buf) {
+  const short* wave = static_cast<const short*>(wave_any);
+  const int a_off = quad_a_off<short>(wave, g0);
   const long long ga = g0 - a_off;
-  const int nv = (a_off + (nF - 1) * p.frame_shift + p.frame_len + 7) >> 3;
+  const int nv = (a_off + n_samples + 7) >> 3;
   constexpr float kScale = 1.0f / 32768.0f;
-  float x[kQuadVecs16][8];
-  if (ga >= 0 && ga + 8ll * nv <= p.wave_total) {
-    const short* src = wave + ga + 8 * lane;
-#pragma unroll
-    for (int u = 0; u < kQuadVecs16; ++u) {
-      uint4 r = make_uint4(0u, 0u, 0u, 0u);
-      if (lane + 32 * u < nv) r = ldg_stream_u4(src + 256 * u);
-      const unsigned w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        x[u][2 * k] = (float)(short)(w[k] & 0xffffu) * kScale;
-        x[u][2 * k + 1] = (float)(short)(w[k] >> 16) * kScale;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int u = 0; u < kQuadVecs16; ++u)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const long long ab = ga + 8ll * (lane + 32 * u) + k;
-        x[u][k] = (lane + 32 * u < nv && ab >= 0 && ab < p.wave_total) ? (float)wave[ab] * kScale : 0.f;
-      }
-  }
-  float cap = 0.f;
-  if (lane < 8 && (lane & 3) < nF)
-    cap = (float)wave[g0 + (long long)(lane & 3) * p.frame_shift + (lane < 4 ? 0 : p.frame_len - 1)] * kScale;
   float4* buf4 = reinterpret_cast<float4*>(buf);
-  float below = 0.f;
+  uint4 r[kQuadVecs16];
+  bool fast[kQuadVecs16];
+#pragma unroll
+  for (int u = 0; u < kQuadVecs16; ++u) {   // all vector loads first: one exposed latency
+    const long long ab = ga + 8ll * (lane + 32 * u);
+    fast[u] = lane + 32 * u < nv && ab >= 0 && ab + 8 <= wave_total;
+    r[u] = fast[u] ? ldg_stream_u4(wave + ab) : make_uint4(0u, 0u, 0u, 0u);
+  }
 #pragma unroll
   for (int u = 0; u < kQuadVecs16; ++u) {
-    const float rot = __shfl_sync(0xffffffffu, x[u][7], (lane + 31) & 31);
-    const float pv = lane == 0 ? below : rot;
-    below = rot;
-    if (lane + 32 * u < nv) {
-      float4 e0, e1;
-      e0.x = fmaf(-p.preemph, pv, x[u][0]);
-      e0.y = fmaf(-p.preemph, x[u][0], x[u][1]);
-      e0.z = fmaf(-p.preemph, x[u][1], x[u][2]);
-      e0.w = fmaf(-p.preemph, x[u][2], x[u][3]);
-      e1.x = fmaf(-p.preemph, x[u][3], x[u][4]);
-      e1.y = fmaf(-p.preemph, x[u][4], x[u][5]);
-      e1.z = fmaf(-p.preemph, x[u][5], x[u][6]);
-      e1.w = fmaf(-p.preemph, x[u][6], x[u][7]);
-      buf4[2 * (lane + 32 * u)] = e0;
-      buf4[2 * (lane + 32 * u) + 1] = e1;
+    if (lane + 32 * u >= nv) continue;
+    float x[8];
+    if (fast[u]) {
+      const unsigned w[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        x[2 * k] = (float)(short)(w[k] & 0xffffu) * kScale;
+        x[2 * k + 1] = (float)(short)(w[k] >> 16) * kScale;
+      }
+    } else {
+      const long long ab = ga + 8ll * (lane + 32 * u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = (ab + k >= 0 && ab + k < wave_total) ? (float)wave[ab + k] * kScale : 0.f;
     }
+    buf4[2 * (lane + 32 * u)] = make_float4(x[0], x[1], x[2], x[3]);
+    buf4[2 * (lane + 32 * u) + 1] = make_float4(x[4], x[5], x[6], x[7]);
   }
-  const int fa = 2 * grp_in_warp;
-  x0.x = __shfl_sync(0xffffffffu, cap, fa);
-  x0.y = __shfl_sync(0xffffffffu, cap, fa + 1);
-  xl.x = __shfl_sync(0xffffffffu, cap, fa + 4);
-  xl.y = __shfl_sync(0xffffffffu, cap, fa + 5);
-  return a_off;
 }
 
 // SR: frame shift in 16-sample rows when it is a whole number of rows and known at compile time (10 for 400/160):
@@ -230,6 +227,8 @@ fbank_warp_kernel(const QuadParams p) {
   float* bufs = reinterpret_cast<float*>(smem_raw);
   float4* xbuf = reinterpret_cast<float4*>(bufs + kWarps * kQuadBuf);
   float2* tw_s = reinterpret_cast<float2*>(xbuf + kWarps * kYWarpF4);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw_s + kTw2Total);
+  constexpr bool kTma = std::is_same<SampleT, float>::value;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -243,19 +242,24 @@ fbank_warp_kernel(const QuadParams p) {
   const int lfr_left = (lfr_m - 1) / 2;
 
   for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  if (kTma && lane == 0) {
+    mbar_init(bars + warp, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy
+  }
   MelTab mel;
   mel.w = p.mel_w; mel.lo = p.mel_lo; mel.rounds = p.mel_rounds;
 #pragma unroll
   for (int r = 0; r < kMelRounds; ++r) { mel.cnt[r] = p.mel_cnt[r]; mel.base[r] = p.mel_base[r]; }
   float win[NROWS + 1];
   load_window_taps<NROWS>(win, p.window, j, grp_in_warp);
-  __syncthreads();   // the only CTA-wide barrier: the twiddle tables
+  __syncthreads();   // the only CTA-wide barrier: the twiddle tables (and the mbarriers)
   // Launched as a programmatic dependent of prep_warp_kernel (b200fe.cu: launch_warp): everything above reads
   // per-handle constants only and overlaps the tail of that kernel; the quad list and the work counter are its
   // output.  (A no-op when the launch carries no such attribute.)
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   float* buf = bufs + warp * kQuadBuf;
+  unsigned long long* bar = bars + warp;
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;
   float4* pbuf4 = xbuf + warp * kYWarpF4;
   float* lm_s = reinterpret_cast<float*>(pbuf4 + kSpecF4);   // log-mel staging tile, behind the warp's spectra
@@ -266,7 +270,7 @@ fbank_warp_kernel(const QuadParams p) {
 
   // The 64-byte descriptor is read in pieces, each just before it is needed, so that it never occupies 16 registers:
   // {g0, utt, f0} and {nF, T, rows} at the top of a quad, the targets before the mel stage, and the next quad's
-  // {g0, nF} (for its sample loads) one quad ahead.
+  // {g0, nF} (for its sample fetch) one quad ahead.
   // Work distribution: the first quad of every warp is static (neighbouring warps start on neighbouring quads), all
   // later ones are claimed from a global counter one quad ahead, so that no SM idles while another still has a queue.
   const int first_wave = gridDim.x * kWarps;
@@ -274,6 +278,14 @@ fbank_warp_kernel(const QuadParams p) {
   if (q >= p.n_quads) return;
   long long g0_cur = __ldg(&p.quads[q].g0);
   int nf_cur = __ldg(&p.quads[q].nF);
+  // the first quad's samples: bulk copy if possible (in_flight), else filled at the top of the loop
+  unsigned phase = 0;
+  int in_flight = 0;
+  if constexpr (kTma) {
+    if (lane == 0)
+      in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_cur, ((nf_cur & 0xff) - 1) * S + L, buf, bar);
+    in_flight = __shfl_sync(0xffffffffu, in_flight, 0);
+  }
 
   while (true) {
     int qn = 0;
@@ -291,32 +303,46 @@ fbank_warp_kernel(const QuadParams p) {
     const int utt = hd.z, f0 = hd.w;
     const int nF = nf_cur & 0xff, slow = (nf_cur >> 8) & 0xf, T = hd1.y, rows = hd1.z;
 
-    // ---- this quad's samples: HBM -> L2 was started a whole quad ago (prefetch below), so these loads hit L2;
-    //      pre-emphasis on the way from registers to the warp's buffer
-    f2 x0, xl;
-    const int a_off = quad_samples<SampleT>(p, g0_cur, nF, lane, grp_in_warp, buf, x0, xl);
-    __syncwarp();
+    // ---- this quad's samples: the bulk copy was issued a whole quad ago; otherwise (ends of the wave buffer, int16
+    //      PCM: prefetched into L2 a quad ago) fill the buffer now
+    if (in_flight) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    } else {
+      quad_fill_generic<SampleT>(p.wave, p.wave_total, g0_cur, (nF - 1) * S + L, lane, buf);
+      __syncwarp();
+    }
+    const int a_off = quad_a_off<SampleT>(p.wave, g0_cur);
 
     // ---- stage 1 (samples -> registers -> real 32-point FFT) and stage 2 (transpose, 16-point FFT, power spectra)
     const int fA = 2 * grp_in_warp;
     const bool vA = fA < nF, vB = fA + 1 < nF;
     {
       f2 zr[16], zi[16], y0, y16;
-      quad_stage1<NROWS, EXACT, DITHER, SR>(buf + a_off + fA * S, x0, xl, vA, vB, S, L, win, p.preemph, p.remove_dc,
-                                            p.dither, p.seed, (unsigned)utt, (unsigned)(f0 + fA), j, g, zr, zi, y0, y16);
+      quad_stage1<NROWS, EXACT, DITHER, SR>(buf + a_off + fA * S, vA, vB, S, L, win, p.preemph, p.remove_dc, p.dither,
+                                            p.seed, (unsigned)utt, (unsigned)(f0 + fA), j, g, zr, zi, y0, y16);
       __syncwarp();   // every lane is done with the sample buffer and with the previous quad's staging tile
+      // ---- the next quad's samples start their way from HBM now: one bulk copy into the (now free) buffer, or one L2
+      //      prefetch per 128-byte line for the generic fill
+      in_flight = 0;
+      if (have_next) {
+        if constexpr (kTma) {
+          if (lane == 0)
+            in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_next,
+                                      ((nf_next & 0xff) - 1) * S + L, buf, bar);
+          in_flight = __shfl_sync(0xffffffffu, in_flight, 0);
+        } else {
+          const char* base = static_cast<const char*>(p.wave);
+          const long long first = (g0_next * (long long)sizeof(SampleT) - 16) & ~127ll;
+          const long long idx = first + 128ll * lane;
+          const long long last = (g0_next + 3 * S + L) * (long long)sizeof(SampleT);
+          if (idx >= 0 && idx < last && idx < p.wave_total * (long long)sizeof(SampleT))
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + idx));
+        }
+      }
       quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
     }
 
-    // ---- the next quad's samples start their way from HBM to L2 now (one 128-byte line per lane)
-    if (have_next) {
-      const char* base = static_cast<const char*>(p.wave);
-      const long long first = (g0_next * (long long)sizeof(SampleT) - 16) & ~127ll;
-      const long long idx = first + 128ll * lane;
-      const long long last = (g0_next + 3 * S + L) * (long long)sizeof(SampleT);
-      if (idx >= 0 && idx < last && idx < p.wave_total * (long long)sizeof(SampleT))
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + idx));
-    }
     const uint4 tg0 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 2);   // targets of frames 0, 1
     const uint4 tg1 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 3);   // targets of frames 2, 3
 

@@ -68,7 +68,6 @@ __host__ __device__ inline size_t stream_smem_bytes(int e_cap, int nf_max, int c
     b += (size_t)kWarps * kQuadBuf * 4;
   } else {
     b += (size_t)e_cap * 4;
-    b += (size_t)2 * ((nf_max + 3) & ~3) * 4;
   }
   b += (size_t)kWarps * kYWarpF4 * 16;
   b += (size_t)(cache_cap + nf_max) * n_mels * 4;
@@ -78,11 +77,9 @@ __host__ __device__ inline size_t stream_smem_bytes(int e_cap, int nf_max, int c
 
 // Samples of one quad of a stream: frames start at virtual index `base` of [carry | chunk].  Vectors that lie inside
 // the chunk are read with aligned 128-bit loads (the load grid is aligned to the chunk's address), vectors that touch
-// the carry or the ends element-wise.  Pre-emphasis on the way to the warp's buffer, raw first / last samples of the
-// group's two frames through shuffles - as in quad_samples (fbank_warp.cuh).  Returns a_off.
+// the carry or the ends element-wise; raw samples go to the warp's buffer (quad_stage1 does the rest).  Returns a_off.
 __device__ __forceinline__ int stream_quad_samples(const float* carry, int carry_len, const float* chunk, int n, int base,
-                                                   int nF, int S, int L, float preemph, int lane, int grp_in_warp,
-                                                   float* buf, f2& x0, f2& xl) {
+                                                   int nF, int S, int L, int lane, float* buf) {
   auto at = [&](int i) { return (i < 0 || i >= n) ? 0.f : (i < carry_len ? carry[i] : chunk[i - carry_len]); };
   const int chunk_mis = (int)((reinterpret_cast<uintptr_t>(chunk) >> 2) & 3);
   const int a_off = (chunk_mis + base - carry_len) & 3;
@@ -98,29 +95,10 @@ __device__ __forceinline__ int stream_quad_samples(const float* carry, int carry
       else x[u] = make_float4(at(s), at(s + 1), at(s + 2), at(s + 3));
     }
   }
-  float cap = 0.f;
-  if (lane < 8 && (lane & 3) < nF) cap = at(base + (lane & 3) * S + (lane < 4 ? 0 : L - 1));
   float4* buf4 = reinterpret_cast<float4*>(buf);
-  float below = 0.f;
 #pragma unroll
-  for (int u = 0; u < kQuadVecs; ++u) {
-    const float rot = __shfl_sync(0xffffffffu, x[u].w, (lane + 31) & 31);
-    const float pv = lane == 0 ? below : rot;
-    below = rot;
-    if (lane + 32 * u < nv) {
-      float4 e;
-      e.x = fmaf(-preemph, pv, x[u].x);
-      e.y = fmaf(-preemph, x[u].x, x[u].y);
-      e.z = fmaf(-preemph, x[u].y, x[u].z);
-      e.w = fmaf(-preemph, x[u].z, x[u].w);
-      buf4[lane + 32 * u] = e;
-    }
-  }
-  const int fa = 2 * grp_in_warp;
-  x0.x = __shfl_sync(0xffffffffu, cap, fa);
-  x0.y = __shfl_sync(0xffffffffu, cap, fa + 1);
-  xl.x = __shfl_sync(0xffffffffu, cap, fa + 4);
-  xl.y = __shfl_sync(0xffffffffu, cap, fa + 5);
+  for (int u = 0; u < kQuadVecs; ++u)
+    if (lane + 32 * u < nv) buf4[lane + 32 * u] = x[u];
   return a_off;
 }
 
@@ -140,11 +118,8 @@ template <int NROWS, bool EXACT, bool DITHER, class MELS, bool PERQUAD>
 __global__ void __launch_bounds__(kCtaThreads, PERQUAD ? 3 : 2)
 stream_push_kernel(const StreamParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nfp = (p.nf_max + 3) & ~3;
   float* e_s = reinterpret_cast<float*>(smem_raw);                       // PERQUAD: [kWarps][kQuadBuf] sample buffers
-  float* x0_s = e_s + (PERQUAD ? kWarps * kQuadBuf : p.e_cap);
-  float* xl_s = x0_s + (PERQUAD ? 0 : nfp);
-  float4* xbuf = reinterpret_cast<float4*>(xl_s + (PERQUAD ? 0 : nfp));
+  float4* xbuf = reinterpret_cast<float4*>(e_s + (PERQUAD ? kWarps * kQuadBuf : p.e_cap));
   float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * kYWarpF4);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + (p.lay.cache_cap + p.nf_max) * p.n_mels);
 
@@ -181,17 +156,8 @@ stream_push_kernel(const StreamParams p) {
   const int n = carry_len + n_new;
   const int nf = n >= L ? (n - L) / S + 1 : 0;
   if constexpr (!PERQUAD) {
-    // stage [carry | chunk] with pre-emphasis
-    for (int i = tid; i < n; i += kCtaThreads) {
-      const float x = i < carry_len ? carry[i] : chunk[i - carry_len];
-      const float xp = i == 0 ? 0.f : (i - 1 < carry_len ? carry[i - 1] : chunk[i - 1 - carry_len]);
-      e_s[i] = fmaf(-p.preemph, xp, x);
-    }
-    for (int f = tid; f < nf; f += kCtaThreads) {
-      const int a = f * S, z = f * S + L - 1;
-      x0_s[f] = a < carry_len ? carry[a] : chunk[a - carry_len];
-      xl_s[f] = z < carry_len ? carry[z] : chunk[z - carry_len];
-    }
+    // stage [carry | chunk], raw
+    for (int i = tid; i < n; i += kCtaThreads) e_s[i] = i < carry_len ? carry[i] : chunk[i - carry_len];
   }
   // samples that stay behind for the next tick (read before anything overwrites the carry)
   const int new_carry = n - nf * S;
@@ -217,15 +183,13 @@ stream_push_kernel(const StreamParams p) {
     const int g = NROWS < 32 ? grp_in_warp : 0;
     for (int quad = warp; 4 * quad < nf; quad += kWarps) {
       const int nFq = min(4, nf - 4 * quad);
-      f2 x0, xl;
-      const int a_off = stream_quad_samples(carry, carry_len, chunk, n, 4 * quad * S, nFq, S, L, p.preemph, lane,
-                                            grp_in_warp, buf, x0, xl);
+      const int a_off = stream_quad_samples(carry, carry_len, chunk, n, 4 * quad * S, nFq, S, L, lane, buf);
       __syncwarp();
       const int fA = 2 * grp_in_warp;
       const bool vA = fA < nFq, vB = fA + 1 < nFq;
       {
         f2 zr[16], zi[16], y0, y16;
-        quad_stage1<NROWS, EXACT, DITHER>(buf + a_off + fA * S, x0, xl, vA, vB, S, L, win, p.preemph, p.remove_dc, p.dither,
+        quad_stage1<NROWS, EXACT, DITHER>(buf + a_off + fA * S, vA, vB, S, L, win, p.preemph, p.remove_dc, p.dither,
                                           p.seed, (unsigned)sid, (unsigned)(t_seen + 4 * quad + fA), j, g, zr, zi, y0, y16);
         __syncwarp();
         quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
@@ -241,7 +205,7 @@ stream_push_kernel(const StreamParams p) {
     }
   } else {
     for (int quad = warp; 4 * quad < nf; quad += kWarps)
-      fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s, x0_s, xl_s, nf, quad, S, L, win, yg, pbuf4, tw_row, c0_row, mel, M,
+      fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s, nf, quad, S, L, win, yg, pbuf4, tw_row, c0_row, mel, M,
                                              p.preemph, p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)sid,
                                              (unsigned)t_seen, logmel_s + cache_len * M, j, grp_in_warp, lane);
   }
