@@ -19,7 +19,7 @@ from oracle import ref_thirdparty as ref  # noqa: E402
 from toolbox_for_asr_and_tts_b200 import synth  # noqa: E402
 
 SEED = 1234
-LENGTHS = [399, 400, 401, 559, 560, 1000, 16000, 160000]
+LENGTHS = [399, 400, 401, 559, 560, 1000, 16000, 160000, 480000]
 PARAFORMER = dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6)
 
 

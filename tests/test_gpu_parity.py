@@ -73,7 +73,7 @@ def test_tables_match_reference_tables():
     assert (win - w).abs().max() <= 5e-7 and (mel - bank).abs().max() <= 3e-5
 
 
-@pytest.mark.parametrize("n", [399, 400, 401, 559, 560, 1000, 16000, 160000])
+@pytest.mark.parametrize("n", [399, 400, 401, 559, 560, 1000, 16000, 160000, 480000])
 def test_paraformer_against_golden(golden, cmvn, n):
     fe = make_fe(cmvn)
     x = torch.from_numpy(synth.uniform_pcm(SEED, n, n))[None].to(DEV)
@@ -154,7 +154,7 @@ def test_packed_unaligned_offsets_equal_dense_bitwise(cmvn):
         for o, w in zip(offs, waves):
             flat[o:o + len(w)] = torch.from_numpy(w)
         packed, pl = fe.forward_packed(flat.to(DEV), offs, lens)
-        assert torch.equal(pl, dl) and torch.equal(packed, dense), (align, lead)
+        assert torch.equal(pl.cpu(), dl) and torch.equal(packed, dense), (align, lead)
 
 
 def test_short_utterances_follow_shrunken_frame_rule(cmvn):
@@ -306,8 +306,8 @@ def test_cpu_tensor_is_rejected_and_unsupported_options_raise():
         fe(torch.zeros(1, 16, device=DEV), [1])
 
 
-def test_raw_c_abi_with_ctypes(cmvn):
-    """The C ABI as a foreign caller would use it: plain pointers and sizes, no torch types in the signatures."""
+def ctypes_handle(cmvn):
+    """(lib, handle) through the plain C ABI: Paraformer configuration, dither 0."""
     lib = _native.cdll()
 
     class Cfg(ctypes.Structure):
@@ -325,6 +325,12 @@ def test_raw_c_abi_with_ctypes(cmvn):
     lib.b200fe_last_error.restype = ctypes.c_char_p
     rc = lib.b200fe_create(ctypes.byref(c), cm.ctypes.data_as(ctypes.c_void_p), ctypes.byref(h))
     assert rc == 0, lib.b200fe_last_error(None)
+    return lib, h
+
+
+def test_raw_c_abi_with_ctypes(cmvn):
+    """The C ABI as a foreign caller would use it: plain pointers and sizes, no torch types in the signatures."""
+    lib, h = ctypes_handle(cmvn)
     try:
         n = 16000
         lens = (ctypes.c_int64 * 1)(n)
@@ -506,7 +512,7 @@ def test_pcm16_input_is_bit_identical_to_converted_float(cmvn):
         for o, w in zip(offs, ints):
             flat[o:o + len(w)] = torch.from_numpy(w)
         p, pl = fe.forward_packed(flat.to(DEV), offs, lens)
-        assert torch.equal(pl, ref_l) and torch.equal(p, ref_f), lead
+        assert torch.equal(pl.cpu(), ref_l) and torch.equal(p, ref_f), lead
     oracle, ol = wf.frontend_forward(floats, lens, cmvn=cmvn, **PARAFORMER)
     assert np.array_equal(gl.cpu().numpy(), ol)
     for i, k in enumerate(ol):
@@ -645,7 +651,7 @@ def test_handles_follow_the_tensor_device(cmvn):
     x = torch.from_numpy(synth.uniform_pcm(SEED, 16000, 16000))[None]
     a, la = fe(x.to("cuda:0"), [16000])
     b, lb = fe(x.to("cuda:1"), [16000])
-    assert b.device.index == 1 and lb.device.index == 1
+    assert b.device.index == 1 and lb.device.type == "cpu" and lb.dtype == torch.int64     # lengths: CPU int64, VF:160
     assert torch.equal(a.cpu(), b.cpu()) and torch.equal(la.cpu(), lb.cpu())
 
 
@@ -877,3 +883,240 @@ def test_stream_tick_is_capturable_in_a_cuda_graph(cmvn):
         for s in range(n_streams):
             k = int(e_rows[s])
             assert torch.equal(g_feats[s, :k], e_feats[s, :k]), (t, s)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Round 2: parity on the benchmarked configuration itself, oracle-driven streaming, state snapshots, buffer edges.
+
+def test_bench_batch_every_valid_row_against_the_reference(cmvn):
+    """The exact batch bench.py times (BASELINE.json configs[1]: bench.batch_layout(0), 256 utterances of 1-30 s,
+    length-packed, synthesised on the device by the same kernel) through forward_packed, every valid row against the
+    reference run live on the same samples (torchaudio kaldi.fbank + apply_lfr + apply_cmvn when importable, else the
+    numpy restatement) - 412 k frames.  Bins more than 12 nepers below their frame's peak are judged against the float64
+    oracle relative to the reference's own float32 noise (conftest.assert_logmel_close)."""
+    import bench
+    from oracle import ref_thirdparty as ref
+    lens, offs, total = bench.batch_layout(0)
+    cm = bench.synthetic_cmvn()
+    wave = torch.zeros(total + 8, dtype=torch.float32, device=DEV)
+    _native.ops().synth_uniform(wave, torch.from_numpy(offs), torch.from_numpy(lens), 0 * 1000 + 1234, 0.3)
+    fe = WavFrontend(cmvn=torch.from_numpy(cm), dither=0.0, **bench.CONF)
+    feats, flens = fe.forward_packed(wave, torch.from_numpy(offs), torch.from_numpy(lens))
+    host = wave.cpu().numpy()
+    assert np.array_equal(host[int(offs[3]):int(offs[3]) + 1000], synth.uniform_pcm(1234, 3, 1000))   # same samples
+    waves = [host[int(o):int(o) + int(n)] for o, n in zip(offs, lens)]
+    t = 1 + (lens - 400) // 160
+    assert np.array_equal(flens.cpu().numpy(), -(-t // 6))
+    assert tuple(feats.shape) == (256, int((-(-t // 6)).max()), 560)
+    sh, sc = cm[0].astype(np.float64), cm[1].astype(np.float64)
+    use_ta = ref.have_torchaudio()
+    rfe = ref.make_reference_frontend(cm, prefer_vllm=False, **bench.CONF) if use_ta else None
+    worst = 0.0
+    kw = dict(num_mel_bins=80, frame_length=25.0, frame_shift=10.0, dither=0.0, energy_floor=0.0, window_type="hamming",
+              sample_frequency=16000.0)
+    for u0 in range(0, 256, 16):
+        us = list(range(u0, u0 + 16))
+        wl = [int(lens[u]) for u in us]
+        if use_ta:
+            r, rl = rfe([waves[u] for u in us], wl)
+            r, rl = r.numpy(), rl.numpy()
+        else:
+            r, rl = wf.frontend_forward([waves[u] for u in us], wl, cmvn=cm, **bench.CONF)
+        got = feats[u0:u0 + 16].cpu().numpy()
+        for k, u in enumerate(us):
+            n = int(rl[k])
+            assert n == int(flens[u]) and not got[k, n:].any()          # pad_sequence zeros, bit-exact
+            lg = (got[k, :n].astype(np.float64) / sc - sh).reshape(n, 7, 80)
+            lr = (r[k, :n].astype(np.float64) / sc - sh).reshape(n, 7, 80)
+            f64 = kf.fbank(waves[u].astype(np.float64) * 32768.0, dtype=np.float64, **kw)
+            l64 = wf._lfr_keep_dtype(f64, 7, 6).reshape(n, 7, 80)
+            assert_logmel_close(lg, lr, ref64=l64)
+            worst = max(worst, float(np.abs(lg - lr).max()))
+    print("bench batch: worst |log-mel - reference| over all 412 k frames", worst)
+
+
+@pytest.mark.parametrize("chunk", [9600, 6400, 3840, 960, 300])
+def test_streaming_against_the_online_oracle_chunk_by_chunk(cmvn, chunk):
+    """oracle.OnlineFrontend (sample carry + LFR splice carry, numpy) and the CUDA StreamPool are driven with the same
+    chunks, chunk by chunk: the number of rows every push returns must be equal and so must the rows.  The last chunk
+    is shorter than one frame (the final flush then only completes the padded rows)."""
+    n = 3 * 9600 + 250          # ends with a chunk (or remainder) shorter than one frame
+    w = synth.uniform_pcm(93, chunk, n)
+    fe = make_fe(cmvn)
+    pool = StreamPool(fe, n_streams=3, max_chunk_samples=9600, device=DEV)
+    orc = wf.OnlineFrontend(cmvn=cmvn, **PARAFORMER)
+    sid = torch.tensor([1], dtype=torch.int32)
+    pos, rows_seen, per_push = 0, 0, []
+    while pos < n:
+        m = min(chunk, n - pos)
+        fin = pos + m >= n
+        c = np.zeros((1, 9600), dtype=np.float32)
+        c[0, :m] = w[pos:pos + m]
+        feats, rows = pool.push(torch.from_numpy(c).to(DEV), torch.tensor([m], dtype=torch.int32), sid,
+                                torch.tensor([1 if fin else 0], dtype=torch.uint8))
+        want = orc.push(w[pos:pos + m], is_final=fin)
+        k = int(rows[0])
+        assert k == want.shape[0], (chunk, pos, k, want.shape)
+        if k:
+            assert_feats_close(feats[0, :k], want, cmvn)
+        per_push.append(k)
+        rows_seen += k
+        pos += m
+    t = 1 + (n - 400) // 160
+    assert rows_seen == -(-t // 6)
+    if chunk == 9600:
+        assert per_push == [10, 10, 10, 0]      # 58 + 60 + 60 frames = 30 rows; the 250-sample tail adds a frame? no: 180 frames in all
+
+
+def test_streaming_fsmn_vad_configuration_against_the_online_oracle(variants_golden):
+    """The FSMN-VAD front-end (LFR 5/1, its own CMVN) in streaming form, 400 ms client chunks
+    (R:voice-service/app/services/voice_interface.py:648, 1585-1590), against the online oracle per push."""
+    cm = variants_golden["vad_5_1_cmvn"]
+    conf = dict(PARAFORMER, lfr_m=5, lfr_n=1)
+    fe = WavFrontend(cmvn=torch.from_numpy(cm), dither=0.0, **conf)
+    pool = StreamPool(fe, n_streams=1, max_chunk_samples=6400, device=DEV)
+    orc = wf.OnlineFrontend(cmvn=cm, **conf)
+    w = synth.uniform_pcm(94, 0, 6400 * 4 + 123)
+    sid = torch.zeros(1, dtype=torch.int32)
+    for pos in range(0, len(w), 6400):
+        m = min(6400, len(w) - pos)
+        fin = pos + m >= len(w)
+        c = np.zeros((1, 6400), dtype=np.float32)
+        c[0, :m] = w[pos:pos + m]
+        feats, rows = pool.push(torch.from_numpy(c).to(DEV), torch.tensor([m], dtype=torch.int32), sid,
+                                torch.tensor([1 if fin else 0], dtype=torch.uint8))
+        want = orc.push(w[pos:pos + m], is_final=fin)
+        assert int(rows[0]) == want.shape[0]
+        sh, sc = cm[0].astype(np.float64), cm[1].astype(np.float64)
+        lg = (feats[0, :want.shape[0]].cpu().numpy().astype(np.float64) / sc - sh).reshape(-1, 5, 80)
+        assert_logmel_close(lg, (want.astype(np.float64) / sc - sh).reshape(-1, 5, 80))
+
+
+def test_stream_state_snapshot_and_restore(cmvn):
+    """a checkpoint of the stream slab (StreamPool.snapshot / restore) taken mid-stream must make the
+    continuation reproduce, bit for bit, what the uninterrupted streams produce - including streams that were reset or
+    had advanced further in between."""
+    fe = make_fe(cmvn)
+    pool = StreamPool(fe, n_streams=4, max_chunk_samples=9600, device=DEV)
+    ids = torch.arange(4, dtype=torch.int32)
+    w = np.stack([synth.uniform_pcm(95, s, 9600 * 4) for s in range(4)])
+    lens = torch.full((4,), 9600, dtype=torch.int32)
+
+    def tick(t, final=False):
+        fin = torch.full((4,), 1 if final else 0, dtype=torch.uint8)
+        f, r = pool.push(torch.from_numpy(w[:, t * 9600:(t + 1) * 9600].copy()).to(DEV), lens, ids, fin)
+        return f.clone(), r.clone()
+
+    tick(0)
+    tick(1)
+    snap = pool.snapshot()
+    a2, ra2 = tick(2)
+    a3, ra3 = tick(3, final=True)
+    pool.reset(torch.tensor([0, 2], dtype=torch.int32))   # disturb the state ...
+    tick(0)
+    pool.restore(snap)                                     # ... and roll it back
+    b2, rb2 = tick(2)
+    b3, rb3 = tick(3, final=True)
+    assert torch.equal(ra2, rb2) and torch.equal(ra3, rb3)
+    for s in range(4):
+        assert torch.equal(a2[s, :int(ra2[s])], b2[s, :int(rb2[s])])
+        assert torch.equal(a3[s, :int(ra3[s])], b3[s, :int(rb3[s])])
+
+
+def test_stream_push_with_too_few_output_rows_fails_loudly(cmvn):
+    """A push whose output buffer holds fewer rows than one push can emit (b200fe_stream_max_rows) is refused by the C
+    ABI with B200FE_E_INVALID and a message - rows are never dropped silently."""
+    lib, h = ctypes_handle(cmvn)
+    try:
+        need = lib.b200fe_stream_max_rows(h, 9600)
+        assert need >= 11
+        sb = ctypes.c_size_t()
+        assert lib.b200fe_stream_state_bytes(h, 1, 9600, ctypes.byref(sb)) == 0
+        state = torch.zeros(sb.value, dtype=torch.uint8, device=DEV)
+        assert lib.b200fe_stream_reset(h, ctypes.c_void_p(state.data_ptr()), 1, 9600, None, 1, None) == 0
+        chunk = torch.from_numpy(synth.uniform_pcm(96, 0, 9600)).to(DEV)
+        clen = torch.tensor([9600], dtype=torch.int32, device=DEV)
+        sid = torch.zeros(1, dtype=torch.int32, device=DEV)
+        rows = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+
+        def push(rows_cap):
+            feats = torch.zeros(1, rows_cap, 560, device=DEV)
+            rc = lib.b200fe_stream_push(h, ctypes.c_void_p(state.data_ptr()), 1, 9600, ctypes.c_void_p(chunk.data_ptr()),
+                                        ctypes.c_int64(9600), ctypes.c_void_p(clen.data_ptr()), ctypes.c_void_p(sid.data_ptr()),
+                                        None, 1, ctypes.c_void_p(feats.data_ptr()), ctypes.c_int64(rows_cap),
+                                        ctypes.c_void_p(rows.data_ptr()), None)
+            torch.cuda.synchronize()
+            return rc
+
+        assert push(need - 1) < 0 and b"rows_cap" in lib.b200fe_last_error(h)
+        assert int(rows[0]) == -1                       # nothing ran, the state is untouched
+        assert push(need) == 0 and int(rows[0]) == 10   # 58 frames -> 10 rows
+    finally:
+        lib.b200fe_destroy(h)
+
+
+def test_pcm16_quad_that_fills_the_warp_buffer():
+    """with frame_shift 10.25 ms (S = 164, L = 400: 3 S + L = 892) an int16 quad starts up to 7 samples before
+    its first frame and stores whole 8-sample vectors, which no longer fits the 896-float warp buffer: int16 input must
+    then be refused (never silently overflow), float32 input (3 samples of slack) still takes the warp kernel, and
+    both agree with the oracle."""
+    conf = dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10.25, lfr_m=1, lfr_n=1)
+    fe = WavFrontend(dither=0.0, **conf)
+    rng = np.random.default_rng(164)
+    n = 8000
+    ints = rng.integers(-20000, 20000, size=n + 7, dtype=np.int16)
+    for lead in (0, 1, 7):
+        xi = torch.from_numpy(ints[lead:lead + n].copy())
+        xf = xi.to(torch.float32) / 32768.0
+        flat = torch.zeros(n + 16, dtype=torch.float32)
+        flat[lead:lead + n] = xf
+        got, gl = fe.forward_packed(flat.to(DEV), [lead], [n])
+        ref = kf.fbank(xf.numpy() * np.float32(32768.0), num_mel_bins=80, frame_length=25.0, frame_shift=10.25, dither=0.0,
+                       energy_floor=0.0, window_type="hamming", sample_frequency=16000.0, dtype=np.float32)
+        assert int(gl[0]) == ref.shape[0] == 1 + (n - 400) // 164
+        assert_logmel_close(got[0, :ref.shape[0]].cpu().numpy(), ref)
+        flat16 = torch.zeros(n + 16, dtype=torch.int16)
+        flat16[lead:lead + n] = xi
+        with pytest.raises(RuntimeError, match="int16 input"):
+            fe.forward_packed(flat16.to(DEV), [lead], [n])
+
+
+def test_online_frontend_hands_back_frame_aligned_waveforms(variants_golden):
+    """like upstream's WavFrontendOnline, every call leaves in cache["waveforms"] the raw samples of
+    the rows it returned ((k-1)*shift + frame samples for the FSMN-VAD setting lfr_n = 1, starting at the first returned
+    row's frame) and keeps the unconsumed tail in cache["reserve_waveforms"]; an empty call returns an empty
+    [1, 0, D] feature tensor; feature lengths are int64 on the CPU; nothing is read back from the device."""
+    cm = variants_golden["vad_5_1_cmvn"]
+    conf = dict(PARAFORMER, lfr_m=5, lfr_n=1)
+    fe = WavFrontendOnline(cmvn=torch.from_numpy(cm), max_chunk_samples=6400, dither=0.0, **conf)
+    off = WavFrontend(cmvn=torch.from_numpy(cm), dither=0.0, **conf)
+    n = 6400 * 3 + 1000
+    w = synth.uniform_pcm(97, 0, n)
+    full, fl = off(torch.from_numpy(w)[None].to(DEV), [n])
+    cache, rows, outs = {}, 0, []
+    first = torch.from_numpy(w[:300])[None].to(DEV)                      # shorter than one frame: nothing yet
+    f, l = fe(first, [300], cache=cache, is_final=False)
+    assert tuple(f.shape) == (1, 0, 400) and f.is_cuda and l.dtype == torch.int64 and l.device.type == "cpu" and int(l[0]) == 0
+    assert cache["waveforms"].shape[1] == 0 and cache["reserve_waveforms"].shape[1] == 300
+    pos = 300
+    while pos < n:
+        m = min(6400, n - pos)
+        fin = pos + m >= n
+        f, l = fe(torch.from_numpy(w[pos:pos + m])[None].to(DEV), [m], cache=cache, is_final=fin)
+        k = int(l[0])
+        assert f.shape[1] == k
+        wav = cache["waveforms"]
+        if k:
+            # rows [rows, rows + k) <-> frames rows .. rows + k - 1 <-> samples [rows*160, (rows + k - 1)*160 + 400)
+            a, b = rows * 160, min(n, (rows + k - 1) * 160 + 400)
+            assert wav.shape == (1, b - a) and np.array_equal(wav[0].cpu().numpy(), w[a:b])
+            outs.append(f[0])
+        rows += k
+        pos += m
+        if not fin:
+            assert np.array_equal(cache["reserve_waveforms"][0].cpu().numpy(), w[rows * 160:pos])
+    assert rows == int(fl[0]) and cache["reserve_waveforms"].shape[1] == 0
+    got = torch.cat(outs)
+    sh, sc = cm[0].astype(np.float64), cm[1].astype(np.float64)
+    assert_logmel_close((got.cpu().numpy().astype(np.float64) / sc - sh).reshape(-1, 5, 80),
+                        (full[0].cpu().numpy().astype(np.float64) / sc - sh).reshape(-1, 5, 80))

@@ -175,3 +175,29 @@ def test_lfr_target_planner_reproduces_apply_lfr(m, n):
                     hits.reshape(-1)[off:off + M] += 1
         assert np.array_equal(got, ref), (m, n, T)
         assert (hits == 1).all(), (m, n, T)       # every output element is written exactly once
+
+
+def test_online_frontend_host_mirror_counts_rows_like_the_oracle():
+    """WavFrontendOnline knows how many rows a push returns without reading the device counters: its host mirror of
+    the stream counters must agree with the online oracle for every chunking (incl. chunks shorter than one frame and
+    a tiny final chunk), for the Paraformer (7/6) and the FSMN-VAD (5/1) LFR settings."""
+    from oracle import wav_frontend_np as wf
+    from toolbox_for_asr_and_tts_b200 import WavFrontendOnline
+    rng = np.random.default_rng(5)
+    for lfr_m, lfr_n in ((7, 6), (5, 1), (1, 1)):
+        fe = WavFrontendOnline(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=lfr_m,
+                               lfr_n=lfr_n, dither=0.0)
+        for trial in range(6):
+            n = int(rng.integers(100, 40000))
+            w = (0.1 * rng.standard_normal(n)).astype(np.float32)
+            orc = wf.OnlineFrontend(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=lfr_m,
+                                    lfr_n=lfr_n)
+            st = dict(carry=0, frames=0, rows=0)
+            pos = 0
+            while pos < n:
+                m = int(min(n - pos, rng.choice([9600, 6400, 3840, 960, 300, 37])))
+                fin = pos + m >= n
+                want = orc.push(w[pos:pos + m], is_final=fin).shape[0]
+                assert fe._rows_after_push(st, m, fin) == want, (lfr_m, lfr_n, n, pos, m)
+                pos += m
+            assert st == dict(carry=0, frames=0, rows=0)

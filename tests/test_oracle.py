@@ -21,7 +21,7 @@ def cmvn_atol(cmvn):
     return LOGMEL_ATOL * float(np.abs(cmvn[1]).max())
 
 
-@pytest.mark.parametrize("n", [399, 400, 401, 559, 560, 1000, 16000, 160000])
+@pytest.mark.parametrize("n", [399, 400, 401, 559, 560, 1000, 16000, 160000, 480000])
 def test_oracle_matches_golden_paraformer(golden, cmvn, n):
     x = synth.uniform_pcm(SEED, n, n)
     feats, lens = wf.frontend_forward([x], [n], cmvn=cmvn, **PARAFORMER)

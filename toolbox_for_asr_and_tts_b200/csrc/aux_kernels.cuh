@@ -204,37 +204,49 @@ __device__ __forceinline__ void build_quad(const UttDesc* utts, int batch, int q
 }
 
 // One launch in front of the warp kernel: blocks [0, quad_blocks) build the quad list (latency-bound: a binary search
-// per quad) while blocks [quad_blocks, quad_blocks + pad_bx * batch) clear the padding rows (bandwidth-bound).
-__device__ __forceinline__ void prep_warp_body(const UttDesc* utts, int batch, int n_quads, int quad_blocks, int S,
-                                               int lfr_m, int lfr_n, int M, QuadDesc* quads, int* next_quad, float* feats,
-                                               long long rows_cap, long long* feat_lens, int pad_bx) {
+// per quad), the next table_blocks write feat_lens (and copy the utterance table to global memory when it arrived in
+// the launch parameters), the remaining pad_bx * batch blocks clear the padding rows (bandwidth-bound; pad_bx = 0
+// when the warp kernel writes them itself, B200FE_PAD_MODE).
+__device__ __forceinline__ void prep_warp_body(const UttDesc* utts, int batch, int n_quads, int quad_blocks, int table_blocks,
+                                               int S, int lfr_m, int lfr_n, int M, QuadDesc* quads, int* next_quad,
+                                               float* feats, long long rows_cap, long long* feat_lens, UttDesc* utts_out,
+                                               int pad_bx) {
   // the warp kernel that follows may start its (input-independent) prologue while this grid drains; it waits for this
   // grid's completion (griddepcontrol.wait) before it touches the quad list
   asm volatile("griddepcontrol.launch_dependents;");
-  if ((int)blockIdx.x < quad_blocks) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.x;
+  if (b < quad_blocks) {
+    const int q = b * blockDim.x + threadIdx.x;
     if (q == 0) *next_quad = 0;   // the warp kernel's work counter
     if (q < n_quads) build_quad(utts, batch, q, S, lfr_m, lfr_n, M, quads);
+  } else if (b < quad_blocks + table_blocks) {
+    const int u = (b - quad_blocks) * blockDim.x + threadIdx.x;
+    if (u < batch) {
+      if (feat_lens) feat_lens[u] = utts[u].n_rows;
+      if (utts_out) utts_out[u] = utts[u];
+    }
   } else {
-    const int b = blockIdx.x - quad_blocks;
-    pad_rows_block(utts, feats, rows_cap, lfr_m * M, feat_lens, b / pad_bx, b % pad_bx, pad_bx);
+    const int k = b - quad_blocks - table_blocks;
+    pad_rows_block(utts, feats, rows_cap, lfr_m * M, nullptr, k / pad_bx, k % pad_bx, pad_bx);
   }
 }
 
-__global__ void prep_warp_kernel(const UttDesc* utts, int batch, int n_quads, int quad_blocks, int S, int lfr_m, int lfr_n,
-                                 int M, QuadDesc* quads, int* next_quad, float* feats, long long rows_cap,
-                                 long long* feat_lens, int pad_bx) {
-  prep_warp_body(utts, batch, n_quads, quad_blocks, S, lfr_m, lfr_n, M, quads, next_quad, feats, rows_cap, feat_lens, pad_bx);
+__global__ void prep_warp_kernel(const UttDesc* utts, int batch, int n_quads, int quad_blocks, int table_blocks, int S,
+                                 int lfr_m, int lfr_n, int M, QuadDesc* quads, int* next_quad, float* feats,
+                                 long long rows_cap, long long* feat_lens, int pad_bx) {
+  prep_warp_body(utts, batch, n_quads, quad_blocks, table_blocks, S, lfr_m, lfr_n, M, quads, next_quad, feats, rows_cap,
+                 feat_lens, nullptr, pad_bx);
 }
 
 // The same with the utterance table carried in the launch itself (kernel parameters, 8 KB of the 32 KB a launch may
 // carry): batches of up to kParamUtts utterances need no host -> device copy in front of the two kernels.
 constexpr int kParamUtts = 256;
 struct UttTable { UttDesc u[kParamUtts]; };
-__global__ void prep_warp_kernel_tab(const __grid_constant__ UttTable tab, int batch, int n_quads, int quad_blocks, int S,
-                                     int lfr_m, int lfr_n, int M, QuadDesc* quads, int* next_quad, float* feats,
-                                     long long rows_cap, long long* feat_lens, int pad_bx) {
-  prep_warp_body(tab.u, batch, n_quads, quad_blocks, S, lfr_m, lfr_n, M, quads, next_quad, feats, rows_cap, feat_lens, pad_bx);
+__global__ void prep_warp_kernel_tab(const __grid_constant__ UttTable tab, int batch, int n_quads, int quad_blocks,
+                                     int table_blocks, int S, int lfr_m, int lfr_n, int M, QuadDesc* quads, int* next_quad,
+                                     float* feats, long long rows_cap, long long* feat_lens, UttDesc* utts_out, int pad_bx) {
+  prep_warp_body(tab.u, batch, n_quads, quad_blocks, table_blocks, S, lfr_m, lfr_n, M, quads, next_quad, feats, rows_cap,
+                 feat_lens, utts_out, pad_bx);
 }
 
 // Counter-based synthetic PCM, bit-identical to toolbox_for_asr_and_tts_b200/synth.py::uniform_pcm.

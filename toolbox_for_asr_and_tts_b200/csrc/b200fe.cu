@@ -280,6 +280,7 @@ struct Plan {
   int n_quads = 0;
   long long max_rows = 0;
   long long total_rows = 0;
+  long long stat_rows = 0;   // rows of regular utterances: the ones the statistics pass accumulates
 };
 
 int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, int64_t row_stride, int batch,
@@ -289,6 +290,7 @@ int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, 
   int tile = 0, quad = 0;
   for (int u = 0; u < batch; ++u) {
     const long long n = lengths[u];
+    if (n < 0 || n > 0x7fffffffll) return fail(h, B200FE_E_INVALID, "utterance length outside [0, 2^31)");
     UttDesc d;
     d.wave_off = offsets ? offsets[u] : (long long)u * row_stride;
     d.n_samples = (int)n;
@@ -300,6 +302,7 @@ int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, 
       d.n_rows = ceil_div(d.n_frames, h->cfg.lfr_n);
       tile += ceil_div(d.n_rows, h->rows_per_tile);
       quad += ceil_div(d.n_frames, 4);
+      pl.stat_rows += d.n_rows;
     } else {
       const int win = short_window(h->cfg, n);
       if (win < 2 || win > n) return fail(h, B200FE_E_SHORT, "choose a window size " + std::to_string(win) +
@@ -375,8 +378,13 @@ int launch_tile(b200fe_handle* h, const TileParams& p, int grid, bool dither, bo
     CUDA_TRY(h, cudaEventCreate(&e1));
     CUDA_TRY(h, cudaEventRecord(e0, st));
   }
+#ifdef B200FE_BENCH_ONLY
+  if (dither || stats) return fail(h, B200FE_E_UNSUPPORTED, "bench-only build");
+  LAUNCH(false, false);
+#else
   if (dither) { if (stats) LAUNCH(true, true); else LAUNCH(true, false); }
   else        { if (stats) LAUNCH(false, true); else LAUNCH(false, false); }
+#endif
 #undef LAUNCH
   if (timed) {
     CUDA_TRY(h, cudaEventRecord(e1, st));
@@ -409,7 +417,12 @@ int launch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cu
     CUDA_TRY(h, cudaEventCreate(&e1));
     CUDA_TRY(h, cudaEventRecord(e0, st));
   }
+#ifdef B200FE_BENCH_ONLY   // experiment builds (tools/build_variant.py): only what bench.py launches is instantiated
+  if (dither) return fail(h, B200FE_E_UNSUPPORTED, "bench-only build");
+  LAUNCHW(false);
+#else
   if (dither) LAUNCHW(true); else LAUNCHW(false);
+#endif
 #undef LAUNCHW
   if (timed) {
     CUDA_TRY(h, cudaEventRecord(e1, st));
@@ -421,23 +434,32 @@ int launch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cu
 }
 
 int ensure_short_banks(b200fe_handle* h, Plan& pl, cudaStream_t st) {
+  (void)st;
   bool grow = false;
   for (auto& s : pl.shorts)
     if (!h->short_mel_off.count(s.nfft)) grow = true;
   if (grow) {
-    // (re)build all banks for fft sizes 2..512; 80 * (1+2+..+256) floats = 164 KB, once per handle
+    // all banks for fft sizes 2..512; 80 * (1+2+..+256) floats = 164 KB, once per handle.  Built into locals and
+    // committed only after the (blocking) upload succeeded, so a failed call leaves the handle as it was.
     std::vector<float> all;
+    std::map<int, int> off;
     for (int nfft = 2; nfft <= 512; nfft <<= 1) {
       std::vector<float> b;
       if (build_mel(h->cfg.n_mels, nfft, h->cfg.sample_rate, h->cfg.low_freq, h->cfg.high_freq, b) != 0)
         return fail(h, B200FE_E_INVALID, "bad low/high frequency");
-      h->short_mel_off[nfft] = (int)all.size();
+      off[nfft] = (int)all.size();
       all.insert(all.end(), b.begin(), b.end());
     }
-    CUDA_TRY(h, cudaMalloc(&h->d_short_mel, all.size() * sizeof(float)));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_short_mel, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(h, cudaStreamSynchronize(st));
+    float* dev = nullptr;
+    CUDA_TRY(h, cudaMalloc(&dev, all.size() * sizeof(float)));
+    const cudaError_t e = cudaMemcpy(dev, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(dev);
+      return fail(h, B200FE_E_CUDA, std::string("short-utterance mel banks: ") + cudaGetErrorString(e));
+    }
+    h->d_short_mel = dev;
     h->short_mel_floats = all.size();
+    h->short_mel_off.swap(off);
   }
   for (auto& s : pl.shorts) s.mel_off = h->short_mel_off[s.nfft];
   return 0;
@@ -651,9 +673,13 @@ namespace {
 template <class SampleT>
 int dispatch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cudaStream_t st) {
   if (h->L == 400 && h->S == 160 && h->mel_paraformer) return launch_warp<25, true, MelShapeParaformer, 10, SampleT>(h, p, grid, dither, st);
+#ifdef B200FE_BENCH_ONLY
+  return fail(h, B200FE_E_UNSUPPORTED, "bench-only build");
+#else
   if (h->L == 400 && h->S == 160) return launch_warp<25, true, MelShapeRuntime, 10, SampleT>(h, p, grid, dither, st);
   if (h->L == 400) return launch_warp<25, true, MelShapeRuntime, 0, SampleT>(h, p, grid, dither, st);
   return launch_warp<32, false, MelShapeRuntime, 0, SampleT>(h, p, grid, dither, st);
+#endif
 }
 
 // b200fe_forward / b200fe_forward_pcm16.  pcm16: `wave_dev` is int16 PCM, sample value = s / 32768.
@@ -696,19 +722,20 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   int gx = (int)((per_utt + 256 * 8 - 1) / (256 * 8));
   gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
   if (use_warp && pl.n_quads > 0) {
-    // 1. one launch: quad list (+ work counter) and padding rows + feat_lens
-    const int qb = (pl.n_quads + 255) / 256;
+    // 1. one launch: quad list (+ work counter), feat_lens, and the padding rows unless the warp kernel writes them
+    const int qb = (pl.n_quads + 255) / 256, ub = (batch + 255) / 256;
+    const int pad_bx = B200FE_PAD_MODE == 1 ? 0 : gx;
+    const int grid0 = qb + ub + pad_bx * batch;
     if (utts_in_params) {
       static_assert(sizeof(UttTable) <= 16384, "kernel parameters");
       UttTable& tab = h->utt_tab;
       memcpy(tab.u, pl.utts.data(), (size_t)batch * sizeof(UttDesc));
-      prep_warp_kernel_tab<<<qb + gx * batch, 256, 0, st>>>(tab, batch, pl.n_quads, qb, h->S, h->cfg.lfr_m, h->cfg.lfr_n,
-                                                            h->cfg.n_mels, d_quads, d_counter, feats_dev, rows_cap,
-                                                            (long long*)feat_lens_dev, gx);
+      prep_warp_kernel_tab<<<grid0, 256, 0, st>>>(tab, batch, pl.n_quads, qb, ub, h->S, h->cfg.lfr_m, h->cfg.lfr_n, h->cfg.n_mels,
+                                                  d_quads, d_counter, feats_dev, rows_cap, (long long*)feat_lens_dev,
+                                                  B200FE_PAD_MODE == 1 ? d_utts : nullptr, pad_bx);
     } else {
-      prep_warp_kernel<<<qb + gx * batch, 256, 0, st>>>(d_utts, batch, pl.n_quads, qb, h->S, h->cfg.lfr_m, h->cfg.lfr_n,
-                                                        h->cfg.n_mels, d_quads, d_counter, feats_dev, rows_cap,
-                                                        (long long*)feat_lens_dev, gx);
+      prep_warp_kernel<<<grid0, 256, 0, st>>>(d_utts, batch, pl.n_quads, qb, ub, h->S, h->cfg.lfr_m, h->cfg.lfr_n, h->cfg.n_mels,
+                                              d_quads, d_counter, feats_dev, rows_cap, (long long*)feat_lens_dev, pad_bx);
     }
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
@@ -736,10 +763,15 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
     p.window = h->d_window; p.twiddle = h->d_twiddle; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_rounds = h->mel_rounds;
     for (int r = 0; r < kMelRounds; ++r) { p.mel_cnt[r] = h->mel_cnt[r]; p.mel_base[r] = h->mel_base[r]; }
     p.cmvn = h->d_cmvn;
+    p.utts = d_utts; p.batch = batch;
     const int ctas = (pl.n_quads + kWarps - 1) / kWarps;
-    const int grid = ctas < 4 * h->n_sms ? ctas : 4 * h->n_sms;
+    const int grid = ctas < B200FE_WARP_CTAS * h->n_sms ? ctas : B200FE_WARP_CTAS * h->n_sms;
     const bool dither = h->cfg.dither != 0.f;
+  #ifdef B200FE_BENCH_ONLY
+    rc = pcm16 ? fail(h, B200FE_E_UNSUPPORTED, "bench-only build") : dispatch_warp<float>(h, p, grid, dither, st);
+#else
     rc = pcm16 ? dispatch_warp<short>(h, p, grid, dither, st) : dispatch_warp<float>(h, p, grid, dither, st);
+#endif
     if (rc) return rc;
   } else if (pl.n_tiles > 0) {
     TileParams p;
@@ -757,8 +789,10 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
     const int grid = pl.n_tiles < 3 * h->n_sms ? pl.n_tiles : 3 * h->n_sms;
     const bool dither = h->cfg.dither != 0.f, stats = stats_dev != nullptr;
     if (h->L == 400 && h->mel_paraformer) rc = launch_tile<25, true, MelShapeParaformer>(h, p, grid, dither, stats, st);
+#ifndef B200FE_BENCH_ONLY
     else if (h->L == 400) rc = launch_tile<25, true, MelShapeRuntime>(h, p, grid, dither, stats, st);
     else rc = launch_tile<32, false, MelShapeRuntime>(h, p, grid, dither, stats, st);
+#endif
     if (rc) return rc;
   }
   // 3. utterances shorter than one frame (VF:147)
@@ -790,7 +824,9 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
     h->launches++;
   }
   if (stats_dev) {
-    add_count_kernel<<<1, 1, 0, st>>>(stats_dev + 2 * h->D, (double)pl.total_rows);
+    // utterances shorter than one frame (shrunken frame, other filterbank: VF:147) stay out of the statistics: their
+    // rows are neither summed nor counted
+    add_count_kernel<<<1, 1, 0, st>>>(stats_dev + 2 * h->D, (double)pl.stat_rows);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
   }

@@ -25,6 +25,10 @@
 
 #include "fft_codelets.cuh"
 
+#ifndef B200FE_S1_UNCOND
+#define B200FE_S1_UNCOND 1
+#endif
+
 namespace b200fe {
 
 constexpr int kGroup = 16;          // threads per frame pair
@@ -342,12 +346,20 @@ __device__ __forceinline__ void quad_stage1(const float* xA, bool vA, bool vB, i
       static_assert(SR < NROWS, "frames of a pair must overlap");
       constexpr int NREG = 2 * LIVE + SR;
       float r[NREG], pr[NREG];
+      // Unconditional loads: registers outside a frame (the rotation's edge rows, rows of a frame beyond the quad's
+      // last one) read whatever the buffer holds - finite stale samples - and only ever reach frames whose results are
+      // discarded, or are masked below (row_in).  No predicates, no zero-initialised registers.
 #pragma unroll
       for (int i = 0; i < NREG; ++i) {
-        const bool need = (i < 2 * LIVE && vA && row_in(i)) || (i >= SR && vB && row_in(i - SR));
         const bool first = j0 && i == g;           // frame A's n = 0: its predecessor is the sample itself
+#if B200FE_S1_UNCOND
+        r[i] = xA[16 * i];
+        pr[i] = xA[16 * i - (first ? 0 : 1)];
+#else
+        const bool need = (i < 2 * LIVE && vA && row_in(i)) || (i >= SR && vB && row_in(i - SR));
         r[i] = need ? xA[16 * i] : 0.f;
         pr[i] = need ? xA[16 * i - (first ? 0 : 1)] : 0.f;
+#endif
       }
 #pragma unroll
       for (int i = 0; i < 2 * LIVE; ++i) {

@@ -23,6 +23,19 @@
 
 #include "fbank_tile.cuh"
 
+#ifndef B200FE_OUT_LEAN      // 1: one divergent region, loads next to their stores; 0: all CMVN loads first (measured faster)
+#define B200FE_OUT_LEAN 0
+#endif
+#ifndef B200FE_CLAIM2        // 1: quads claimed two ahead (atomic read at the end of the iteration); 0: one ahead
+#define B200FE_CLAIM2 0
+#endif
+#ifndef B200FE_WARP_CTAS     // resident CTAs per SM the warp kernel is compiled and launched for
+#define B200FE_WARP_CTAS 4
+#endif
+#ifndef B200FE_PAD_MODE      // 1: padding rows by bulk stores inside the fused kernel; 0: by the prep kernel in front of it
+#define B200FE_PAD_MODE 0
+#endif
+
 namespace b200fe {
 
 constexpr int kQuadVecs = 7;                      // float4 per lane and quad
@@ -30,12 +43,13 @@ constexpr int kQuadBuf = kQuadVecs * 32 * 4;      // 896 floats per warp
 constexpr unsigned kNoTarget = 0xFFFFFFFFu;
 constexpr int kTargetOffBits = 27;                // output offsets inside one utterance must stay below 2^27 floats
 
-// One unit of work, fully resolved by build_quads_kernel (64 bytes, read one quad ahead).
+// One unit of work, fully resolved by build_quads_kernel (64 bytes).  The first 16 bytes are everything the sample
+// fetch of a quad needs and are read one quad ahead; the second 16 bytes and the targets are read by the quad itself.
 struct __align__(16) QuadDesc {
   long long g0;       // absolute index (in the wave buffer) of the first sample of the quad's first frame
+  int nF;             // bits 0..7: frames in the quad (1..4); bits 8..11: frame t takes the generic LFR path
   int utt;
   int f0;             // first frame of the quad
-  int nF;             // bits 0..7: frames in the quad (1..4); bits 8..11: frame t takes the generic LFR path
   int T;              // frames of the utterance
   int rows;           // LFR rows of the utterance
   int pad;
@@ -64,10 +78,21 @@ struct QuadParams {
   int mel_cnt[kMelRounds];
   int mel_base[kMelRounds];
   const float* cmvn;      // nullptr or [2][out_dim]
+  const UttDesc* utts;    // [batch] in global memory: the padding fill reads n_rows from it
+  int batch;
 };
 
+// Padding rows (pad_sequence zeros, VF:163-166) are written by the fused kernel itself, as bulk stores
+// (cp.async.bulk shared -> global, SASS UBLKCP) of a zeroed shared-memory block: no registers, no LSU traffic, no
+// separate pass over 133 MB (configs[1]) in front of the kernel - the stores ride on DRAM bandwidth the kernel leaves
+// idle.  Every utterance's padding region is cut into kPadPieces pieces; piece i belongs to quad i (mod n_quads).
+constexpr int kPadPieceShift = 6;
+constexpr int kPadPieces = 1 << kPadPieceShift;
+constexpr int kPadChunk = 2048;                   // bytes per bulk store = size of the zeroed block
+
 __host__ __device__ inline size_t warp_smem_bytes() {
-  return (size_t)kWarps * kQuadBuf * 4 + (size_t)kWarps * kYWarpF4 * 16 + (size_t)kTw2Total * 8 + (size_t)kWarps * 8;
+  return (size_t)kWarps * kQuadBuf * 4 + (size_t)kWarps * kYWarpF4 * 16 + (size_t)kTw2Total * 8 + (size_t)kWarps * 8 +
+         (B200FE_PAD_MODE ? kPadChunk : 0);
 }
 // The quad of a (frame_len, frame_shift) pair fits the per-warp buffer: whole 16-byte vectors are stored, starting up
 // to one vector minus one sample before the quad's first sample (3 floats for float32 PCM, 7 for int16 PCM).
@@ -147,6 +172,30 @@ __device__ __forceinline__ bool quad_fill_tma(const float* wave, long long wave_
   return true;
 }
 
+// Lane 0 only: zero piece `item` of the padding regions (see kPadPieces).  n_rows = valid rows of utterance item >> 6.
+__device__ __forceinline__ void pad_piece_store(float* feats, long long rows_cap, int D, int item, int n_rows,
+                                                const void* zero_block) {
+  const int u = item >> kPadPieceShift, piece = item & (kPadPieces - 1);
+  const long long region = (rows_cap - n_rows) * (long long)D * 4;            // bytes, a multiple of 16
+  if (region <= 0) return;
+  const long long per = ((region / 16 + kPadPieces - 1) >> kPadPieceShift) * 16;
+  const long long start = piece * per;
+  if (start >= region) return;
+  const long long len = region - start < per ? region - start : per;
+  char* dst = reinterpret_cast<char*>(feats + ((long long)u * rows_cap + n_rows) * D) + start;
+  const unsigned src = smem_u32(zero_block);
+  for (long long off = 0; off < len; off += kPadChunk) {
+    const unsigned bytes = (unsigned)(len - off < kPadChunk ? len - off : kPadChunk);
+#if B200FE_PAD_MODE == 1
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src), "r"(bytes) : "memory");
+#elif B200FE_PAD_MODE == 3   // experiment: same stores, L2-resident destination
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<char*>(feats) + (((unsigned long long)(dst + off) >> 3) & 0xFF800ull)), "r"(src), "r"(bytes) : "memory");
+#else                        // experiment: address arithmetic only
+    asm volatile("" ::"l"(dst + off), "r"(src), "r"(bytes) : "memory");
+#endif
+  }
+}
+
 template <class SampleT>
 __device__ __forceinline__ void quad_fill_generic(const void* wave_any, long long wave_total, long long g0, int n_samples,
                                                   int lane, float* buf);
@@ -221,13 +270,14 @@ __device__ __forceinline__ void quad_fill_generic<short>(const void* wave_any, l
 // SR: frame shift in 16-sample rows when it is a whole number of rows and known at compile time (10 for 400/160):
 // the two frames of a pair then share their overlapping sample loads.  0 = generic.
 template <int NROWS, bool EXACT, bool DITHER, class MELS, int SR, class SampleT>
-__global__ void __launch_bounds__(kCtaThreads, 4)
+__global__ void __launch_bounds__(kCtaThreads, B200FE_WARP_CTAS)
 fbank_warp_kernel(const QuadParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* bufs = reinterpret_cast<float*>(smem_raw);
   float4* xbuf = reinterpret_cast<float4*>(bufs + kWarps * kQuadBuf);
   float2* tw_s = reinterpret_cast<float2*>(xbuf + kWarps * kYWarpF4);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw_s + kTw2Total);
+  float4* zero_block = reinterpret_cast<float4*>(bars + kWarps);   // kPadChunk bytes of zeros: source of the padding stores
   constexpr bool kTma = std::is_same<SampleT, float>::value;
 
   const int tid = threadIdx.x;
@@ -242,6 +292,8 @@ fbank_warp_kernel(const QuadParams p) {
   const int lfr_left = (lfr_m - 1) / 2;
 
   for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  if (B200FE_PAD_MODE)
+    for (int i = tid; i < kPadChunk / 16; i += kCtaThreads) zero_block[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (kTma && lane == 0) {
     mbar_init(bars + warp, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy
@@ -268,40 +320,55 @@ fbank_warp_kernel(const QuadParams p) {
   const int M4 = M >> 2;
   const bool act = lane < M4;      // lanes that move a float4 of a log-mel row (n_mels <= 128)
 
-  // The 64-byte descriptor is read in pieces, each just before it is needed, so that it never occupies 16 registers:
-  // {g0, utt, f0} and {nF, T, rows} at the top of a quad, the targets before the mel stage, and the next quad's
-  // {g0, nF} (for its sample fetch) one quad ahead.
   // Work distribution: the first quad of every warp is static (neighbouring warps start on neighbouring quads), all
-  // later ones are claimed from a global counter one quad ahead, so that no SM idles while another still has a queue.
+  // later ones are claimed from a global counter TWO quads ahead: the claim for quad k+2 is issued at the top of quad k
+  // and read at its end, the 16-byte head {g0, nF, utt} of quad k+1 is loaded then and first used in the middle of
+  // quad k+1 (for its bulk copy), so neither the atomic's nor the descriptor's L2 round trip is ever waited for.
+  // The rest of the 64-byte descriptor ({f0, T, rows}, the LFR targets) is read by the quad itself, just before use.
   const int first_wave = gridDim.x * kWarps;
+  const int n_pad_items = p.batch << kPadPieceShift;
   int q = blockIdx.x * kWarps + warp;
   if (q >= p.n_quads) return;
-  long long g0_cur = __ldg(&p.quads[q].g0);
-  int nf_cur = __ldg(&p.quads[q].nF);
+  if (B200FE_PAD_MODE && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero block
+  long long g0_cur;
+  int nF, slow, utt;
+  {
+    const int4 hd = __ldg(reinterpret_cast<const int4*>(p.quads + q));
+    g0_cur = ((long long)hd.y << 32) | (unsigned)hd.x;
+    nF = hd.z & 0xff; slow = (hd.z >> 8) & 0xf; utt = hd.w;
+  }
+#if B200FE_CLAIM2
+  int qn = 0;
+  if (lane == 0) qn = first_wave + atomicAdd(p.next_quad, 1);
+  qn = __shfl_sync(0xffffffffu, qn, 0);
+  bool have_next = qn < p.n_quads;
+  int4 hdn = make_int4(0, 0, 0, 0);
+  if (have_next) hdn = __ldg(reinterpret_cast<const int4*>(p.quads + qn));
+#endif
   // the first quad's samples: bulk copy if possible (in_flight), else filled at the top of the loop
   unsigned phase = 0;
   int in_flight = 0;
   if constexpr (kTma) {
     if (lane == 0)
-      in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_cur, ((nf_cur & 0xff) - 1) * S + L, buf, bar);
+      in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_cur, (nF - 1) * S + L, buf, bar);
     in_flight = __shfl_sync(0xffffffffu, in_flight, 0);
   }
 
   while (true) {
+#if B200FE_CLAIM2
+    int claim = 0;
+    if (lane == 0) claim = atomicAdd(p.next_quad, 1);      // quad k+2; read at the end of this iteration
+#else
     int qn = 0;
     if (lane == 0) qn = first_wave + atomicAdd(p.next_quad, 1);
     qn = __shfl_sync(0xffffffffu, qn, 0);
     const bool have_next = qn < p.n_quads;
-    long long g0_next = 0;
-    int nf_next = 0;
-    if (have_next) {
-      g0_next = __ldg(&p.quads[qn].g0);
-      nf_next = __ldg(&p.quads[qn].nF);
-    }
-    const int4 hd = __ldg(reinterpret_cast<const int4*>(p.quads + q));        // g0 (2 words), utt, f0
-    const int4 hd1 = __ldg(reinterpret_cast<const int4*>(p.quads + q) + 1);   // nF | slow << 8, T, rows, pad
-    const int utt = hd.z, f0 = hd.w;
-    const int nF = nf_cur & 0xff, slow = (nf_cur >> 8) & 0xf, T = hd1.y, rows = hd1.z;
+    int4 hdn = make_int4(0, 0, 0, 0);
+    if (have_next) hdn = __ldg(reinterpret_cast<const int4*>(p.quads + qn));
+#endif
+    const int4 hd1 = __ldg(reinterpret_cast<const int4*>(p.quads + q) + 1);   // f0, T, rows, pad: used by the output stage
+    int pad_rows = 0;                                                          // padding piece q: read now, stored mid-quad
+    if (B200FE_PAD_MODE && lane == 0 && q < n_pad_items) pad_rows = __ldg(&p.utts[q >> kPadPieceShift].n_rows);
 
     // ---- this quad's samples: the bulk copy was issued a whole quad ago; otherwise (ends of the wave buffer, int16
     //      PCM: prefetched into L2 a quad ago) fill the buffer now
@@ -317,19 +384,24 @@ fbank_warp_kernel(const QuadParams p) {
     // ---- stage 1 (samples -> registers -> real 32-point FFT) and stage 2 (transpose, 16-point FFT, power spectra)
     const int fA = 2 * grp_in_warp;
     const bool vA = fA < nF, vB = fA + 1 < nF;
+    long long g0_next = 0;
+    int nF_next = 0, slow_next = 0, utt_next = 0;
     {
       f2 zr[16], zi[16], y0, y16;
+      int f0_dither = 0;
+      if constexpr (DITHER) f0_dither = hd1.x;
       quad_stage1<NROWS, EXACT, DITHER, SR>(buf + a_off + fA * S, vA, vB, S, L, win, p.preemph, p.remove_dc, p.dither,
-                                            p.seed, (unsigned)utt, (unsigned)(f0 + fA), j, g, zr, zi, y0, y16);
+                                            p.seed, (unsigned)utt, (unsigned)(f0_dither + fA), j, g, zr, zi, y0, y16);
       __syncwarp();   // every lane is done with the sample buffer and with the previous quad's staging tile
       // ---- the next quad's samples start their way from HBM now: one bulk copy into the (now free) buffer, or one L2
       //      prefetch per 128-byte line for the generic fill
       in_flight = 0;
       if (have_next) {
+        g0_next = ((long long)hdn.y << 32) | (unsigned)hdn.x;
+        nF_next = hdn.z & 0xff; slow_next = (hdn.z >> 8) & 0xf; utt_next = hdn.w;
         if constexpr (kTma) {
           if (lane == 0)
-            in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_next,
-                                      ((nf_next & 0xff) - 1) * S + L, buf, bar);
+            in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_next, (nF_next - 1) * S + L, buf, bar);
           in_flight = __shfl_sync(0xffffffffu, in_flight, 0);
         } else {
           const char* base = static_cast<const char*>(p.wave);
@@ -340,9 +412,14 @@ fbank_warp_kernel(const QuadParams p) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(base + idx));
         }
       }
+      // ---- this quad's share of the padding rows: bulk stores of the zero block
+      if (B200FE_PAD_MODE != 0 && lane == 0 && q < n_pad_items) {
+        pad_piece_store(p.feats, p.rows_cap, D, q, pad_rows, zero_block);
+        for (int it = q + p.n_quads; it < n_pad_items; it += p.n_quads)      // fewer quads than pieces: rare
+          pad_piece_store(p.feats, p.rows_cap, D, it, __ldg(&p.utts[it >> kPadPieceShift].n_rows), zero_block);
+      }
       quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
     }
-
     const uint4 tg0 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 2);   // targets of frames 0, 1
     const uint4 tg1 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 3);   // targets of frames 2, 3
 
@@ -355,8 +432,54 @@ fbank_warp_kernel(const QuadParams p) {
     });
     __syncwarp();
 
+#if B200FE_OUT_LEAN
+    // ---- LFR + CMVN: each frame's row of n_mels goes, as 128-bit pieces, to the (row, slot) pairs of its descriptor.
+    //      One divergent region for the lanes that carry a piece; inside it every branch is warp-uniform.
+    if (act) {
+      const int f0 = hd1.x, T = hd1.y, rows = hd1.z;
+      float* out_l = p.feats + (long long)utt * p.rows_cap * D + 4 * lane;
+      const float* cm_l = p.cmvn ? p.cmvn + 4 * lane : nullptr;
+      const float4* lm4 = reinterpret_cast<const float4*>(lm_s) + lane;
+      const unsigned tgt[8] = {tg0.x, tg0.y, tg0.z, tg0.w, tg1.x, tg1.y, tg1.z, tg1.w};
+      auto emit = [&](const float4& v, int jm, float* dst) {   // (x + shift) * scale in the reference's order, VF:34-35
+        float4 o = v;
+        if (cm_l) {
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(cm_l + jm));
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(cm_l + D + jm));
+          o = make_float4((v.x + sh.x) * sc.x, (v.y + sh.y) * sc.y, (v.z + sh.z) * sc.z, (v.w + sh.w) * sc.w);
+        }
+        stg_stream4(dst, o);
+      };
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const unsigned c0 = tgt[2 * t], c1 = tgt[2 * t + 1];
+        if (c0 == kNoTarget && c1 == kNoTarget) continue;          // invalid frame, or the generic path below
+        const float4 v = lm4[t * M4];
+        if (c0 != kNoTarget) emit(v, (int)(c0 >> kTargetOffBits) * M, out_l + (c0 & ((1u << kTargetOffBits) - 1)));
+        if (c1 != kNoTarget) emit(v, (int)(c1 >> kTargetOffBits) * M, out_l + (c1 & ((1u << kTargetOffBits) - 1)));
+      }
+      if (slow) {   // first / last frame of the utterance (replicated by the LFR padding), or lfr_m > 2 lfr_n
+#pragma unroll 1
+        for (int t = 0; t < nF; ++t) {
+          if (!((slow >> t) & 1)) continue;
+          const int f = f0 + t;
+          const int num = f + lfr_left - (lfr_m - 1);
+          const int i_lo = (f == 0 || num <= 0) ? 0 : (num + lfr_n - 1) / lfr_n;
+          const int i_top = f == T - 1 ? rows - 1 : min((f + lfr_left) / lfr_n, rows - 1);
+          const float4 v = lm4[t * M4];
+#pragma unroll 1
+          for (int i = i_lo; i <= i_top; ++i)
+#pragma unroll 1
+            for (int jj = 0; jj < lfr_m; ++jj)
+              if (min(max(lfr_n * i + jj - lfr_left, 0), T - 1) == f) emit(v, jj * M, out_l + (long long)i * D + jj * M);
+        }
+      }
+    }
+
+#else
     // ---- LFR + CMVN: each frame's row of n_mels goes, as 128-bit pieces, to the (row, slot) pairs of its descriptor
     {
+      const int f0 = hd1.x, T = hd1.y, rows = hd1.z;
       float* out_l = p.feats + (long long)utt * p.rows_cap * D + 4 * lane;
       const unsigned tgt[8] = {tg0.x, tg0.y, tg0.z, tg0.w, tg1.x, tg1.y, tg1.z, tg1.w};
       const float* cm_l = p.cmvn ? p.cmvn + 4 * lane : nullptr;
@@ -424,10 +547,21 @@ fbank_warp_kernel(const QuadParams p) {
       }
     }
 
+#endif
     if (!have_next) break;
     q = qn;
     g0_cur = g0_next;
-    nf_cur = nf_next;
+    nF = nF_next; slow = slow_next; utt = utt_next;
+#if B200FE_CLAIM2
+    qn = first_wave + __shfl_sync(0xffffffffu, claim, 0);
+    have_next = qn < p.n_quads;
+    if (have_next) hdn = __ldg(reinterpret_cast<const int4*>(p.quads + qn));
+#endif
+  }
+  // the zero block must outlive the bulk stores that read it
+  if (B200FE_PAD_MODE && lane == 0) {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
 

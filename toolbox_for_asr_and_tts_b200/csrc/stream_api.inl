@@ -23,8 +23,13 @@ int launch_stream(b200fe_handle* h, const StreamParams& p, size_t smem, bool dit
     k<<<p.n, kCtaThreads, smem, st>>>(p);                                                             \
   } while (0)
   const bool per_quad = warp_kernel_fits(h->L, h->S);   // every warp fetches its own quads (3 CTAs per SM)
+#ifdef B200FE_BENCH_ONLY
+  if (!per_quad || dither) return fail(h, B200FE_E_UNSUPPORTED, "bench-only build");
+  LAUNCHS(false, true);
+#else
   if (per_quad) { if (dither) LAUNCHS(true, true); else LAUNCHS(false, true); }
   else          { if (dither) LAUNCHS(true, false); else LAUNCHS(false, false); }
+#endif
 #undef LAUNCHS
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
@@ -87,6 +92,9 @@ int b200fe_stream_push(b200fe_handle* h, void* state_dev, int n_streams, int max
   for (int r = 0; r < kMelRounds; ++r) { p.mel_cnt[r] = h->mel_cnt[r]; p.mel_base[r] = h->mel_base[r]; } p.cmvn = h->d_cmvn;
   const bool dither = h->cfg.dither != 0.f;
   if (h->L == 400 && h->mel_paraformer) return launch_stream<25, true, MelShapeParaformer>(h, p, smem, dither, (cudaStream_t)stream);
+#ifdef B200FE_BENCH_ONLY
+  return fail(h, B200FE_E_UNSUPPORTED, "bench-only build");
+#endif
   if (h->L == 400) return launch_stream<25, true, MelShapeRuntime>(h, p, smem, dither, (cudaStream_t)stream);
   return launch_stream<32, false, MelShapeRuntime>(h, p, smem, dither, (cudaStream_t)stream);
 }

@@ -226,7 +226,13 @@ stream_push_kernel(const StreamParams p) {
   rows_total = min(rows_total, rows_all);
   rows_total = max(rows_total, rows_done);
   int n_emit = rows_total - rows_done;
-  if (n_emit > p.rows_cap) n_emit = (int)p.rows_cap;
+  // b200fe_stream_push refuses rows_cap < b200fe_stream_max_rows, so this cannot trigger through the ABI; if it ever
+  // does, the rows that do not fit stay pending (the counters below follow n_emit) instead of being lost
+  const bool truncated = n_emit > p.rows_cap;
+  if (truncated) {
+    n_emit = (int)p.rows_cap;
+    rows_total = rows_done + n_emit;
+  }
   {
     float* out = p.feats + (long long)b * p.rows_cap * D;
     const int D4 = D >> 2, M4 = M >> 2;
@@ -260,7 +266,7 @@ stream_push_kernel(const StreamParams p) {
 
   if (tid == 0) {
     p.rows_out[b] = n_emit;
-    if (fin) {
+    if (fin && !truncated) {
       cnt[sid] = 0; cnt[NS + sid] = 0; cnt[2 * NS + sid] = 0; cnt[3 * NS + sid] = 0;
     } else {
       cnt[sid] = new_carry; cnt[NS + sid] = T; cnt[2 * NS + sid] = rows_total; cnt[3 * NS + sid] = new_cache;

@@ -98,6 +98,10 @@ std::tuple<at::Tensor, at::Tensor> fe_forward(int64_t h, const at::Tensor& wave,
   } else {
     TORCH_CHECK(w.dim() == 2 && w.size(0) == b, "waveform must be [B, Nmax] when no offsets are given");
     row_stride = w.size(1);
+    // upstream slices input[i][:len] (VF:138): a length beyond the row would read the next utterance here
+    for (int u = 0; u < b; ++u)
+      TORCH_CHECK(len.data_ptr<int64_t>()[u] >= 0 && len.data_ptr<int64_t>()[u] <= row_stride,
+                  "input_lengths[", u, "] = ", len.data_ptr<int64_t>()[u], " is outside [0, ", row_stride, "]");
   }
   int64_t max_rows = 0;
   size_t ws = 0;

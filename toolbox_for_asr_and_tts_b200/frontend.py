@@ -171,7 +171,14 @@ class WavFrontend(nn.Module):
                                          int(self.dither_seed + self._calls))
         if self.subtract_mean:
             h.ops.subtract_column_mean(feats, feat_lens)
-        return feats, feat_lens
+        return feats, self._host_lengths(h, lens)
+
+    @staticmethod
+    def _host_lengths(h: "_Handle", lens: torch.Tensor) -> torch.Tensor:
+        """feats_lens as the reference returns them: an int64 CPU tensor (VF:160, torch.as_tensor of a Python list).
+        The counts are a function of the input lengths alone (TA:65-70, VF:43), so they come from the host-side plan:
+        no device read-back, no synchronisation.  (`forward_packed` returns the kernel's device-side copy instead.)"""
+        return h.ops.plan(h.h, lens)[1]
 
     @staticmethod
     def _pcm(x: torch.Tensor) -> torch.Tensor:
@@ -195,11 +202,11 @@ class WavFrontend(nn.Module):
         self._check_cuda(input, "input")
         h = self._handle(lfr=False, cmvn=False, fbank_only_cfg=True, device=input.device)
         self._calls += 1
-        feats, feat_lens = h.ops.forward(h.h, self._pcm(input), None, _as_length_tensor(input_lengths), 0, None,
-                                         int(self.dither_seed + self._calls))
+        lens = _as_length_tensor(input_lengths)
+        feats, feat_lens = h.ops.forward(h.h, self._pcm(input), None, lens, 0, None, int(self.dither_seed + self._calls))
         if self.subtract_mean:
             h.ops.subtract_column_mean(feats, feat_lens)
-        return feats, feat_lens
+        return feats, self._host_lengths(h, lens)
 
     def forward_lfr_cmvn(self, input: torch.Tensor, input_lengths) -> Tuple[torch.Tensor, torch.Tensor]:
         """VF:198-218: LFR + CMVN of given [B, T, n_mels] features."""
@@ -208,7 +215,7 @@ class WavFrontend(nn.Module):
         h = self._handle(lfr=True, cmvn=True, device=input.device)
         feats, feat_lens = h.ops.lfr_cmvn(h.h, input.to(torch.float32), lens)
         rows = int(-(-int(lens.max()) // self.lfr_n)) if lens.numel() else 0
-        return feats[:, :rows], feat_lens
+        return feats[:, :rows], -(-lens // self.lfr_n)      # int64 on the CPU, as VF:218
 
     @staticmethod
     def audio_statistics(wave: torch.Tensor, lengths, offsets=None, clip_level: float = 0.999) -> torch.Tensor:

@@ -84,7 +84,18 @@ class AudioRing:
 
 
 class WavFrontendOnline(WavFrontend):
-    """Chunked front-end with upstream's call shape (batch size 1, state in the caller's `cache` dict)."""
+    """Chunked front-end with upstream's call shape (batch size 1, state in the caller's `cache` dict).
+
+    forward(input[1, n], input_lengths, cache=dict, is_final=bool) -> (feats[1, k, D], feats_lengths[1]); k may be 0
+    (then feats is an empty [1, 0, D] tensor).  Like upstream's `WavFrontendOnline`, every call also leaves the raw
+    samples that belong to the rows it returned in `cache["waveforms"]` ([1, (k'-1)*shift + frame] samples, k' = lfr_n*(k-1)+1
+    frames starting at the first returned row's centre frame) and keeps the not yet consumed tail in
+    `cache["reserve_waveforms"]`: FSMN-VAD reads its per-frame energies from there (the consumer call is
+    R:voice-service/app/services/voice_interface.py:1585-1590, R:voice-service/app/api/voice.py:465-470).
+
+    The stream counters are deterministic functions of the chunk lengths, so the host mirrors them (`cache["_host"]`)
+    and knows how many rows a push returns without reading anything back: no synchronisation, no per-call allocation
+    besides the output."""
 
     def __init__(self, *args, max_chunk_samples: int = 16000, **kwargs):
         super().__init__(*args, **kwargs)
@@ -93,9 +104,33 @@ class WavFrontendOnline(WavFrontend):
         self.frame_shift_sample_length = int(self.frame_shift * self.fs / 1000)
 
     def init_cache(self, cache: dict, device="cuda") -> dict:
-        cache["pool"] = StreamPool(self, 1, self.max_chunk_samples, device)
-        cache["ids"] = torch.zeros(1, dtype=torch.int32, device=device)
+        dev = torch.device(device)
+        cache["pool"] = StreamPool(self, 1, self.max_chunk_samples, dev)
+        cache["ids"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        cache["_len"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        cache["_fin"] = (torch.zeros(1, dtype=torch.uint8, device=dev), torch.ones(1, dtype=torch.uint8, device=dev))
+        cache["_host"] = dict(carry=0, frames=0, rows=0)
+        cache["reserve_waveforms"] = torch.zeros(1, 0, dtype=torch.float32, device=dev)
+        cache["waveforms"] = torch.zeros(1, 0, dtype=torch.float32, device=dev)
         return cache
+
+    def _rows_after_push(self, st: dict, m: int, final: bool) -> int:
+        """Host mirror of the stream counters (csrc/stream_kernel.cuh): rows one push of m samples returns."""
+        L, S = self.frame_sample_length, self.frame_shift_sample_length
+        total = st["carry"] + m
+        nf = (total - L) // S + 1 if total >= L else 0
+        st["carry"] = total - nf * S
+        st["frames"] += nf
+        t = st["frames"]
+        rows_all = -(-t // self.lfr_n) if t > 0 else 0
+        need = self.lfr_m - 1 - (self.lfr_m - 1) // 2
+        rows_total = rows_all if final else ((t - 1 - need) // self.lfr_n + 1 if t - 1 >= need else 0)
+        rows_total = max(min(rows_total, rows_all), st["rows"])
+        k = rows_total - st["rows"]
+        st["rows"] = rows_total
+        if final:
+            st["carry"] = st["frames"] = st["rows"] = 0
+        return k
 
     def forward(self, input: torch.Tensor, input_lengths, cache: Optional[dict] = None, is_final: bool = False,
                 **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -106,24 +141,35 @@ class WavFrontendOnline(WavFrontend):
         if "pool" not in cache:
             self.init_cache(cache, input.device)
         pool: StreamPool = cache["pool"]
+        st = cache["_host"]
         n = int(_as_length_tensor(input_lengths)[0])
-        x = input[0, :n].to(torch.float32)
-        outs = []
-        pos = 0
+        x = input[:, :n].to(torch.float32)
+        L, S = self.frame_sample_length, self.frame_shift_sample_length
+        outs, k_total, pos = [], 0, 0
         while True:
             m = min(self.max_chunk_samples, n - pos)
             last = pos + m >= n
-            chunk = torch.zeros(1, self.max_chunk_samples, dtype=torch.float32, device=input.device)
-            chunk[0, :m] = x[pos:pos + m]
-            fin = torch.tensor([1 if (is_final and last) else 0], dtype=torch.uint8, device=input.device)
-            feats, rows = pool.push(chunk, torch.tensor([m], dtype=torch.int32, device=input.device), cache["ids"], fin)
-            k = int(rows[0])   # the reference returns exact-size tensors, so this path synchronises
+            fin = bool(is_final and last)
+            cache["_len"].fill_(m)
+            k = self._rows_after_push(st, m, fin)
+            chunk = x[:, pos:pos + m] if m > 0 else x.new_zeros(1, 1)
+            feats, _ = pool.push(chunk, cache["_len"], cache["ids"], cache["_fin"][1 if fin else 0])
             if k:
                 outs.append(feats[0, :k])
+            k_total += k
             pos += m
             if last:
                 break
+        # raw samples of the returned rows (upstream: cache["waveforms"]) and of the rows still to come
+        # (cache["reserve_waveforms"]): reserve starts at the centre frame of the first row not returned yet
+        wav = torch.cat((cache["reserve_waveforms"], x), dim=1)
+        if k_total:
+            cache["waveforms"] = wav[:, :min(wav.shape[1], self.lfr_n * (k_total - 1) * S + L)]
+            wav = wav[:, min(wav.shape[1], self.lfr_n * k_total * S):]
+        else:
+            cache["waveforms"] = wav[:, :0]
+        cache["reserve_waveforms"] = wav[:, :0] if is_final else wav
         if not outs:
-            return torch.empty(0, device=input.device), torch.zeros(1, dtype=torch.int64)
-        out = torch.cat(outs, dim=0).unsqueeze(0)
-        return out, torch.as_tensor([out.shape[1]], dtype=torch.int64)
+            return input.new_zeros((1, 0, self.output_size()), dtype=torch.float32), torch.zeros(1, dtype=torch.int64)
+        out = (outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)).unsqueeze(0)
+        return out, torch.as_tensor([k_total], dtype=torch.int64)
