@@ -156,6 +156,20 @@ int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total,
                        const int64_t* lengths_dev, int batch, int64_t max_frames, float* mel_dev, int64_t frames_cap,
                        int64_t* mel_lens_dev, void* stream);
 
+/* ---- host ingest: the gather funasr performs on the HOST in front of the front-end call - the list of np.float32
+ * utterances the reference hands to it (R:voice-service/app/services/voice_interface.py:2049-2053, 1370-1374) padded into
+ * one [B, Nmax] tensor (pad_sequence in funasr's extract_fbank, UPSTREAM-RECALLED).  Here: utterance u (host pointer
+ * utterances_host[u], lengths[u] elements of elem_size 4 = float32 or 2 = int16 PCM) is copied by `threads` host threads
+ * (0 = all cores, at most 32) to staging_pinned + dst_offsets[u] (a caller-owned cudaMallocHost buffer) and from there to
+ * wave_dev + dst_offsets[u] with cudaMemcpyAsync on `stream`, in `groups` groups of consecutive utterances so that the
+ * gather of group g+1 overlaps the PCIe copy of group g.  dst_offsets must ascend and not overlap; the result is the
+ * length-packed buffer b200fe_forward takes.  The call returns when the last copy is ENQUEUED; staging_pinned may be
+ * reused once that copy has completed (record an event on `stream`). */
+int b200fe_host_threads(void);
+int b200fe_host_ingest(const void* const* utterances_host, const int64_t* lengths, const int64_t* dst_offsets, int batch,
+                       int elem_size, void* staging_pinned, void* wave_dev, int64_t capacity_elems, int groups, int threads,
+                       void* stream);
+
 /* ---- by-products the reference computes on the host around its funasr calls.
  * b200fe_audio_stats replaces _log_audio_statistics and the per-chunk energy gate (R:voice-service/app/services/
  * voice_interface.py:873-939, 1298-1300, 1569-1570) for a whole ragged batch: out_dev is float64 [batch, 6] =

@@ -41,3 +41,17 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"] == bench.WORKLOAD
+    assert line["config"]["batch_per_gpu"] == bench.BATCH and "all 256 utterances" in line["cpu_baseline"]["sample"]
+
+
+def test_host_ingest_packs_like_numpy_concatenate():
+    """b200fe_host_ingest's host side (the multi-threaded gather into the staging buffer) through ctypes, without a GPU:
+    a NULL device destination is refused before any CUDA call, and the symbol set is the header's."""
+    import ctypes
+
+    from toolbox_for_asr_and_tts_b200 import _native
+    lib = _native.cdll()
+    assert lib.b200fe_host_threads() >= 1
+    rc = lib.b200fe_host_ingest(None, None, None, 3, 4, None, None, ctypes.c_int64(0), 2, 2, None)
+    assert rc < 0
+    assert lib.b200fe_host_ingest(None, None, None, 0, 4, None, None, ctypes.c_int64(0), 2, 2, None) == 0   # empty batch

@@ -1120,3 +1120,32 @@ def test_online_frontend_hands_back_frame_aligned_waveforms(variants_golden):
     sh, sc = cm[0].astype(np.float64), cm[1].astype(np.float64)
     assert_logmel_close((got.cpu().numpy().astype(np.float64) / sc - sh).reshape(-1, 5, 80),
                         (full[0].cpu().numpy().astype(np.float64) / sc - sh).reshape(-1, 5, 80))
+
+
+def test_host_ingest_from_numpy_list_and_dense_tensor_equals_device_resident_forward(cmvn):
+    """HostIngest: the utterances as a reference caller holds them (a list of separate np.float32 arrays, or the dense
+    [B, Nmax] host tensor funasr pads them into) -> multi-threaded gather into pinned staging -> H2D -> fused kernels.
+    Must equal, bit for bit, forward() on the same data already on the device; double-buffering must survive many calls
+    with changing batches; int16 PCM takes the same route."""
+    from toolbox_for_asr_and_tts_b200.ingest import HostIngest
+    fe = make_fe(cmvn)
+    ing = HostIngest(fe, capacity_samples=400000, device=DEV, groups=3, threads=4)
+    rng = np.random.default_rng(12)
+    for it in range(5):
+        lens = [int(n) for n in rng.integers(300, 60000, size=int(rng.integers(1, 7)))]
+        waves = [synth.uniform_pcm(200 + it, i, n) for i, n in enumerate(lens)]
+        ref, rl = fe(dense_batch(waves), lens)
+        got, gl = ing.forward(waves)
+        assert torch.equal(gl.cpu(), rl) and torch.equal(got, ref), it
+        dense = torch.zeros(len(lens), max(lens))
+        for i, w in enumerate(waves):
+            dense[i, :len(w)] = torch.from_numpy(w)
+        got2, gl2 = ing.forward(dense, lens)
+        assert torch.equal(gl2.cpu(), rl) and torch.equal(got2, ref), it
+    ing16 = HostIngest(fe, capacity_samples=400000, dtype=torch.int16, device=DEV)
+    ints = [rng.integers(-20000, 20000, size=n, dtype=np.int16) for n in (16000, 401, 7777)]
+    ref, rl = fe(dense_batch([w.astype(np.float32) / np.float32(32768.0) for w in ints]), [16000, 401, 7777])
+    got, gl = ing16.forward(ints)
+    assert torch.equal(gl.cpu(), rl) and torch.equal(got, ref)
+    with pytest.raises(ValueError, match="capacity"):
+        ing.forward([np.zeros(500000, dtype=np.float32)])

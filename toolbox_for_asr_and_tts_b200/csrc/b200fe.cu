@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -898,3 +899,4 @@ int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int6
 #include "extras_api.inl"
 #include "stream_api.inl"
 #include "tts_api.inl"
+#include "host_ingest.inl"

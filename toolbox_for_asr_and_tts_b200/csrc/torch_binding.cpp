@@ -391,6 +391,36 @@ void fe_subtract_column_mean(at::Tensor feats, const at::Tensor& n_rows) {
   TORCH_CHECK(rc == B200FE_OK, "b200fe_subtract_column_mean failed (", rc, ")");
 }
 
+// Host ingest: utterances (CPU tensors, float32 or int16, 1-D contiguous; e.g. torch.from_numpy views of the arrays the
+// reference hands to funasr) -> pinned staging -> device, multi-threaded gather pipelined with the PCIe copy, on the
+// current stream of `wave_dev`'s device.
+void fe_host_ingest(at::TensorList waves, const at::Tensor& lengths, const at::Tensor& offsets, at::Tensor staging,
+                    at::Tensor wave_dev, int64_t groups, int64_t threads) {
+  TORCH_CHECK(wave_dev.is_cuda() && wave_dev.is_contiguous(), "b200fe.host_ingest: destination must be a contiguous CUDA tensor");
+  TORCH_CHECK(!staging.is_cuda() && staging.is_pinned() && staging.is_contiguous(),
+              "b200fe.host_ingest: staging must be a pinned, contiguous host tensor");
+  TORCH_CHECK(staging.scalar_type() == wave_dev.scalar_type() && staging.numel() >= wave_dev.numel(),
+              "b200fe.host_ingest: staging and destination must have one dtype and staging must be at least as large");
+  const auto dt = wave_dev.scalar_type();
+  TORCH_CHECK(dt == at::kFloat || dt == at::kShort, "b200fe.host_ingest: float32 or int16 PCM");
+  auto len = lengths.to(at::kCPU, at::kLong).contiguous();
+  auto off = offsets.to(at::kCPU, at::kLong).contiguous();
+  const int b = (int)len.numel();
+  TORCH_CHECK((int)waves.size() == b && off.numel() == b, "b200fe.host_ingest: one utterance, length and offset per entry");
+  std::vector<const void*> src(b);
+  for (int u = 0; u < b; ++u) {
+    const at::Tensor& w = waves[u];
+    TORCH_CHECK(!w.is_cuda() && w.scalar_type() == dt && w.is_contiguous() && w.numel() >= len.data_ptr<int64_t>()[u],
+                "b200fe.host_ingest: utterance ", u, " must be a contiguous host tensor of the destination's dtype holding its length");
+    src[u] = w.data_ptr();
+  }
+  c10::cuda::CUDAGuard guard(wave_dev.device());
+  const int rc = b200fe_host_ingest(src.data(), len.data_ptr<int64_t>(), off.data_ptr<int64_t>(), b, (int)wave_dev.element_size(),
+                                    staging.data_ptr(), wave_dev.data_ptr(), wave_dev.numel(), (int)groups, (int)threads,
+                                    cur_stream());
+  TORCH_CHECK(rc == B200FE_OK, "b200fe_host_ingest failed (", rc, ")");
+}
+
 int64_t fe_launch_count(int64_t h) { return b200fe_launch_count(H(h)); }
 
 void fe_select_kernel(int64_t h, int64_t which) { check(b200fe_select_kernel(H(h), (int)which), H(h), "b200fe_select_kernel"); }
@@ -433,6 +463,8 @@ TORCH_LIBRARY(b200fe, m) {
   m.def("ring_reset(Tensor(a!) state, int n_streams, int capacity, Tensor ids) -> ()", ring_reset);
   m.def("ring_push(Tensor(a!) state, int n_streams, int capacity, Tensor chunks, Tensor lens, Tensor ids) -> ()", ring_push);
   m.def("ring_window(Tensor state, int n_streams, int capacity, Tensor ids) -> (Tensor, Tensor)", ring_window);
+  m.def("host_ingest(Tensor[] waves, Tensor lengths, Tensor offsets, Tensor(a!) staging, Tensor(b!) wave_dev, int groups, "
+        "int threads) -> ()", fe_host_ingest);
   m.def("launch_count(int h) -> int", fe_launch_count);
   m.def("select_kernel(int h, int which) -> ()", fe_select_kernel);
   m.def("profile_enable(int h, int every) -> ()", fe_profile_enable);
