@@ -141,6 +141,14 @@ int b200fe_stream_push(b200fe_handle* h, void* state_dev, int n_streams, int max
                        const float* chunks_dev, int64_t chunk_stride, const int32_t* chunk_lens_dev,
                        const int32_t* stream_ids_dev, const uint8_t* is_final_dev, int n,
                        float* feats_dev, int64_t rows_cap, int32_t* rows_out_dev, void* stream);
+/* The same tick that also returns the reference's per-chunk energy gate inputs (R:voice-service/app/services/
+ * voice_interface.py:1569-1578, 1298-1300: is_speech = mean|x| > 0.03 and max|x| > 0.17): chunk_stats_dev out [n, 2]
+ * = {mean |x|, max |x|} of each pushed chunk (NULL = plain b200fe_stream_push). */
+int b200fe_stream_push_stats(b200fe_handle* h, void* state_dev, int n_streams, int max_chunk_samples,
+                             const float* chunks_dev, int64_t chunk_stride, const int32_t* chunk_lens_dev,
+                             const int32_t* stream_ids_dev, const uint8_t* is_final_dev, int n,
+                             float* feats_dev, int64_t rows_cap, int32_t* rows_out_dev, float* chunk_stats_dev,
+                             void* stream);
 /* Upper bound of rows one push can emit for a chunk of max_chunk_samples (sizes rows_cap). */
 int b200fe_stream_max_rows(const b200fe_handle* h, int max_chunk_samples);
 
@@ -213,6 +221,11 @@ int b200fe_subtract_column_mean(float* feats_dev, int64_t rows_cap, int dim, con
  * x[u][n] = amp * (2*U01(hash(seed,u,n)) - 1) written at wave_dev[offsets_dev[u] + n], n < lengths_dev[u]. */
 int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int64_t* lengths_dev, int batch,
                          uint64_t seed, float amp, void* stream);
+/* The same with an explicit generator id per batch entry (utt_ids_dev, int64 device array, NULL = 0..batch-1): a rank
+ * synthesises its shard of a corpus (longest-first partition) bit-identically to the single-process
+ * corpus. */
+int b200fe_synth_uniform_ids(float* wave_dev, const int64_t* offsets_dev, const int64_t* lengths_dev,
+                             const int64_t* utt_ids_dev_or_null, int batch, uint64_t seed, float amp, void* stream);
 
 /* Kernel launches issued by this handle since create() (bench.py's gpu_launches). */
 int64_t b200fe_launch_count(const b200fe_handle* h);

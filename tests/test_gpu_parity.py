@@ -1149,3 +1149,33 @@ def test_host_ingest_from_numpy_list_and_dense_tensor_equals_device_resident_for
     assert torch.equal(gl.cpu(), rl) and torch.equal(got, ref)
     with pytest.raises(ValueError, match="capacity"):
         ing.forward([np.zeros(500000, dtype=np.float32)])
+
+
+def test_stream_tick_returns_the_reference_energy_gate(cmvn):
+    """the per-chunk energy gate of StreamingASRSession.process_chunk (R:voice_interface.py:1569-1578:
+    is_speech = mean|x| > 0.03 and max|x| > 0.17, numpy on the host) comes back from the same launch as the rows."""
+    fe = make_fe(cmvn)
+    pool = StreamPool(fe, n_streams=6, max_chunk_samples=6400, device=DEV)
+    rng = np.random.default_rng(41)
+    lens = [6400, 3840, 6400, 100, 0, 6400]
+    amps = [0.3, 0.02, 0.05, 0.5, 0.0, 0.001]
+    chunks = np.zeros((6, 6400), dtype=np.float32)
+    for i, (n, a) in enumerate(zip(lens, amps)):
+        chunks[i, :n] = a * rng.standard_normal(n).clip(-3, 3).astype(np.float32)
+    chunks[2, 17] = 0.9                       # loud click in a quiet chunk: max passes, mean does not
+    ids = torch.arange(6, dtype=torch.int32)
+    plain_f, plain_r = pool.push(torch.from_numpy(chunks).to(DEV), torch.tensor(lens, dtype=torch.int32), ids)
+    pool.reset()
+    feats, rows, flags, stats = pool.push_with_speech_flags(torch.from_numpy(chunks).to(DEV),
+                                                            torch.tensor(lens, dtype=torch.int32), ids)
+    assert torch.equal(rows, plain_r) and torch.equal(feats[:, :int(rows.max())], plain_f[:, :int(rows.max())])
+    st = stats.cpu().numpy()
+    for i, n in enumerate(lens):
+        x = chunks[i, :n]
+        energy = float(np.mean(np.abs(x))) if n else 0.0            # :1569
+        peak = float(np.max(np.abs(x))) if n else 0.0               # :1570
+        assert abs(st[i, 0] - energy) <= 1e-6 * max(energy, 1e-3) and st[i, 1] == np.float32(peak), i
+        assert bool(flags[i]) == (energy > 0.03 and peak > 0.17), i  # STREAMING_VAD_USE_AND_LOGIC = True (:658)
+    _, _, or_flags, _ = pool.push_with_speech_flags(torch.from_numpy(chunks).to(DEV), torch.tensor(lens, dtype=torch.int32),
+                                                    ids, use_and_logic=False)
+    assert or_flags.cpu().tolist() == [True, False, True, True, False, False]

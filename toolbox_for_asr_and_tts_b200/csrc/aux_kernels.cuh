@@ -259,17 +259,20 @@ __device__ __forceinline__ unsigned long long synth_mix(unsigned long long seed,
   return z;
 }
 
-__global__ void synth_uniform_kernel(float* wave, const long long* offsets, const long long* lengths, int batch,
-                                     unsigned long long seed, float amp) {
-  const int u = blockIdx.y;
-  if (u >= batch) return;
+// utt_ids (optional): the generator's utterance id of batch entry u (default: u itself), so that a rank can synthesise
+// an arbitrary subset of a corpus (sharding.partition_utterances) bit-identically to synth.uniform_pcm(seed, id, n).
+__global__ void synth_uniform_kernel(float* wave, const long long* offsets, const long long* lengths,
+                                     const long long* utt_ids, int batch, unsigned long long seed, float amp) {
+  for (int u = blockIdx.y; u < batch; u += gridDim.y) {
   const long long n_u = lengths[u];
+  const unsigned long long id = utt_ids ? (unsigned long long)utt_ids[u] : (unsigned long long)u;
   float* dst = wave + offsets[u];
   for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_u;
        n += (long long)gridDim.x * blockDim.x) {
-    const unsigned k = (unsigned)(synth_mix(seed, (unsigned long long)u, (unsigned long long)n) >> 40);
+    const unsigned k = (unsigned)(synth_mix(seed, id, (unsigned long long)n) >> 40);
     const float c = (float)((int)k - (1 << 23)) * (1.0f / 8388608.0f);   // exact: 2*U01 - 1
     dst[n] = __fmul_rn(amp, c);
+  }
   }
 }
 

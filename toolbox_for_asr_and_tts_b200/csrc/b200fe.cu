@@ -886,12 +886,18 @@ int b200fe_lfr_cmvn(b200fe_handle* h, const float* fbank_dev, int64_t frames_cap
   return B200FE_OK;
 }
 
+int b200fe_synth_uniform_ids(float* wave_dev, const int64_t* offsets_dev, const int64_t* lengths_dev,
+                             const int64_t* utt_ids_dev_or_null, int batch, uint64_t seed, float amp, void* stream) {
+  if (!wave_dev || !offsets_dev || !lengths_dev || batch <= 0) return B200FE_E_INVALID;
+  synth_uniform_kernel<<<dim3(64, batch < 65535 ? batch : 65535), 256, 0, (cudaStream_t)stream>>>(
+      wave_dev, (const long long*)offsets_dev, (const long long*)lengths_dev, (const long long*)utt_ids_dev_or_null, batch, seed,
+      amp);
+  return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
+}
+
 int b200fe_synth_uniform(float* wave_dev, const int64_t* offsets_dev, const int64_t* lengths_dev, int batch, uint64_t seed,
                          float amp, void* stream) {
-  if (!wave_dev || !offsets_dev || !lengths_dev || batch <= 0) return B200FE_E_INVALID;
-  synth_uniform_kernel<<<dim3(64, batch), 256, 0, (cudaStream_t)stream>>>(
-      wave_dev, (const long long*)offsets_dev, (const long long*)lengths_dev, batch, seed, amp);
-  return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
+  return b200fe_synth_uniform_ids(wave_dev, offsets_dev, lengths_dev, nullptr, batch, seed, amp, stream);
 }
 
 }  // extern "C"

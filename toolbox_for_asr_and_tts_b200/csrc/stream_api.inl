@@ -73,6 +73,14 @@ int b200fe_stream_push(b200fe_handle* h, void* state_dev, int n_streams, int max
                        int64_t chunk_stride, const int32_t* chunk_lens_dev, const int32_t* stream_ids_dev,
                        const uint8_t* is_final_dev, int n, float* feats_dev, int64_t rows_cap, int32_t* rows_out_dev,
                        void* stream) {
+  return b200fe_stream_push_stats(h, state_dev, n_streams, max_chunk_samples, chunks_dev, chunk_stride, chunk_lens_dev,
+                                  stream_ids_dev, is_final_dev, n, feats_dev, rows_cap, rows_out_dev, nullptr, stream);
+}
+
+int b200fe_stream_push_stats(b200fe_handle* h, void* state_dev, int n_streams, int max_chunk_samples,
+                             const float* chunks_dev, int64_t chunk_stride, const int32_t* chunk_lens_dev,
+                             const int32_t* stream_ids_dev, const uint8_t* is_final_dev, int n, float* feats_dev,
+                             int64_t rows_cap, int32_t* rows_out_dev, float* chunk_stats_dev, void* stream) {
   StreamLayout lay; int nf_max, e_cap; size_t smem;
   int rc = stream_layout(h, n_streams, max_chunk_samples, lay, nf_max, e_cap, smem);
   if (rc) return rc;
@@ -84,7 +92,7 @@ int b200fe_stream_push(b200fe_handle* h, void* state_dev, int n_streams, int max
   StreamParams p;
   p.state = state_dev; p.lay = lay; p.chunks = chunks_dev; p.chunk_stride = chunk_stride; p.chunk_lens = chunk_lens_dev;
   p.stream_ids = stream_ids_dev; p.is_final = is_final_dev; p.n = n; p.max_chunk = max_chunk_samples; p.nf_max = nf_max;
-  p.feats = feats_dev; p.rows_cap = rows_cap; p.rows_out = rows_out_dev;
+  p.feats = feats_dev; p.rows_cap = rows_cap; p.rows_out = rows_out_dev; p.chunk_stats = chunk_stats_dev;
   p.frame_len = h->L; p.frame_shift = h->S; p.n_mels = h->cfg.n_mels; p.lfr_m = h->cfg.lfr_m; p.lfr_n = h->cfg.lfr_n;
   p.e_cap = e_cap; p.preemph = h->cfg.preemphasis; p.remove_dc = h->cfg.remove_dc_offset; p.log_floor = h->cfg.log_floor;
   p.dither = h->cfg.dither / (h->cfg.upscale_samples ? 32768.f : 1.f); p.seed = 0;

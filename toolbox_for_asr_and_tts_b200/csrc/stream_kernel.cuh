@@ -43,6 +43,7 @@ struct StreamParams {
   float* feats;           // [n, rows_cap, D]
   long long rows_cap;
   int* rows_out;          // [n]
+  float* chunk_stats;     // nullptr or [n, 2]: mean |x| and max |x| of each pushed chunk (the reference's energy gate)
   int frame_len, frame_shift, n_mels, lfr_m, lfr_n;
   int e_cap;
   float preemph;
@@ -130,7 +131,10 @@ stream_push_kernel(const StreamParams p) {
   const int b = blockIdx.x;
   const int sid = p.stream_ids[b];
   if (sid < 0 || sid >= p.lay.n_streams) {
-    if (tid == 0) p.rows_out[b] = 0;
+    if (tid == 0) {
+      p.rows_out[b] = 0;
+      if (p.chunk_stats) p.chunk_stats[2 * b] = p.chunk_stats[2 * b + 1] = 0.f;
+    }
     return;
   }
   int* cnt = p.lay.counters(p.state);
@@ -263,6 +267,33 @@ stream_push_kernel(const StreamParams p) {
   keep_from = max(keep_from, T - p.lay.cache_cap);
   const int new_cache = T > 0 ? T - keep_from : 0;
   for (int i = tid; i < new_cache * M; i += kCtaThreads) cache[i] = logmel_s[(keep_from - base_abs) * M + i];
+
+  // The reference's per-chunk energy gate (R:voice-service/app/services/voice_interface.py:1569-1578: mean |x| and
+  // max |x| of the chunk against two thresholds) as a by-product of the tick: the chunk was just read by the framing
+  // pass (L2-resident), the CTA reduces it once more and returns both numbers next to the rows.
+  if (p.chunk_stats) {
+    float sa = 0.f, mx = 0.f;
+    for (int i = tid; i < n_new; i += kCtaThreads) {
+      const float a = fabsf(chunk[i]);
+      sa += a;
+      mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __syncthreads();                       // logmel_s is free: every thread is past the row / splice copies above
+    if (lane == 0) { logmel_s[warp] = sa; logmel_s[kWarps + warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      float m = 0.f;
+      for (int w = 0; w < kWarps; ++w) { tot += (double)logmel_s[w]; m = fmaxf(m, logmel_s[kWarps + w]); }
+      p.chunk_stats[2 * b] = n_new > 0 ? (float)(tot / (double)n_new) : 0.f;
+      p.chunk_stats[2 * b + 1] = m;
+    }
+  }
 
   if (tid == 0) {
     p.rows_out[b] = n_emit;

@@ -200,9 +200,10 @@ void fe_stream_reset(int64_t h, at::Tensor state, int64_t n_streams, int64_t max
         "b200fe_stream_reset");
 }
 
-std::tuple<at::Tensor, at::Tensor> fe_stream_push(int64_t h, at::Tensor state, int64_t n_streams, int64_t max_chunk,
-                                                  const at::Tensor& chunks, const at::Tensor& chunk_lens,
-                                                  const at::Tensor& stream_ids, const c10::optional<at::Tensor>& is_final) {
+std::tuple<at::Tensor, at::Tensor, at::Tensor> fe_stream_push_impl(int64_t h, at::Tensor state, int64_t n_streams,
+                                                                   int64_t max_chunk, const at::Tensor& chunks,
+                                                                   const at::Tensor& chunk_lens, const at::Tensor& stream_ids,
+                                                                   const c10::optional<at::Tensor>& is_final, bool want_stats) {
   TORCH_CHECK(state.is_cuda() && chunks.is_cuda(), "b200fe.stream_push: state and chunks must be CUDA tensors");
   TORCH_CHECK(chunks.scalar_type() == at::kFloat && chunks.dim() == 2, "chunks must be float32 [n, chunk_max]");
   c10::cuda::CUDAGuard guard(chunks.device());
@@ -223,21 +224,50 @@ std::tuple<at::Tensor, at::Tensor> fe_stream_push(int64_t h, at::Tensor state, i
   const int64_t d = b200fe_output_dim(H(h));
   auto feats = at::empty({n, rows_cap, d}, c.options());
   auto rows = at::empty({n}, c.options().dtype(at::kInt));
-  check(b200fe_stream_push(H(h), state.data_ptr(), (int)n_streams, (int)max_chunk, c.data_ptr<float>(), c.size(1),
-                           cl.data_ptr<int32_t>(), ids.data_ptr<int32_t>(), finp, n, feats.data_ptr<float>(), rows_cap,
-                           rows.data_ptr<int32_t>(), cur_stream()),
+  at::Tensor stats;
+  if (want_stats) stats = at::empty({n, 2}, c.options());
+  check(b200fe_stream_push_stats(H(h), state.data_ptr(), (int)n_streams, (int)max_chunk, c.data_ptr<float>(), c.size(1),
+                                 cl.data_ptr<int32_t>(), ids.data_ptr<int32_t>(), finp, n, feats.data_ptr<float>(), rows_cap,
+                                 rows.data_ptr<int32_t>(), want_stats ? stats.data_ptr<float>() : nullptr, cur_stream()),
         H(h), "b200fe_stream_push");
-  return {feats, rows};
+  return {feats, rows, stats};
 }
 
-void fe_synth_uniform(at::Tensor wave, const at::Tensor& offsets, const at::Tensor& lengths, int64_t seed, double amp) {
+std::tuple<at::Tensor, at::Tensor> fe_stream_push(int64_t h, at::Tensor state, int64_t n_streams, int64_t max_chunk,
+                                                  const at::Tensor& chunks, const at::Tensor& chunk_lens,
+                                                  const at::Tensor& stream_ids, const c10::optional<at::Tensor>& is_final) {
+  auto r = fe_stream_push_impl(h, state, n_streams, max_chunk, chunks, chunk_lens, stream_ids, is_final, false);
+  return {std::get<0>(r), std::get<1>(r)};
+}
+
+// + [n, 2] = {mean |x|, max |x|} of every chunk: the reference's energy gate (R:voice_interface.py:1569-1578)
+std::tuple<at::Tensor, at::Tensor, at::Tensor> fe_stream_push_stats(int64_t h, at::Tensor state, int64_t n_streams,
+                                                                    int64_t max_chunk, const at::Tensor& chunks,
+                                                                    const at::Tensor& chunk_lens, const at::Tensor& stream_ids,
+                                                                    const c10::optional<at::Tensor>& is_final) {
+  return fe_stream_push_impl(h, state, n_streams, max_chunk, chunks, chunk_lens, stream_ids, is_final, true);
+}
+
+void fe_synth_uniform_ids(at::Tensor wave, const at::Tensor& offsets, const at::Tensor& lengths,
+                          const c10::optional<at::Tensor>& utt_ids, int64_t seed, double amp) {
   TORCH_CHECK(wave.is_cuda() && wave.scalar_type() == at::kFloat && wave.is_contiguous(), "wave must be contiguous CUDA float32");
   c10::cuda::CUDAGuard guard(wave.device());
   auto off = offsets.to(wave.device(), at::kLong).contiguous();
   auto len = lengths.to(wave.device(), at::kLong).contiguous();
-  int rc = b200fe_synth_uniform(wave.data_ptr<float>(), off.data_ptr<int64_t>(), len.data_ptr<int64_t>(), (int)len.numel(),
-                                (uint64_t)seed, (float)amp, cur_stream());
+  at::Tensor ids;
+  const int64_t* idp = nullptr;
+  if (utt_ids.has_value() && utt_ids->defined()) {
+    ids = utt_ids->to(wave.device(), at::kLong).contiguous();
+    TORCH_CHECK(ids.numel() == len.numel(), "utt_ids and lengths differ in size");
+    idp = ids.data_ptr<int64_t>();
+  }
+  int rc = b200fe_synth_uniform_ids(wave.data_ptr<float>(), off.data_ptr<int64_t>(), len.data_ptr<int64_t>(), idp,
+                                    (int)len.numel(), (uint64_t)seed, (float)amp, cur_stream());
   TORCH_CHECK(rc == B200FE_OK, "b200fe_synth_uniform failed");
+}
+
+void fe_synth_uniform(at::Tensor wave, const at::Tensor& offsets, const at::Tensor& lengths, int64_t seed, double amp) {
+  fe_synth_uniform_ids(wave, offsets, lengths, c10::nullopt, seed, amp);
 }
 
 int64_t tts_create(int64_t sample_rate, int64_t n_fft, int64_t hop, int64_t n_mels, double f_min, double f_max) {
@@ -452,7 +482,11 @@ TORCH_LIBRARY(b200fe, m) {
   m.def("stream_reset(int h, Tensor state, int n_streams, int max_chunk, Tensor? ids) -> ()", fe_stream_reset);
   m.def("stream_push(int h, Tensor state, int n_streams, int max_chunk, Tensor chunks, Tensor chunk_lens, Tensor stream_ids, "
         "Tensor? is_final) -> (Tensor, Tensor)", fe_stream_push);
+  m.def("stream_push_stats(int h, Tensor state, int n_streams, int max_chunk, Tensor chunks, Tensor chunk_lens, "
+        "Tensor stream_ids, Tensor? is_final) -> (Tensor, Tensor, Tensor)", fe_stream_push_stats);
   m.def("synth_uniform(Tensor wave, Tensor offsets, Tensor lengths, int seed, float amp) -> ()", fe_synth_uniform);
+  m.def("synth_uniform_ids(Tensor wave, Tensor offsets, Tensor lengths, Tensor? utt_ids, int seed, float amp) -> ()",
+        fe_synth_uniform_ids);
   m.def("tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_min, float f_max) -> int", tts_create);
   m.def("tts_destroy(int t) -> ()", tts_destroy);
   m.def("tts_forward(int t, Tensor wave, Tensor? offsets, Tensor lengths, int hop, int n_mels) -> (Tensor, Tensor)", tts_forward);

@@ -45,6 +45,22 @@ class StreamPool:
         return self._h.ops.stream_push(self._h.h, self.state, self.n_streams, self.max_chunk, chunks, chunk_lens,
                                        stream_ids, is_final)
 
+    # the reference's energy gate constants (R:voice-service/app/services/voice_interface.py:656-658)
+    VAD_ENERGY_THRESHOLD, VAD_MAX_THRESHOLD = 0.03, 0.17
+
+    def push_with_speech_flags(self, chunks: torch.Tensor, chunk_lens: torch.Tensor, stream_ids: torch.Tensor,
+                               is_final: Optional[torch.Tensor] = None, energy_threshold: float = VAD_ENERGY_THRESHOLD,
+                               max_threshold: float = VAD_MAX_THRESHOLD, use_and_logic: bool = True):
+        """`push` that also returns what `StreamingASRSession.process_chunk` computes on the host for every chunk
+        (R:voice_interface.py:1569-1578): is_speech = mean|x| > 0.03 AND (or OR) max|x| > 0.17, as a by-product of the
+        same kernel launch.  Returns (feats, rows, is_speech bool [n], stats float32 [n, 2] = mean|x|, max|x|)."""
+        if not chunks.is_cuda:
+            raise RuntimeError("chunks must be a CUDA tensor: the B200 front-end has no CPU fallback")
+        feats, rows, stats = self._h.ops.stream_push_stats(self._h.h, self.state, self.n_streams, self.max_chunk, chunks,
+                                                           chunk_lens, stream_ids, is_final)
+        a, b = stats[:, 0] > energy_threshold, stats[:, 1] > max_threshold
+        return feats, rows, (a & b) if use_and_logic else (a | b), stats
+
     def snapshot(self) -> torch.Tensor:
         """Checkpoint of every stream (one memcpy of the slab)."""
         return self.state.clone()
