@@ -191,12 +191,21 @@ int b200fe_audio_stats(const float* wave_dev, const int64_t* offsets_dev, int64_
 /* base64_to_audio_np after the WAV header (R:voice_interface.py:1004-1034): wire PCM (sample_width 1 = uint8, 2 = int16,
  * 4 = int32; interleaved channels) -> float32 mono at dst_rate: width normalisation, channel mean and - when the rates
  * differ - the linear-interpolation resampling of its numpy branch (np.interp over np.linspace), in float64 and the
- * reference's operation order, so the float32 output is bit-identical to numpy's.  (The scipy.signal.resample branch is
- * a whole-signal FFT of arbitrary length and is not implemented.)  n_frames_in counts sample FRAMES (all channels);
+ * reference's operation order, so the float32 output is bit-identical to numpy's.  b200fe_ingest_pcm_fft below is the
+ * branch the reference takes when scipy is installed.  n_frames_in counts sample FRAMES (all channels);
  * b200fe_ingest_length gives the output length, int(n * dst_rate / src_rate). */
 int64_t b200fe_ingest_length(int64_t n_frames_in, int src_rate, int dst_rate);
 int b200fe_ingest_pcm(const void* pcm_dev, int sample_width, int channels, int64_t n_frames_in, int src_rate, int dst_rate,
                       float* out_dev, int64_t out_capacity, void* stream);
+/* The same ingest with scipy.signal.resample (Fourier method) as the resampler: the branch the reference takes when scipy
+ * is importable (R:voice_interface.py:1022-1027): X = rfft(x), bins 0..min(n, num)/2 kept (the unpaired middle bin x2 when
+ * shortening, x0.5 when lengthening), y = irfft(X * num / n, num), float64, cast to float32 (:1045).  Arbitrary lengths:
+ * evaluated as the two DFT sums in float64 (see csrc/resample_fft.cuh); agrees with scipy to float64 round-off, i.e. to
+ * <= 1 float32 ulp after the cast.  workspace: b200fe_resample_fft_workspace bytes of device memory. */
+size_t b200fe_resample_fft_workspace(int64_t n_frames_in, int src_rate, int dst_rate);
+int b200fe_ingest_pcm_fft(const void* pcm_dev, int sample_width, int channels, int64_t n_frames_in, int src_rate,
+                          int dst_rate, float* out_dev, int64_t out_capacity, void* workspace_dev, size_t workspace_bytes,
+                          void* stream);
 /* Sliding audio windows per stream, resident in HBM: replaces `buf = np.concatenate([buf, chunk])[-target:]` of the KWS
  * window (1.6 s) and the pre-speech guard (0.4 s) (R:voice_interface.py:1304-1311, 1742-1746).  One slab holds a circular
  * buffer of capacity_samples per stream.  push appends chunk b ([n, chunk_stride] float32, chunk_lens_dev[b] samples) to

@@ -243,9 +243,23 @@ def subtract_column_mean(feats: np.ndarray) -> np.ndarray:
     return (feats - feats.mean(axis=0, keepdims=True)).astype(feats.dtype)
 
 
-def ingest_pcm(raw: np.ndarray, channels: int, src_rate: int, dst_rate: int = 16000) -> np.ndarray:
-    """R:voice-service/app/services/voice_interface.py:1004-1034 (base64_to_audio_np after the WAV header), with the numpy
-    (np.interp) resampling branch of :1029-1034.  raw: uint8 / int16 / int32 interleaved samples."""
+def resample_fourier(x: np.ndarray, num: int) -> np.ndarray:
+    """scipy.signal.resample(x, num) for real 1-D input, window=None, restated with numpy's FFT (scipy 1.18,
+    scipy/signal/_signaltools.py::resample): keep rfft bins 0 .. min(n, num)//2, the unpaired middle bin x2 when
+    shortening / x0.5 when lengthening, irfft(X / (n / num), n=num).  float64 in, float64 out."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    m = min(num, n)
+    X = np.fft.rfft(x)[: m // 2 + 1].copy()
+    if m % 2 == 0 and num != n:
+        X[m // 2] *= 2 if num < n else 0.5
+    return np.fft.irfft(X / (n / num), n=num)
+
+
+def ingest_pcm(raw: np.ndarray, channels: int, src_rate: int, dst_rate: int = 16000, method: str = "interp") -> np.ndarray:
+    """R:voice-service/app/services/voice_interface.py:1004-1045 (base64_to_audio_np after the WAV header).  raw: uint8 /
+    int16 / int32 interleaved samples.  method "scipy": the scipy.signal.resample branch (:1022-1027, what runs when
+    scipy is installed); "interp": the numpy fallback (:1028-1034)."""
     if raw.dtype == np.uint8:
         audio = (raw - 128) / 128.0          # :1007, uint8 arithmetic wraps exactly as upstream's does
     elif raw.dtype == np.int16:
@@ -258,8 +272,11 @@ def ingest_pcm(raw: np.ndarray, channels: int, src_rate: int, dst_rate: int = 16
         audio = np.mean(audio.reshape(-1, channels), axis=1)     # :1019
     if src_rate != dst_rate:
         old_length = len(audio)
-        new_length = int(old_length * dst_rate / src_rate)
-        old_indices = np.linspace(0, old_length - 1, old_length)
-        new_indices = np.linspace(0, old_length - 1, new_length)
-        audio = np.interp(new_indices, old_indices, audio)        # :1031-1034
+        new_length = int(old_length * dst_rate / src_rate)        # :1026 / :1030
+        if method == "scipy":
+            audio = resample_fourier(audio, new_length)           # :1027
+        else:
+            old_indices = np.linspace(0, old_length - 1, old_length)
+            new_indices = np.linspace(0, old_length - 1, new_length)
+            audio = np.interp(new_indices, old_indices, audio)    # :1031-1034
     return audio.astype(np.float32)                                # :1045

@@ -638,7 +638,7 @@ def test_ingest_pcm_is_bit_identical_to_numpy(dtype, channels, src):
         raw = rng.integers(info.min, info.max, size=n * channels, dtype=dtype, endpoint=True)
         ref = wf.ingest_pcm(raw, channels, src)
         t = torch.from_numpy(raw.view(np.uint8) if dtype == np.uint8 else raw).to(DEV)
-        got = WavFrontend.ingest_pcm(t, channels=channels, src_rate=src).cpu().numpy()
+        got = WavFrontend.ingest_pcm(t, channels=channels, src_rate=src, method="interp").cpu().numpy()
         assert got.dtype == np.float32 and got.shape == ref.shape, (n, got.shape, ref.shape)
         assert np.array_equal(got, ref), (n, np.abs(got - ref).max() if got.size else 0)
 
@@ -1179,3 +1179,60 @@ def test_stream_tick_returns_the_reference_energy_gate(cmvn):
     _, _, or_flags, _ = pool.push_with_speech_flags(torch.from_numpy(chunks).to(DEV), torch.tensor(lens, dtype=torch.int32),
                                                     ids, use_and_logic=False)
     assert or_flags.cpu().tolist() == [True, False, True, True, False, False]
+
+
+def test_ingest_with_scipy_fourier_resampling_against_the_scipy_golden():
+    """the resampling branch the reference takes when scipy is installed (scipy.signal.resample,
+    R:voice_interface.py:1022-1027) on the GPU, against outputs of scipy itself (tests/golden/resample_golden.npz):
+    240 / 400 ms chunks at 48 / 44.1 / 8 kHz, odd lengths, stereo, all three sample widths.  The float64 DFT sums agree
+    with pocketfft to round-off, so after the float32 cast at most a handful of samples may differ, by one ulp."""
+    import importlib.util
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("make_golden_resample", root / "tests" / "golden" / "make_golden_resample.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = dict(np.load(root / "tests" / "golden" / "resample_golden.npz"))
+    for name, (dtype, ch, rate, n) in mod.CASES.items():
+        raw = mod.wire_pcm(name)
+        t = torch.from_numpy(raw).to(DEV)
+        got = WavFrontend.ingest_pcm(t, channels=ch, src_rate=rate, dst_rate=16000, method="scipy").cpu().numpy()
+        ref = g[name]
+        assert got.dtype == np.float32 and got.shape == ref.shape, name
+        ulp = np.spacing(np.abs(ref).astype(np.float32))
+        assert (np.abs(got - ref) <= ulp).all(), (name, float(np.abs(got - ref).max()))
+        assert (got != ref).mean() <= 1e-3, (name, float((got != ref).mean()))
+    # equal rates: no resampling on either branch
+    raw = np.arange(-50, 50, dtype=np.int16)
+    a = WavFrontend.ingest_pcm(torch.from_numpy(raw).to(DEV), 1, 16000, 16000, method="scipy").cpu().numpy()
+    assert np.array_equal(a, (raw / 32768.0).astype(np.float32))
+
+
+def test_kws_sliding_window_through_the_charctc_preset():
+    """the wake-word path.  The reference keeps the newest 1.6 s of audio per session
+    (kws_audio_buffer, R:voice_interface.py:1304-1311) and hands it to the CharCTC-KWS model on every chunk (:1370-1374),
+    whose front-end stacks 5 frames every 3 (presets.CHARCTC_KWS).  Here: device-resident AudioRing windows of several
+    sessions -> one batched forward, against numpy's sliding window + the oracle."""
+    from toolbox_for_asr_and_tts_b200 import AudioRing, presets
+    conf = presets.CHARCTC_KWS
+    fe = WavFrontend(**conf)
+    ring = AudioRing(n_streams=4, capacity_samples=presets.KWS_WINDOW_SAMPLES, device=DEV)
+    rng = np.random.default_rng(77)
+    host = [np.zeros(0, dtype=np.float32) for _ in range(4)]
+    ids = [0, 1, 3]
+    ring.reset([0, 1, 2, 3])
+    for tick in range(9):                                   # 240 ms chunks (R:voice_interface.py:648): 2.16 s in all
+        chunks = np.stack([0.2 * rng.standard_normal(3840).astype(np.float32) for _ in ids])
+        ring.push(torch.from_numpy(chunks).to(DEV), [3840] * len(ids), ids)
+        for k, s in enumerate(ids):
+            host[s] = np.concatenate([host[s], chunks[k]])[-presets.KWS_WINDOW_SAMPLES:]      # :1304-1311
+        win, lens = ring.window(ids)
+        assert lens.cpu().tolist() == [len(host[s]) for s in ids]
+        feats, fl = fe(win, lens)
+        oconf = {k: v for k, v in conf.items() if k != "dither"}
+        ref, rl = wf.frontend_forward([host[s] for s in ids], [len(host[s]) for s in ids], cmvn=None, **oconf)
+        assert np.array_equal(fl.numpy(), rl) and feats.shape[-1] == 400
+        for k in range(len(ids)):
+            n = int(rl[k])
+            assert_logmel_close(feats[k, :n].cpu().numpy().reshape(n, 5, 80), ref[k, :n].reshape(n, 5, 80))
+            assert not feats[k, n:].any()

@@ -9,10 +9,14 @@ from conftest import LOGMEL_ATOL, PARAFORMER, VARIANT_CONFS, VARIANT_LENS, VARIA
 from hypothesis import given, settings
 from hypothesis import strategies as st
 
+from pathlib import Path
+
 from oracle import kaldi_fbank_np as kf
 from oracle import ref_thirdparty as ref
 from oracle import wav_frontend_np as wf
 from toolbox_for_asr_and_tts_b200 import synth
+
+ROOT = Path(__file__).resolve().parents[1]
 
 SEED = 1234
 
@@ -208,3 +212,18 @@ def test_oracle_matches_golden_fsmn_vad_frontend(variants_golden):
     g = variants_golden["vad_5_1_feats"]
     assert int(lens[0]) == g.shape[0] == 298 and feats.shape[1:] == g.shape
     assert np.abs(feats[0] - g).max() <= cmvn_atol(cm)
+
+
+def test_oracle_fourier_resampling_matches_the_scipy_golden():
+    """The oracle's restatement of scipy.signal.resample (the reference's resampler when scipy is installed,
+    R:voice_interface.py:1022-1027) against outputs of scipy itself (tests/golden/make_golden_resample.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_resample", ROOT / "tests" / "golden" / "make_golden_resample.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = dict(np.load(ROOT / "tests" / "golden" / "resample_golden.npz"))
+    for name, (dtype, ch, rate, n) in mod.CASES.items():
+        got = wf.ingest_pcm(mod.wire_pcm(name), ch, rate, 16000, method="scipy")
+        assert got.dtype == np.float32 and got.shape == g[name].shape, name
+        assert np.abs(got.astype(np.float64) - g[name]).max() <= 2e-7, name       # float64 round-off before the cast
+        assert (got != g[name]).mean() <= 1e-3, name

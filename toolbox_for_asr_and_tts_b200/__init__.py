@@ -9,5 +9,8 @@ from .cmvn import load_cmvn, stats_to_cmvn, write_cmvn  # noqa: F401
 from .frontend import WavFrontend  # noqa: F401
 from .online import AudioRing, StreamPool, WavFrontendOnline  # noqa: F401
 from .tts_mel import TtsLogMel  # noqa: F401
+from . import presets  # noqa: F401
+from .ingest import HostIngest  # noqa: F401
 
-__all__ = ["WavFrontend", "WavFrontendOnline", "StreamPool", "AudioRing", "TtsLogMel", "load_cmvn", "write_cmvn", "stats_to_cmvn"]
+__all__ = ["WavFrontend", "WavFrontendOnline", "StreamPool", "AudioRing", "HostIngest", "TtsLogMel", "presets", "load_cmvn",
+           "write_cmvn", "stats_to_cmvn"]

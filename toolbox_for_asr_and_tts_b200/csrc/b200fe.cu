@@ -19,6 +19,7 @@
 
 #include "aux_kernels.cuh"
 #include "extras.cuh"
+#include "resample_fft.cuh"
 #include "fbank_tile.cuh"
 #include "fbank_warp.cuh"
 #include "stream_kernel.cuh"

@@ -43,6 +43,37 @@ int b200fe_ingest_pcm(const void* pcm_dev, int sample_width, int channels, int64
   return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
 }
 
+size_t b200fe_resample_fft_workspace(int64_t n_frames_in, int src_rate, int dst_rate) {
+  const int64_t n_out = b200fe_ingest_length(n_frames_in, src_rate, dst_rate);
+  if (n_out <= 0 || n_frames_in <= 0) return 0;
+  const int64_t m = n_out < n_frames_in ? n_out : n_frames_in;
+  return (size_t)n_frames_in * sizeof(double) + (size_t)(m / 2 + 1) * sizeof(double2) + 256;
+}
+
+int b200fe_ingest_pcm_fft(const void* pcm_dev, int sample_width, int channels, int64_t n_frames_in, int src_rate,
+                          int dst_rate, float* out_dev, int64_t out_capacity, void* workspace_dev, size_t workspace_bytes,
+                          void* stream) {
+  if (src_rate == dst_rate)
+    return b200fe_ingest_pcm(pcm_dev, sample_width, channels, n_frames_in, src_rate, dst_rate, out_dev, out_capacity, stream);
+  if (!pcm_dev || !out_dev || !workspace_dev || channels < 1 || (sample_width != 1 && sample_width != 2 && sample_width != 4))
+    return B200FE_E_INVALID;
+  const int64_t n_out = b200fe_ingest_length(n_frames_in, src_rate, dst_rate);
+  if (n_out < 0 || n_out > out_capacity) return B200FE_E_INVALID;
+  if (n_out == 0) return B200FE_OK;
+  if (n_frames_in < 1 || workspace_bytes < b200fe_resample_fft_workspace(n_frames_in, src_rate, dst_rate)) return B200FE_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* mono = reinterpret_cast<double*>(workspace_dev);
+  double2* X = reinterpret_cast<double2*>(reinterpret_cast<char*>(workspace_dev) + (((size_t)n_frames_in * sizeof(double) + 255) & ~(size_t)255));
+  const int64_t m = n_out < n_frames_in ? n_out : n_frames_in;
+  const int n_bins = (int)(m / 2 + 1);
+  long long blocks = (n_frames_in + 255) / 256;
+  blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
+  resample_mono_kernel<<<(unsigned)blocks, 256, 0, st>>>(pcm_dev, sample_width, channels, n_frames_in, mono);
+  resample_dft_kernel<<<n_bins, 256, 0, st>>>(mono, n_frames_in, n_bins, X);
+  resample_idft_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(X, n_frames_in, n_out, out_dev);
+  return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
+}
+
 size_t b200fe_ring_state_bytes(int n_streams, int capacity_samples) {
   if (n_streams <= 0 || capacity_samples <= 0) return 0;
   RingLayout lay{n_streams, capacity_samples};

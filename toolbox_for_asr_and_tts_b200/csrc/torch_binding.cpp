@@ -348,7 +348,15 @@ at::Tensor fe_audio_stats(const at::Tensor& wave, const c10::optional<at::Tensor
 }
 
 // pcm: CUDA uint8 / int16 / int32, interleaved channels -> float32 mono at dst_rate
+at::Tensor fe_ingest_pcm_impl(const at::Tensor& pcm, int64_t channels, int64_t src_rate, int64_t dst_rate, bool fourier);
 at::Tensor fe_ingest_pcm(const at::Tensor& pcm, int64_t channels, int64_t src_rate, int64_t dst_rate) {
+  return fe_ingest_pcm_impl(pcm, channels, src_rate, dst_rate, false);
+}
+// scipy.signal.resample as the resampler (the reference's branch when scipy is installed)
+at::Tensor fe_ingest_pcm_fft(const at::Tensor& pcm, int64_t channels, int64_t src_rate, int64_t dst_rate) {
+  return fe_ingest_pcm_impl(pcm, channels, src_rate, dst_rate, true);
+}
+at::Tensor fe_ingest_pcm_impl(const at::Tensor& pcm, int64_t channels, int64_t src_rate, int64_t dst_rate, bool fourier) {
   TORCH_CHECK(pcm.is_cuda(), "b200fe.ingest_pcm: PCM must be a CUDA tensor");
   int width = 0;
   if (pcm.scalar_type() == at::kByte) width = 1;
@@ -363,8 +371,16 @@ at::Tensor fe_ingest_pcm(const at::Tensor& pcm, int64_t channels, int64_t src_ra
   TORCH_CHECK(n_out >= 0, "b200fe.ingest_pcm: bad sample rates");
   auto out = at::empty({n_out}, x.options().dtype(at::kFloat));
   if (n_out == 0) return out;
-  int rc = b200fe_ingest_pcm(x.data_ptr(), width, (int)channels, n_in, (int)src_rate, (int)dst_rate, out.data_ptr<float>(),
-                             n_out, cur_stream());
+  int rc;
+  if (fourier && src_rate != dst_rate) {
+    const size_t ws = b200fe_resample_fft_workspace(n_in, (int)src_rate, (int)dst_rate);
+    auto work = at::empty({(int64_t)ws}, x.options().dtype(at::kByte));
+    rc = b200fe_ingest_pcm_fft(x.data_ptr(), width, (int)channels, n_in, (int)src_rate, (int)dst_rate, out.data_ptr<float>(),
+                               n_out, work.data_ptr(), ws, cur_stream());
+  } else {
+    rc = b200fe_ingest_pcm(x.data_ptr(), width, (int)channels, n_in, (int)src_rate, (int)dst_rate, out.data_ptr<float>(),
+                           n_out, cur_stream());
+  }
   TORCH_CHECK(rc == B200FE_OK, "b200fe_ingest_pcm failed (", rc, ")");
   return out;
 }
@@ -493,6 +509,7 @@ TORCH_LIBRARY(b200fe, m) {
   m.def("audio_stats(Tensor wave, Tensor? offsets, Tensor lengths, float clip_level) -> Tensor", fe_audio_stats);
   m.def("subtract_column_mean(Tensor(a!) feats, Tensor n_rows) -> ()", fe_subtract_column_mean);
   m.def("ingest_pcm(Tensor pcm, int channels, int src_rate, int dst_rate) -> Tensor", fe_ingest_pcm);
+  m.def("ingest_pcm_fft(Tensor pcm, int channels, int src_rate, int dst_rate) -> Tensor", fe_ingest_pcm_fft);
   m.def("ring_state(int n_streams, int capacity, Device device) -> Tensor", ring_state);
   m.def("ring_reset(Tensor(a!) state, int n_streams, int capacity, Tensor ids) -> ()", ring_reset);
   m.def("ring_push(Tensor(a!) state, int n_streams, int capacity, Tensor chunks, Tensor lens, Tensor ids) -> ()", ring_push);

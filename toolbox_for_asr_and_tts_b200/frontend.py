@@ -228,13 +228,19 @@ class WavFrontend(nn.Module):
                                          _as_length_tensor(lengths), float(clip_level))
 
     @staticmethod
-    def ingest_pcm(pcm: torch.Tensor, channels: int = 1, src_rate: int = 16000, dst_rate: int = 16000) -> torch.Tensor:
+    def ingest_pcm(pcm: torch.Tensor, channels: int = 1, src_rate: int = 16000, dst_rate: int = 16000,
+                   method: str = "scipy") -> torch.Tensor:
         """Wire PCM (CUDA uint8 / int16 / int32, interleaved channels) -> float32 mono at dst_rate, exactly as the
-        reference's base64_to_audio_np does after the WAV header (R:voice_interface.py:1004-1034: width normalisation,
-        channel mean, np.interp resampling - its numpy branch), bit-identical to numpy."""
+        reference's base64_to_audio_np does after the WAV header (R:voice_interface.py:1004-1045): width normalisation,
+        channel mean, resampling, float32.  method = "scipy": scipy.signal.resample, the Fourier method the reference
+        uses whenever scipy is installed (:1022-1027; float64 DFT sums on the GPU, equal to scipy's result up to float64
+        round-off); method = "interp": its numpy fallback np.interp (:1028-1034), bit-identical to numpy."""
         WavFrontend._check_cuda(pcm, "pcm")
         from . import _native
-        return _native.ops().ingest_pcm(pcm, int(channels), int(src_rate), int(dst_rate))
+        if method not in ("scipy", "interp"):
+            raise ValueError("method must be 'scipy' or 'interp'")
+        op = _native.ops().ingest_pcm_fft if method == "scipy" else _native.ops().ingest_pcm
+        return op(pcm, int(channels), int(src_rate), int(dst_rate))
 
     # ------------------------------------------------------------------ extras used by tests / tools
     def frame_counts(self, input_lengths) -> Tuple[torch.Tensor, torch.Tensor]:
