@@ -1162,19 +1162,21 @@ def test_stream_tick_returns_the_reference_energy_gate(cmvn):
     chunks = np.zeros((6, 6400), dtype=np.float32)
     for i, (n, a) in enumerate(zip(lens, amps)):
         chunks[i, :n] = a * rng.standard_normal(n).clip(-3, 3).astype(np.float32)
-    chunks[2, 17] = 0.9                       # loud click in a quiet chunk: max passes, mean does not
+    chunks[2, 17] = 0.9                       # a loud click in a quiet chunk
     ids = torch.arange(6, dtype=torch.int32)
     plain_f, plain_r = pool.push(torch.from_numpy(chunks).to(DEV), torch.tensor(lens, dtype=torch.int32), ids)
     pool.reset()
     feats, rows, flags, stats = pool.push_with_speech_flags(torch.from_numpy(chunks).to(DEV),
                                                             torch.tensor(lens, dtype=torch.int32), ids)
-    assert torch.equal(rows, plain_r) and torch.equal(feats[:, :int(rows.max())], plain_f[:, :int(rows.max())])
+    assert torch.equal(rows, plain_r)
+    for i in range(6):                                     # rows beyond a stream's count are not written
+        assert torch.equal(feats[i, :int(rows[i])], plain_f[i, :int(rows[i])]), i
     st = stats.cpu().numpy()
     for i, n in enumerate(lens):
         x = chunks[i, :n]
         energy = float(np.mean(np.abs(x))) if n else 0.0            # :1569
         peak = float(np.max(np.abs(x))) if n else 0.0               # :1570
-        assert abs(st[i, 0] - energy) <= 1e-6 * max(energy, 1e-3) and st[i, 1] == np.float32(peak), i
+        assert abs(st[i, 0] - energy) <= 1e-5 * max(energy, 1e-3) and st[i, 1] == np.float32(peak), i
         assert bool(flags[i]) == (energy > 0.03 and peak > 0.17), i  # STREAMING_VAD_USE_AND_LOGIC = True (:658)
     _, _, or_flags, _ = pool.push_with_speech_flags(torch.from_numpy(chunks).to(DEV), torch.tensor(lens, dtype=torch.int32),
                                                     ids, use_and_logic=False)

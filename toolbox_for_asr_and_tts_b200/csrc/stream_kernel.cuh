@@ -63,14 +63,15 @@ struct StreamParams {
 
 // per_quad: every warp fetches the samples of its quads itself (3.5 KB per warp) instead of the CTA staging the whole
 // [carry | chunk] buffer: 74 KB instead of 100 KB for a 600 ms chunk, i.e. 3 stream-CTAs per SM instead of 2.
-__host__ __device__ inline size_t stream_smem_bytes(int e_cap, int nf_max, int cache_cap, int n_mels, bool per_quad) {
+__host__ __device__ inline size_t stream_smem_bytes(int e_cap, int nf_max, int cache_cap, int n_mels, bool per_quad,
+                                                    int warps = kWarps) {
   size_t b = 0;
   if (per_quad) {
-    b += (size_t)kWarps * kQuadBuf * 4;
+    b += (size_t)warps * kQuadBuf * 4;
   } else {
     b += (size_t)e_cap * 4;
   }
-  b += (size_t)kWarps * kYWarpF4 * 16;
+  b += (size_t)warps * kYWarpF4 * 16;
   b += (size_t)(cache_cap + nf_max) * n_mels * 4;
   b += kTw2Total * 8;
   return b;
@@ -115,9 +116,13 @@ __global__ void stream_reset_kernel(void* state, StreamLayout lay, const int* id
   c[3 * lay.n_streams + s] = 0;
 }
 
-template <int NROWS, bool EXACT, bool DITHER, class MELS, bool PERQUAD>
-__global__ void __launch_bounds__(kCtaThreads, PERQUAD ? 3 : 2)
+// WARPS: warps per stream-CTA.  4 is the default; 2 halves the CTA's shared memory (49 KB for 600 ms chunks: 4 CTAs per SM)
+// so that 445..592 streams still run as ONE wave on 148 SMs instead of a full wave plus a mostly empty one.
+template <int NROWS, bool EXACT, bool DITHER, class MELS, bool PERQUAD, int WARPS = kWarps>
+__global__ void __launch_bounds__(32 * WARPS, PERQUAD ? (WARPS == 2 ? 4 : 3) : 2)
 stream_push_kernel(const StreamParams p) {
+  constexpr int kWarps = WARPS;                 // shadows the namespace constants inside this kernel
+  constexpr int kCtaThreads = 32 * WARPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* e_s = reinterpret_cast<float*>(smem_raw);                       // PERQUAD: [kWarps][kQuadBuf] sample buffers
   float4* xbuf = reinterpret_cast<float4*>(e_s + (PERQUAD ? kWarps * kQuadBuf : p.e_cap));
@@ -165,9 +170,10 @@ stream_push_kernel(const StreamParams p) {
   }
   // samples that stay behind for the next tick (read before anything overwrites the carry)
   const int new_carry = n - nf * S;
-  float keep[4];
+  constexpr int kKeep = (512 + kCtaThreads - 1) / kCtaThreads;   // the carry is shorter than one frame (<= 512 samples)
+  float keep[kKeep];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < kKeep; ++q) {
     const int k = tid + q * kCtaThreads;
     keep[q] = 0.f;
     if (k < new_carry) {
@@ -216,7 +222,7 @@ stream_push_kernel(const StreamParams p) {
   __syncthreads();
 
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < kKeep; ++q) {
     const int k = tid + q * kCtaThreads;
     if (k < new_carry) carry[k] = keep[q];
   }
