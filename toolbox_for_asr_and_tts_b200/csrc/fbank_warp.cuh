@@ -26,6 +26,9 @@
 #ifndef B200FE_OUT_LEAN      // 1: one divergent region, loads next to their stores; 0: all CMVN loads first (measured faster)
 #define B200FE_OUT_LEAN 0
 #endif
+#ifndef B200FE_OUT_DIRECT    // 1: the mel epilogue writes the output rows itself (32-bit stores, no staging tile)
+#define B200FE_OUT_DIRECT 0
+#endif
 #ifndef B200FE_CLAIM2        // 1: quads claimed two ahead (atomic read at the end of the iteration); 0: one ahead
 #define B200FE_CLAIM2 0
 #endif
@@ -423,6 +426,55 @@ fbank_warp_kernel(const QuadParams p) {
     const uint4 tg0 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 2);   // targets of frames 0, 1
     const uint4 tg1 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 3);   // targets of frames 2, 3
 
+#if B200FE_OUT_DIRECT
+    // ---- mel + log + LFR + CMVN in one go: the lane that holds filter iv of the quad's 4 frames writes it straight to
+    //      the (row, slot) targets of each frame - out[target + iv] = (x + shift[slot][iv]) * scale[slot][iv]
+    //      (VF:34-35, VF:40-60) - as 32-bit stores that a warp coalesces into one or two 128-byte lines.  No staging tile,
+    //      no regrouping into 128-bit pieces, the CMVN entries are per-lane scalar loads.
+    {
+      float* out_u = p.feats + (long long)utt * p.rows_cap * D;
+      const float* cm = p.cmvn;
+      const unsigned tgt[8] = {tg0.x, tg0.y, tg0.z, tg0.w, tg1.x, tg1.y, tg1.z, tg1.w};
+      constexpr unsigned kOffMask = (1u << kTargetOffBits) - 1;
+      mel_stage<MELS>(mel, pbuf4, lane, M, p.log_floor, [&](int iv, float a, float b, float c, float d) {
+        const float val[4] = {a, b, c, d};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const unsigned cd = tgt[2 * t + k];
+            if (cd == kNoTarget) continue;                       // warp-uniform
+            float x = val[t];
+            if (cm) {
+              const int jm = (int)(cd >> kTargetOffBits) * M + iv;
+              x = (x + __ldg(cm + jm)) * __ldg(cm + D + jm);
+            }
+            out_u[(cd & kOffMask) + iv] = x;
+          }
+        if (slow) {   // first / last frame of the utterance (replicated by the LFR padding), or lfr_m > 2 lfr_n
+          const int f0 = hd1.x, T = hd1.y, rows = hd1.z;
+#pragma unroll 1
+          for (int t = 0; t < nF; ++t) {
+            if (!((slow >> t) & 1)) continue;
+            const int f = f0 + t;
+            const int num = f + lfr_left - (lfr_m - 1);
+            const int i_lo = (f == 0 || num <= 0) ? 0 : (num + lfr_n - 1) / lfr_n;
+            const int i_top = f == T - 1 ? rows - 1 : min((f + lfr_left) / lfr_n, rows - 1);
+            const float v = t == 0 ? a : (t == 1 ? b : (t == 2 ? c : d));
+#pragma unroll 1
+            for (int i = i_lo; i <= i_top; ++i)
+#pragma unroll 1
+              for (int jj = 0; jj < lfr_m; ++jj)
+                if (min(max(lfr_n * i + jj - lfr_left, 0), T - 1) == f) {
+                  float x = v;
+                  if (cm) x = (x + __ldg(cm + jj * M + iv)) * __ldg(cm + D + jj * M + iv);
+                  out_u[(long long)i * D + jj * M + iv] = x;
+                }
+          }
+        }
+      });
+    }
+#else
     // ---- log-mel of the 4 frames into the warp's staging tile
     mel_stage<MELS>(mel, pbuf4, lane, M, p.log_floor, [&](int iv, float a, float b, float c, float d) {
       lm_s[iv] = a;
@@ -431,8 +483,10 @@ fbank_warp_kernel(const QuadParams p) {
       lm_s[3 * M + iv] = d;
     });
     __syncwarp();
+#endif
 
-#if B200FE_OUT_LEAN
+#if B200FE_OUT_DIRECT
+#elif B200FE_OUT_LEAN
     // ---- LFR + CMVN: each frame's row of n_mels goes, as 128-bit pieces, to the (row, slot) pairs of its descriptor.
     //      One divergent region for the lanes that carry a piece; inside it every branch is warp-uniform.
     if (act) {

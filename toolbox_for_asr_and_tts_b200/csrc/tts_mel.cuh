@@ -50,7 +50,8 @@ __host__ __device__ inline size_t tts_smem_bytes(int hop, int n_mels) {
   return b;
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 2)
+// 154 registers and 68 KB of shared memory per CTA: three CTAs (12 warps) per SM
+__global__ void __launch_bounds__(kCtaThreads, 3)
 tts_mel_kernel(const TtsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int hop = p.hop, M = p.n_mels;
