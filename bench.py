@@ -221,6 +221,27 @@ def run_ours(args, rank, world, local_rank):
     ms_total = float(t[0])
     value = audio_s * world * args.steps / (ms_total * 1e-3)
 
+    # ---------------- side measurement: the rows-packed output (forward_packed(pad=False): [sum of rows, 560] + offsets,
+    #                  for consumers that batch by length): no padding rows exist, so the 133 MB of zeros per step are
+    #                  not written.  Reported beside `value`, which keeps the reference's padded layout.
+    for _ in range(3):
+        fe.forward_packed(wave, offs_t, lens_t, pad=False)
+    barrier()
+    ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ep0.record()
+    t_host0 = time.perf_counter()
+    for _ in range(args.steps):
+        rows_feats, rows_lens, rows_offs = fe.forward_packed(wave, offs_t, lens_t, pad=False)
+    packed_host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
+    ep1.record()
+    barrier()
+    tp = torch.tensor([ep0.elapsed_time(ep1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    packed_ms = float(tp[0])
+    assert torch.equal(rows_lens, flens) and int(rows_offs[-1]) == rows_feats.shape[0]
+    del rows_feats
+
     # ---------------- end to end (`e2e`): every step starts from the utterances as a reference caller holds them - a
     #                  list of 256 separate np.float32 arrays in pageable host memory - and ends with the step's result
     #                  (the feature lengths) back on the host.  Inside the timed region, per step: multi-threaded gather
@@ -427,6 +448,10 @@ def run_ours(args, rank, world, local_rank):
                                   "inside the kernel's loads: bit-identical features at half the PCIe bytes"},
             "configs0_one_10s_utterance_gpu": {"ms_p50": lat[len(lat) // 2], "ms_p90": lat[int(len(lat) * 0.9)],
                                                "note": "pinned host PCM -> H2D -> forward -> synchronize, through WavFrontend.forward"},
+            "rows_packed_output": {"value": audio_s * world * args.steps / (packed_ms * 1e-3), "unit": UNIT,
+                                   "ms_per_step": packed_ms / args.steps, "host_enqueue_ms_per_step": packed_host_ms,
+                                   "note": "side measurement: forward_packed(pad=False) -> [sum of rows, 560] + row offsets; no "
+                                           "padding rows to clear (the padded layout above writes 133 MB of zeros per step)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu}

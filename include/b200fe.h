@@ -94,6 +94,12 @@ int b200fe_get_tables(const b200fe_handle* h, float* window_out_host, float* mel
 int b200fe_plan(b200fe_handle* h, const int64_t* lengths_host, int batch,
                 int64_t* n_frames_out, int64_t* n_rows_out, int64_t* max_rows_out, size_t* workspace_bytes);
 
+/* rows_cap value that selects the ROWS-PACKED output of b200fe_forward / b200fe_forward_pcm16: feats_dev is
+ * [sum_u n_rows[u], output_dim] and utterance u starts at row sum_{v<u} n_rows[v] (b200fe_plan gives n_rows); no padding
+ * rows exist, so none are written (133 MB of zeros per call for BASELINE configs[1]).  For consumers that batch by
+ * length themselves; the reference's own layout (pad_sequence, VF:163-166) is rows_cap >= max n_rows. */
+#define B200FE_ROWS_PACKED (-1)
+
 /* Replaces WavFrontend.forward (VF:128-168): fbank (TA:514-645) -> apply_lfr (VF:40-60) -> apply_cmvn (VF:23-37)
  * -> pad_sequence, for a whole batch in one pass.
  *   wave_dev      float32 PCM in [-1,1] (or already upscaled when upscale_samples=0)

@@ -911,7 +911,7 @@ def test_bench_batch_every_valid_row_against_the_reference(cmvn):
     sh, sc = cm[0].astype(np.float64), cm[1].astype(np.float64)
     use_ta = ref.have_torchaudio()
     rfe = ref.make_reference_frontend(cm, prefer_vllm=False, **bench.CONF) if use_ta else None
-    worst = 0.0
+    worst, deep_n, deep_got, deep_ref = 0.0, 0, 0.0, 0.0
     kw = dict(num_mel_bins=80, frame_length=25.0, frame_shift=10.0, dither=0.0, energy_floor=0.0, window_type="hamming",
               sample_frequency=16000.0)
     for u0 in range(0, 256, 16):
@@ -931,8 +931,14 @@ def test_bench_batch_every_valid_row_against_the_reference(cmvn):
             f64 = kf.fbank(waves[u].astype(np.float64) * 32768.0, dtype=np.float64, **kw)
             l64 = wf._lfr_keep_dtype(f64, 7, 6).reshape(n, 7, 80)
             assert_logmel_close(lg, lr, ref64=l64)
-            worst = max(worst, float(np.abs(lg - lr).max()))
-    print("bench batch: worst |log-mel - reference| over all 412 k frames", worst)
+            well = (lr.max(axis=-1, keepdims=True) - lr) <= 12.0
+            worst = max(worst, float(np.abs(lg - lr)[well].max()))
+            if (~well).any():
+                deep_n += int((~well).sum())
+                deep_got = max(deep_got, float(np.abs(lg - l64)[~well].max()))
+                deep_ref = max(deep_ref, float(np.abs(lr - l64)[~well].max()))
+    print(f"bench batch, 412 k frames: worst |log-mel - reference| over bins within 12 nepers of their frame's peak {worst:.2e}; "
+          f"{deep_n} deeper bins: worst vs float64 {deep_got:.2e} (the float32 reference itself: {deep_ref:.2e})")
 
 
 @pytest.mark.parametrize("chunk", [9600, 6400, 3840, 960, 300])
@@ -1238,3 +1244,24 @@ def test_kws_sliding_window_through_the_charctc_preset():
             n = int(rl[k])
             assert_logmel_close(feats[k, :n].cpu().numpy().reshape(n, 5, 80), ref[k, :n].reshape(n, 5, 80))
             assert not feats[k, n:].any()
+
+
+def test_rows_packed_output_equals_the_padded_output(cmvn):
+    """forward_packed(..., pad=False): [sum of rows, D] + row offsets instead of the zero-padded [B, max rows, D]
+    (B200FE_ROWS_PACKED in the C ABI).  Same rows, bit for bit, including an utterance shorter than one frame; options the
+    warp kernel does not cover refuse the layout."""
+    fe = make_fe(cmvn)
+    lens = np.array([4001, 16003, 399, 7777, 480000, 401, 1601], dtype=np.int64)
+    waves = [synth.uniform_pcm(33, i, int(n)) for i, n in enumerate(lens)]
+    offs, total = synth.packed_offsets(lens, align=4)
+    flat = torch.zeros(int(total) + 8)
+    for o, w in zip(offs, waves):
+        flat[o:o + len(w)] = torch.from_numpy(w)
+    padded, pl = fe.forward_packed(flat.to(DEV), offs, lens)
+    rows, rl, ro = fe.forward_packed(flat.to(DEV), offs, lens, pad=False)
+    assert torch.equal(rl, pl) and ro.dtype == torch.int64 and ro.device.type == "cpu"
+    assert rows.shape == (int(pl.sum()), 560) and int(ro[-1]) == rows.shape[0]
+    for i in range(len(lens)):
+        assert torch.equal(rows[int(ro[i]):int(ro[i + 1])], padded[i, :int(pl[i])]), i
+    with pytest.raises(RuntimeError, match="rows-packed"):
+        fe.forward_packed(flat.to(DEV), offs, lens, pad=False, stats=torch.zeros(1121, dtype=torch.float64, device=DEV))

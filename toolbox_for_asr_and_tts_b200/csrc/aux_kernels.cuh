@@ -63,6 +63,7 @@ struct ShortDesc {
   int n_frames;
   int n_rows;
   int mel_off;      // offset (floats) of this nfft's dense [n_mels, nfft/2] bank inside short_mel
+  int row_begin;    // first row of the utterance in a rows-packed output
 };
 
 __global__ void __launch_bounds__(256)
@@ -77,7 +78,7 @@ short_utt_kernel(const float* wave, const ShortDesc* descs, const float* short_m
   const int tid = threadIdx.x;
   const int W = sd.win, N = sd.nfft, D = lfr_m * M, left = (lfr_m - 1) / 2;
   const float* x = wave + sd.wave_off;
-  float* out = feats + (long long)sd.utt * rows_cap * D;
+  float* out = feats + (rows_cap >= 0 ? (long long)sd.utt * rows_cap : (long long)sd.row_begin) * D;
   // n_frames is 1 unless frame_shift is tiny; LFR rows are emitted per frame window in order, recomputing frames.
   for (int r = 0; r < sd.n_rows; ++r) {
     for (int jj = 0; jj < lfr_m; ++jj) {
@@ -192,7 +193,7 @@ __device__ __forceinline__ void build_quad(const UttDesc* utts, int batch, int q
   d.f0 = 4 * (q - ud.quad_begin);
   const int nF = min(4, ud.n_frames - d.f0);
   d.g0 = ud.wave_off + (long long)d.f0 * S;
-  d.pad = 0;
+  d.row_begin = ud.row_begin;
   int slow = 0;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {

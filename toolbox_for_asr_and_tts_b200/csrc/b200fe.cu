@@ -298,7 +298,7 @@ int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, 
     d.n_samples = (int)n;
     d.tile_begin = tile;
     d.quad_begin = quad;
-    d.reserved = 0;
+    d.row_begin = (int)pl.total_rows;
     if (n >= h->L) {
       d.n_frames = frame_count(n, h->L, h->S);
       d.n_rows = ceil_div(d.n_frames, h->cfg.lfr_n);
@@ -318,6 +318,7 @@ int make_plan(b200fe_handle* h, const int64_t* lengths, const int64_t* offsets, 
       s.n_frames = frame_count(n, win, h->S);
       s.n_rows = ceil_div(s.n_frames, h->cfg.lfr_n);
       s.mel_off = 0;
+      s.row_begin = (int)pl.total_rows;
       pl.shorts.push_back(s);
       d.n_frames = 0;          // the tile kernel skips it (no tiles); rows come from the short path
       d.n_rows = s.n_rows;
@@ -402,7 +403,8 @@ int launch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cu
   const size_t smem = warp_smem_bytes();
 #define LAUNCHW(DI)                                                                                   \
   do {                                                                                                \
-    auto k = fbank_warp_kernel<NROWS, EXACT, DI, MELS, SR, SampleT>;                                             \
+    auto k = p.rows_cap < 0 ? fbank_warp_kernel<NROWS, EXACT, DI, MELS, SR, SampleT, true>                      \
+                            : fbank_warp_kernel<NROWS, EXACT, DI, MELS, SR, SampleT, false>;                     \
     CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     cudaLaunchConfig_t lc = {};                                                                       \
     lc.gridDim = dim3(grid); lc.blockDim = dim3(kCtaThreads); lc.dynamicSmemBytes = smem; lc.stream = st; \
@@ -700,7 +702,9 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   int rc = make_plan(h, lengths_host, offsets_host, row_stride, batch, pl);
   if (rc) return rc;
   if (workspace_bytes < workspace_need(batch, pl.n_tiles, pl.n_quads, (int)pl.shorts.size())) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
-  if (pl.max_rows > rows_cap) return fail(h, B200FE_E_INVALID, "rows_cap smaller than the longest utterance's row count");
+  const bool rows_packed = rows_cap == B200FE_ROWS_PACKED;   // feats_dev = [sum of rows, D], utterance u at row_begin[u]
+  if (!rows_packed && pl.max_rows > rows_cap) return fail(h, B200FE_E_INVALID, "rows_cap smaller than the longest utterance's row count");
+  if (pl.total_rows > 0x7fffffffll) return fail(h, B200FE_E_INVALID, "more than 2^31 output rows in one call");
   for (int u = 0; u < batch; ++u) {
     const long long end = pl.utts[u].wave_off + lengths_host[u];
     if (pl.utts[u].wave_off < 0 || end > wave_total) return fail(h, B200FE_E_INVALID, "utterance outside the wave buffer");
@@ -712,11 +716,14 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   QuadDesc* d_quads = reinterpret_cast<QuadDesc*>(d_tiles);   // same region: a launch uses one of the two lists
   // the warp kernel does everything except the CMVN statistics (which need the row-major tile pass)
   const bool use_warp = stats_dev == nullptr && warp_kernel_fits(h->L, h->S, pcm16) && (!h->force_tile || pcm16) &&
-                        pl.max_rows * (long long)h->D < (1ll << kTargetOffBits) - 1;
+                        pl.max_rows * (long long)h->D < (1ll << kTargetOffBits) - 1;   // target offsets are relative to the utterance
   // utterance table: inside the prep launch's parameters when it fits (warp path, no short utterances, which read
   // d_utts-independent descriptors of their own), else one pinned-buffer upload
   const bool utts_in_params = use_warp && pl.n_quads > 0 && batch <= kParamUtts;
   if (!utts_in_params && (rc = upload(h, pl.utts.data(), (size_t)batch * sizeof(UttDesc), d_utts, st))) return rc;
+  if (rows_packed && !(use_warp && pl.n_quads > 0))
+    return fail(h, B200FE_E_UNSUPPORTED, "the rows-packed output is written by the warp kernel only (no statistics pass, "
+                                         "frame shifts whose quad fits its buffer, at least one full frame in the batch)");
   if (pcm16 && !use_warp)
     return fail(h, B200FE_E_UNSUPPORTED, "int16 input is implemented in the warp kernel only (no statistics pass, "
                                          "frame shifts whose quad fits its buffer)");
@@ -726,7 +733,7 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   if (use_warp && pl.n_quads > 0) {
     // 1. one launch: quad list (+ work counter), feat_lens, and the padding rows unless the warp kernel writes them
     const int qb = (pl.n_quads + 255) / 256, ub = (batch + 255) / 256;
-    const int pad_bx = B200FE_PAD_MODE == 1 ? 0 : gx;
+    const int pad_bx = (B200FE_PAD_MODE == 1 || rows_packed) ? 0 : gx;
     const int grid0 = qb + ub + pad_bx * batch;
     if (utts_in_params) {
       static_assert(sizeof(UttTable) <= 16384, "kernel parameters");

@@ -63,7 +63,7 @@ struct UttDesc {          // built on the host by b200fe_plan/forward
   int n_rows;             // T_lfr  (VF:43)
   int tile_begin;         // index of the utterance's first tile in the launch-wide tile list
   int quad_begin;         // index of the utterance's first quad in the launch-wide quad list (fbank_warp.cuh)
-  int reserved;
+  int row_begin;          // rows of all earlier utterances: where this one starts in a rows-packed output
 };
 
 // One tile of the launch-wide work list, fully resolved by build_tiles_kernel so that the fused kernel never chases a

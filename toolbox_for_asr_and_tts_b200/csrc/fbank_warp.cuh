@@ -55,7 +55,7 @@ struct __align__(16) QuadDesc {
   int f0;             // first frame of the quad
   int T;              // frames of the utterance
   int rows;           // LFR rows of the utterance
-  int pad;
+  int row_begin;      // first row of the utterance in a rows-packed output (QuadParams::rows_cap < 0)
   unsigned tgt[8];    // tgt[2 t + k]: where frame f0 + t goes: (jj << 27) | (row * D + jj * M), or kNoTarget
 };
 
@@ -65,7 +65,7 @@ struct QuadParams {
   const QuadDesc* quads;
   int n_quads;
   int* next_quad;         // work counter (zeroed by build_quads_kernel): quads beyond the first wave are claimed dynamically
-  float* feats;           // [batch, rows_cap, out_dim]
+  float* feats;           // [batch, rows_cap, out_dim], or rows-packed [sum of rows, out_dim] when rows_cap < 0
   long long rows_cap;
   int frame_len, frame_shift, n_mels, lfr_m, lfr_n;
   float preemph;
@@ -272,7 +272,9 @@ __device__ __forceinline__ void quad_fill_generic<short>(const void* wave_any, l
 
 // SR: frame shift in 16-sample rows when it is a whole number of rows and known at compile time (10 for 400/160):
 // the two frames of a pair then share their overlapping sample loads.  0 = generic.
-template <int NROWS, bool EXACT, bool DITHER, class MELS, int SR, class SampleT>
+// PACKED: rows-packed output (utterance u starts at row QuadDesc::row_begin) instead of the padded [B, rows_cap, D]; a
+// separate instantiation so that the padded kernel's address arithmetic stays as it is.
+template <int NROWS, bool EXACT, bool DITHER, class MELS, int SR, class SampleT, bool PACKED = false>
 __global__ void __launch_bounds__(kCtaThreads, B200FE_WARP_CTAS)
 fbank_warp_kernel(const QuadParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -432,7 +434,7 @@ fbank_warp_kernel(const QuadParams p) {
     //      (VF:34-35, VF:40-60) - as 32-bit stores that a warp coalesces into one or two 128-byte lines.  No staging tile,
     //      no regrouping into 128-bit pieces, the CMVN entries are per-lane scalar loads.
     {
-      float* out_u = p.feats + (long long)utt * p.rows_cap * D;
+      float* out_u = p.feats + (PACKED ? (long long)hd1.w : (long long)utt * p.rows_cap) * D;
       const float* cm = p.cmvn;
       const unsigned tgt[8] = {tg0.x, tg0.y, tg0.z, tg0.w, tg1.x, tg1.y, tg1.z, tg1.w};
       constexpr unsigned kOffMask = (1u << kTargetOffBits) - 1;
@@ -491,7 +493,7 @@ fbank_warp_kernel(const QuadParams p) {
     //      One divergent region for the lanes that carry a piece; inside it every branch is warp-uniform.
     if (act) {
       const int f0 = hd1.x, T = hd1.y, rows = hd1.z;
-      float* out_l = p.feats + (long long)utt * p.rows_cap * D + 4 * lane;
+      float* out_l = p.feats + (PACKED ? (long long)hd1.w : (long long)utt * p.rows_cap) * D + 4 * lane;
       const float* cm_l = p.cmvn ? p.cmvn + 4 * lane : nullptr;
       const float4* lm4 = reinterpret_cast<const float4*>(lm_s) + lane;
       const unsigned tgt[8] = {tg0.x, tg0.y, tg0.z, tg0.w, tg1.x, tg1.y, tg1.z, tg1.w};
@@ -534,7 +536,7 @@ fbank_warp_kernel(const QuadParams p) {
     // ---- LFR + CMVN: each frame's row of n_mels goes, as 128-bit pieces, to the (row, slot) pairs of its descriptor
     {
       const int f0 = hd1.x, T = hd1.y, rows = hd1.z;
-      float* out_l = p.feats + (long long)utt * p.rows_cap * D + 4 * lane;
+      float* out_l = p.feats + (PACKED ? (long long)hd1.w : (long long)utt * p.rows_cap) * D + 4 * lane;
       const unsigned tgt[8] = {tg0.x, tg0.y, tg0.z, tg0.w, tg1.x, tg1.y, tg1.z, tg1.w};
       const float* cm_l = p.cmvn ? p.cmvn + 4 * lane : nullptr;
       const float4* lm4 = reinterpret_cast<const float4*>(lm_s) + lane;

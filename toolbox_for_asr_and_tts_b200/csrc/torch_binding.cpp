@@ -105,11 +105,15 @@ std::tuple<at::Tensor, at::Tensor> fe_forward(int64_t h, const at::Tensor& wave,
   }
   int64_t max_rows = 0;
   size_t ws = 0;
-  check(b200fe_plan(H(h), len.data_ptr<int64_t>(), b, nullptr, nullptr, &max_rows, &ws), H(h), "b200fe_plan");
-  if (rows_cap <= 0) rows_cap = max_rows;
+  std::vector<int64_t> n_rows(b);
+  check(b200fe_plan(H(h), len.data_ptr<int64_t>(), b, nullptr, n_rows.data(), &max_rows, &ws), H(h), "b200fe_plan");
+  const bool rows_packed = rows_cap == B200FE_ROWS_PACKED;     // [sum of rows, D] instead of the padded [B, rows_cap, D]
+  if (!rows_packed && rows_cap <= 0) rows_cap = max_rows;
   const int64_t d = b200fe_output_dim(H(h));
   auto opts = w.options().dtype(at::kFloat);
-  auto feats = at::empty({b, rows_cap, d}, opts);
+  int64_t total_rows = 0;
+  for (int u = 0; u < b; ++u) total_rows += n_rows[u];
+  auto feats = rows_packed ? at::empty({total_rows, d}, opts) : at::empty({b, rows_cap, d}, opts);
   auto lens = at::empty({b}, opts.dtype(at::kLong));
   auto work = at::empty({(int64_t)(ws ? ws : 256)}, opts.dtype(at::kByte));
   double* st = nullptr;

@@ -187,15 +187,24 @@ class WavFrontend(nn.Module):
         return x if x.dtype == torch.int16 else x.to(torch.float32)
 
     def forward_packed(self, wave: torch.Tensor, offsets, lengths, stats: Optional[torch.Tensor] = None,
-                       rows_cap: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                       rows_cap: int = 0, pad: bool = True):
         """Length-packed batch: `wave` is one flat CUDA buffer, utterance i occupies wave[offsets[i] : +lengths[i]].
-        Same outputs as `forward`.  `stats` (CUDA float64 [2*D+1]) accumulates global CMVN statistics of the
-        un-normalised LFR features."""
+        Same outputs as `forward` (feature lengths on the device).  `stats` (CUDA float64 [2*D+1]) accumulates global
+        CMVN statistics of the un-normalised LFR features.
+        pad=False: ROWS-PACKED output for consumers that batch by length themselves - returns (feats [sum of rows, D],
+        feature lengths on the device, row_offsets int64 [B+1] on the CPU); utterance i is feats[row_offsets[i] :
+        row_offsets[i+1]].  No padding rows exist, so none are written."""
         self._check_cuda(wave, "wave")
         h = self._handle(lfr=True, cmvn=True, device=wave.device)
         self._calls += 1
-        return h.ops.forward(h.h, self._pcm(wave), _as_length_tensor(offsets), _as_length_tensor(lengths), int(rows_cap),
-                             stats, int(self.dither_seed + self._calls))
+        lens = _as_length_tensor(lengths)
+        if pad:
+            return h.ops.forward(h.h, self._pcm(wave), _as_length_tensor(offsets), lens, int(rows_cap), stats,
+                                 int(self.dither_seed + self._calls))
+        feats, feat_lens = h.ops.forward(h.h, self._pcm(wave), _as_length_tensor(offsets), lens, -1, stats,
+                                         int(self.dither_seed + self._calls))
+        rows = self._host_lengths(h, lens)
+        return feats, feat_lens, torch.cat((torch.zeros(1, dtype=torch.int64), torch.cumsum(rows, 0)))
 
     def forward_fbank(self, input: torch.Tensor, input_lengths) -> Tuple[torch.Tensor, torch.Tensor]:
         """VF:170-196: Kaldi fbank only (always upscaled by 2^15 upstream), zero-padded, lengths int64."""
