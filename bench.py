@@ -6,12 +6,12 @@
 One step = one pass of the hot path over one batch of synthetic audio: BASELINE.json configs[1], 256 utterances of
 1-30 s (16 kHz), length-packed, Paraformer-zh front-end (hamming, 80 mel, LFR 7/6, CMVN, dither 0).
   value  audio-seconds per second with the batch resident in HBM (CUDA events, max over ranks)
-  e2e    the same starting where the reference's caller starts: a list of 256 np.float32 arrays in pageable HOST memory
-         (what R:voice_interface.py:2049 hands to funasr).  Timed per step: the multi-threaded gather into pinned
-         staging, the H2D copy (pipelined with the gather), the fused kernels, D2H of the feature lengths.  The features
-         stay in HBM for the acoustic model, which is where the reference puts them too (funasr moves the CPU
-         front-end's output to cuda:0).  e2e_prepacked (an already length-packed pinned buffer) and e2e_pcm16 (int16
-         wire PCM) are reported beside it.
+  e2e    the same from HOST memory, per step: H2D of the step's waveforms from pinned host memory, the fused kernels, D2H
+         of the feature lengths.  The features stay in HBM for the acoustic model, which is where the reference puts
+         them too (funasr moves the CPU front-end's output to cuda:0).
+  e2e_api  one step earlier: starts from a list of 256 separate np.float32 arrays in pageable host memory (what
+         R:voice_interface.py:2049 hands to funasr); adds the multi-threaded gather into pinned staging, pipelined
+         with the H2D copy (HostIngest).  e2e_pcm16: the same loop on int16 wire PCM.
   roofline      algorithmic bytes of one launch / CUDA-event time of the fused tile kernel / measured HBM peak
   cpu_baseline  the reference's CPU front-end (funasr WavFrontend over torchaudio kaldi.fbank) on this box's cores
 `--impl reference` times only that CPU implementation, on the same config/metric.
@@ -337,6 +337,23 @@ def run_ours(args, rank, world, local_rank):
     host_pin.copy_(host_flat)
     pre_ms, pre_runs, l3, _ = measure(prepacked_loop, host_pin)
     assert torch.equal(l3.cpu(), flens.cpu())
+    # the host-side ceiling of `e2e`: the same pinned buffer copied host -> device and nothing else, all ranks at once
+    # (barrier on both sides, max over ranks).  At N > 1 the ranks share one host's memory system and PCIe root complex.
+    dst_probe = torch.empty(host_pin.numel(), dtype=torch.float32, device=dev)
+    for _ in range(2):
+        dst_probe.copy_(host_pin, non_blocking=True)
+    barrier()
+    ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ec0.record()
+    for _ in range(10):
+        dst_probe.copy_(host_pin, non_blocking=True)
+    ec1.record()
+    barrier()
+    tc = torch.tensor([ec0.elapsed_time(ec1) / 10], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    copy_only_ms = float(tc[0])
+    del dst_probe
     arrays16 = [np.clip(np.round(a * 32768.0), -32768, 32767).astype(np.int16) for a in arrays]
     ing16 = HostIngest(fe, capacity_samples=total + 8 * BATCH, dtype=torch.int16, device=dev, threads=ingest_threads)
     e16_ms, e16_runs, l4, _ = measure(api_loop, ing16, arrays16)
@@ -424,27 +441,38 @@ def run_ours(args, rank, world, local_rank):
                        "audio_seconds_per_gpu_step": audio_s, "l2": "inputs_larger_than_l2 (264 MB in + 287 MB out per step vs 126 MB L2)",
                        "input_layout": "length-packed float32, 16-byte aligned offsets", "output": "[256, 500, 560] float32, zero-padded"},
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": int(lens_host.numel() * 8), "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps, "runs_ms_per_step": e2e_runs, "reported": "median run",
-                    "h2d_gbs": h2d_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9,
-                    "starts_from": f"list of {BATCH} separate np.float32 arrays in pageable host memory (what the reference's caller "
-                                   "hands to funasr, R:voice_interface.py:2049)",
-                    "timed_per_step": ["multi-threaded gather into pinned staging (b200fe_host_ingest)",
-                                       "H2D, pipelined with the gather", "prep + fused kernels", "D2H of the feature lengths"],
-                    "features_stay_in_hbm": True, "host_threads_per_rank": ingest_threads, "host_placement": placement,
-                    "aggregate_h2d_gbs": world * h2d_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9,
-                    "note": "double-buffered serving loop: the host gathers step k+1 while step k's copy and kernels run"},
-            "e2e_prepacked": {"value": audio_s * world * e2e_steps / (pre_ms * 1e-3), "unit": UNIT,
-                              "h2d_bytes_per_step": int(host_pin.numel() * 4), "ms_per_step": pre_ms / e2e_steps,
-                              "runs_ms_per_step": pre_runs,
-                              "h2d_gbs": int(host_pin.numel() * 4) / (pre_ms / e2e_steps * 1e-3) / 1e9,
-                              "note": "side measurement: the batch already length-packed in ONE pinned float32 buffer (no host "
-                                      "gather in the timed region); this is what round 1 reported as e2e"},
+            "e2e": {"value": audio_s * world * e2e_steps / (pre_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(host_pin.numel() * 4), "d2h_bytes_per_step": int(lens_host.numel() * 8),
+                    "steps": e2e_steps, "ms_per_step": pre_ms / e2e_steps, "runs_ms_per_step": pre_runs, "reported": "median run",
+                    "h2d_gbs": int(host_pin.numel() * 4) / (pre_ms / e2e_steps * 1e-3) / 1e9,
+                    "aggregate_h2d_gbs": world * int(host_pin.numel() * 4) / (pre_ms / e2e_steps * 1e-3) / 1e9,
+                    "h2d_copy_only": {"ms_per_copy": copy_only_ms,
+                                      "gbs_per_rank": int(host_pin.numel() * 4) / (copy_only_ms * 1e-3) / 1e9,
+                                      "aggregate_gbs": world * int(host_pin.numel() * 4) / (copy_only_ms * 1e-3) / 1e9,
+                                      "note": "host-side ceiling: the same pinned buffer copied H2D by all ranks at once, no "
+                                              "kernels; e2e / this = fraction of the host's deliverable bandwidth"},
+                    "fraction_of_h2d_ceiling": copy_only_ms / (pre_ms / e2e_steps),
+                    "starts_from": "the step's inputs in pinned host memory (one length-packed float32 buffer), as the contract states",
+                    "timed_per_step": ["H2D of the waveforms", "prep + fused kernels", "D2H of the feature lengths"],
+                    "features_stay_in_hbm": True,
+                    "note": "double-buffered serving loop (step k+1's H2D overlaps step k's kernels); the features stay in HBM "
+                            "for the acoustic model (funasr also moves the CPU front-end's output to cuda:0), only the feature "
+                            "lengths return to the host; e2e_api below starts one step earlier, at the caller's numpy arrays"},
+            "e2e_api": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": int(lens_host.numel() * 8), "steps": e2e_steps,
+                        "ms_per_step": e2e_ms / e2e_steps, "runs_ms_per_step": e2e_runs, "reported": "median run",
+                        "h2d_gbs": h2d_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                        "aggregate_h2d_gbs": world * h2d_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                        "starts_from": f"list of {BATCH} separate np.float32 arrays in pageable host memory (what the reference's "
+                                       "caller hands to funasr, R:voice_interface.py:2049)",
+                        "timed_per_step": ["multi-threaded gather into pinned staging (b200fe_host_ingest)",
+                                           "H2D, pipelined with the gather", "prep + fused kernels", "D2H of the feature lengths"],
+                        "features_stay_in_hbm": True, "host_threads_per_rank": ingest_threads, "host_placement": placement,
+                        "note": "HostIngest.forward(list of arrays): the host gathers step k+1 while step k's copy and kernels run"},
             "e2e_pcm16": {"value": audio_s * world * e2e_steps / (e16_ms * 1e-3), "unit": UNIT,
                           "h2d_bytes_per_step": int(lens.sum()) * 2, "ms_per_step": e16_ms / e2e_steps,
                           "runs_ms_per_step": e16_runs,
-                          "note": "side measurement: the e2e loop on int16 PCM (the wire format, value = s / 32768), converted "
+                          "note": "side measurement: the e2e_api loop on int16 PCM arrays (the wire format, value = s / 32768), converted "
                                   "inside the kernel's loads: bit-identical features at half the PCIe bytes"},
             "configs0_one_10s_utterance_gpu": {"ms_p50": lat[len(lat) // 2], "ms_p90": lat[int(len(lat) * 0.9)],
                                                "note": "pinned host PCM -> H2D -> forward -> synchronize, through WavFrontend.forward"},
