@@ -15,7 +15,10 @@
  *     except b200fe_plan / b200fe_create / b200fe_destroy which are host-side;
  *   - return value: 0 = OK, negative = error (B200FE_E_*); b200fe_last_error(handle) gives the text;
  *   - no exceptions cross the ABI; there is NO CPU fallback: without a CUDA device create() fails;
- *   - one handle may be used from several host threads only with distinct streams AND distinct workspaces.
+ *   - one handle may be used from several host threads only with distinct streams AND distinct workspaces;
+ *   - batches of more than 65535 utterances per call are taken by b200fe_forward / _pcm16 on the warp-kernel path
+ *     only; the statistics pass, b200fe_lfr_cmvn, b200fe_audio_stats, b200fe_tts_forward and
+ *     b200fe_subtract_column_mean put the batch index in grid.y and refuse (or fail to launch) beyond that.
  */
 #ifndef B200FE_H_
 #define B200FE_H_

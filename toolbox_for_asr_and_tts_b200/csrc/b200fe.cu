@@ -66,6 +66,7 @@ struct b200fe_handle {
   int profile_every = 0, profile_tick = 0;   // b200fe_profile_enable: time every n-th fused-kernel launch
   bool force_tile = false;           // b200fe_select_kernel(h, 1): keep the tile kernel (A/B measurements, tests)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<cudaEvent_t> event_pool;   // recycled by b200fe_profile_collect
   UttTable utt_tab;                  // staging for the prep launch's by-value utterance table (under mu)
   mutable std::string err;
 };
@@ -366,19 +367,46 @@ int upload(b200fe_handle* h, const void* src, size_t bytes, void* dst, cudaStrea
   return 0;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is set once per (kernel, device) and grown when a larger size is asked for
+cudaError_t allow_dynamic_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = done[{func, dev}];
+  if (have >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
+}
+
+// event pairs of the timed launches come from a per-handle pool (no cudaEventCreate on the launch path after warm-up)
+int timed_events(b200fe_handle* h, cudaEvent_t& e0, cudaEvent_t& e1) {
+  if (h->event_pool.size() < 2) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    CUDA_TRY(h, cudaEventCreate(&a));
+    CUDA_TRY(h, cudaEventCreate(&b));
+    h->event_pool.push_back(a);
+    h->event_pool.push_back(b);
+  }
+  e1 = h->event_pool.back(); h->event_pool.pop_back();
+  e0 = h->event_pool.back(); h->event_pool.pop_back();
+  return 0;
+}
+
 template <int NROWS, bool EXACT, class MELS>
 int launch_tile(b200fe_handle* h, const TileParams& p, int grid, bool dither, bool stats, cudaStream_t st) {
 #define LAUNCH(DI, STT)                                                                                         \
   do {                                                                                                          \
     auto k = fbank_lfr_cmvn_tile_kernel<NROWS, EXACT, DI, STT, MELS>;                                                 \
-    CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));      \
+    CUDA_TRY(h, allow_dynamic_smem((const void*)k, h->smem_bytes));                                             \
     k<<<grid, kCtaThreads, h->smem_bytes, st>>>(p);                                                             \
   } while (0)
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool timed = h->profile_every > 0 && (h->profile_tick++ % h->profile_every) == 0;
   if (timed) {
-    CUDA_TRY(h, cudaEventCreate(&e0));
-    CUDA_TRY(h, cudaEventCreate(&e1));
+    if (int rc_ev = timed_events(h, e0, e1)) return rc_ev;
     CUDA_TRY(h, cudaEventRecord(e0, st));
   }
 #ifdef B200FE_BENCH_ONLY
@@ -405,7 +433,7 @@ int launch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cu
   do {                                                                                                \
     auto k = p.rows_cap < 0 ? fbank_warp_kernel<NROWS, EXACT, DI, MELS, SR, SampleT, true>                      \
                             : fbank_warp_kernel<NROWS, EXACT, DI, MELS, SR, SampleT, false>;                     \
-    CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    CUDA_TRY(h, allow_dynamic_smem((const void*)k, smem));                                            \
     cudaLaunchConfig_t lc = {};                                                                       \
     lc.gridDim = dim3(grid); lc.blockDim = dim3(kCtaThreads); lc.dynamicSmemBytes = smem; lc.stream = st; \
     cudaLaunchAttribute at[1];                                                                        \
@@ -417,8 +445,7 @@ int launch_warp(b200fe_handle* h, const QuadParams& p, int grid, bool dither, cu
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool timed = h->profile_every > 0 && (h->profile_tick++ % h->profile_every) == 0;
   if (timed) {
-    CUDA_TRY(h, cudaEventCreate(&e0));
-    CUDA_TRY(h, cudaEventCreate(&e1));
+    if (int rc_ev = timed_events(h, e0, e1)) return rc_ev;
     CUDA_TRY(h, cudaEventRecord(e0, st));
   }
 #ifdef B200FE_BENCH_ONLY   // experiment builds (tools/build_variant.py): only what bench.py launches is instantiated
@@ -589,6 +616,8 @@ void b200fe_destroy(b200fe_handle* h) {
   if (!h) return;
   cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo);
   cudaFree(h->d_cmvn); cudaFree(h->d_short_mel);
+  for (auto& pr : h->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto& e : h->event_pool) cudaEventDestroy(e);
   for (auto& s : h->slots) {
     if (s.ev) { cudaEventSynchronize(s.ev); cudaEventDestroy(s.ev); }
     if (s.ptr) cudaFreeHost(s.ptr);
@@ -636,8 +665,8 @@ int b200fe_profile_collect(b200fe_handle* h, double* total_ms, int64_t* n_launch
     float ms = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, pr.first, pr.second));
     tot += ms;
-    cudaEventDestroy(pr.first);
-    cudaEventDestroy(pr.second);
+    h->event_pool.push_back(pr.first);
+    h->event_pool.push_back(pr.second);
   }
   if (total_ms) *total_ms = tot;
   if (n_launches) *n_launches = (int64_t)h->prof_events.size();
@@ -724,6 +753,9 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
   if (rows_packed && !(use_warp && pl.n_quads > 0))
     return fail(h, B200FE_E_UNSUPPORTED, "the rows-packed output is written by the warp kernel only (no statistics pass, "
                                          "frame shifts whose quad fits its buffer, at least one full frame in the batch)");
+  if (!(use_warp && pl.n_quads > 0) && batch > 65535)
+    return fail(h, B200FE_E_UNSUPPORTED, "more than 65535 utterances per call are implemented in the warp kernel only "
+                                         "(the tile / statistics path puts the batch in grid.y)");
   if (pcm16 && !use_warp)
     return fail(h, B200FE_E_UNSUPPORTED, "int16 input is implemented in the warp kernel only (no statistics pass, "
                                          "frame shifts whose quad fits its buffer)");
@@ -869,6 +901,7 @@ int b200fe_lfr_cmvn(b200fe_handle* h, const float* fbank_dev, int64_t frames_cap
   if (batch == 0) return B200FE_OK;
   if (!fbank_dev || !n_frames_host || !feats_dev || !workspace_dev) return fail(h, B200FE_E_INVALID, "null argument");
   if (workspace_bytes < workspace_need(batch)) return fail(h, B200FE_E_WORKSPACE, "workspace too small");
+  if (batch > 65535) return fail(h, B200FE_E_UNSUPPORTED, "at most 65535 utterances per b200fe_lfr_cmvn call");
   cudaStream_t st = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lock(h->mu);
   std::vector<UttDesc> utts(batch);

@@ -35,7 +35,7 @@ int launch_stream(b200fe_handle* h, const StreamParams& p, size_t smem, bool dit
 #define LAUNCHS(DI, PQ, W)                                                                            \
   do {                                                                                                \
     auto k = stream_push_kernel<NROWS, EXACT, DI, MELS, PQ, W>;                                       \
-    CUDA_TRY(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));   \
+    CUDA_TRY(h, allow_dynamic_smem((const void*)k, smem_w));                                          \
     k<<<p.n, 32 * W, smem_w, st>>>(p);                                                                \
   } while (0)
   const bool per_quad = warp_kernel_fits(h->L, h->S);   // every warp fetches its own quads (3 CTAs per SM)
@@ -86,6 +86,7 @@ int b200fe_stream_reset(b200fe_handle* h, void* state_dev, int n_streams, int ma
   int rc = stream_layout(h, n_streams, max_chunk_samples, lay, nf_max, e_cap, smem);
   if (rc) return rc;
   if (!state_dev) return fail(h, B200FE_E_INVALID, "null state");
+  std::lock_guard<std::mutex> lock(h->mu);     // launches / err are shared with the other entry points
   const int cnt = stream_ids_dev_or_null ? n : n_streams;
   if (cnt <= 0) return B200FE_OK;
   stream_reset_kernel<<<(cnt + 255) / 256, 256, 0, (cudaStream_t)stream>>>(state_dev, lay, stream_ids_dev_or_null, cnt);
@@ -110,6 +111,7 @@ int b200fe_stream_push_stats(b200fe_handle* h, void* state_dev, int n_streams, i
   int rc = stream_layout(h, n_streams, max_chunk_samples, lay, nf_max, e_cap, smem);
   if (rc) return rc;
   if (n == 0) return B200FE_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
   if (!state_dev || !chunks_dev || !chunk_lens_dev || !stream_ids_dev || !feats_dev || !rows_out_dev || n < 0)
     return fail(h, B200FE_E_INVALID, "null argument");
   if (smem > 227 * 1024) return fail(h, B200FE_E_UNSUPPORTED, "max_chunk_samples too large for one shared-memory tile");
