@@ -1,7 +1,6 @@
 // TTS log-mel entry points of the C ABI (included at the end of b200fe.cu).
 struct b200fe_tts {
   int sample_rate = 0, n_fft = 0, hop = 0, n_mels = 0;
-  float* d_window = nullptr;
   float2* d_twiddle = nullptr;
   float2* d_w1024 = nullptr;
   float2* d_mel_w = nullptr;
@@ -64,27 +63,30 @@ int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_m
   std::vector<float2> mw;
   std::vector<int> mlo;
   std::string why;
-  if (build_interval_table(bank, n_mels, n_fft / 2, n_fft / 2 + 1, 1.0f, mw, mlo, t->mel_rounds, t->mel_cnt, t->mel_base, why) != 0) {
+  if (build_interval_table(bank, n_mels, n_fft / 2, n_fft / 2 + 1, 1.0f, mw, mlo, t->mel_rounds, t->mel_cnt, t->mel_base, why, 16) != 0) {
     delete t;
     return failc(B200FE_E_UNSUPPORTED, why);
   }
   for (int m = 0; m < n_mels; ++m)
     if (bank[(size_t)m * (n_fft / 2 + 1) + n_fft / 2] != 0.f) { delete t; return failc(B200FE_E_UNSUPPORTED, "the Nyquist bin must not carry mel weight"); }
-  std::vector<float> win(n_fft);
-  for (int n = 0; n < n_fft; ++n) win[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / n_fft));   // periodic Hann
-  std::vector<float2> tw(kTwTable, make_float2(0.f, 0.f)), w1024(16);
-  for (int r = 0; r < kTwRows; ++r)
-    for (int n2 = 0; n2 < 16; ++n2) {
-      const int ph = (n2 * r) & 511;
-      tw[r * kXRow + n2] = make_float2((float)cos(2.0 * M_PI * ph / 512.0), (float)(-sin(2.0 * M_PI * ph / 512.0)));
+  // stage-2 twiddles + column-0 table of the packed 512-point real FFT (same tables as b200fe_create), W1024^col
+  std::vector<float2> tw(kTw2Total, make_float2(0.f, 0.f)), w1024(17);
+  for (int k1 = 1; k1 <= 16; ++k1)
+    for (int c = 0; c < 16; ++c) {
+      const int ph = (c * k1) % 512;
+      const double sc = (k1 == 8 || k1 == 16) ? 2.0 : 1.0;
+      tw[(k1 - 1) * kTwPitch + c] = make_float2((float)(sc * cos(2.0 * M_PI * ph / 512.0)), (float)(-sc * sin(2.0 * M_PI * ph / 512.0)));
     }
-  for (int jj = 0; jj < 16; ++jj) w1024[jj] = make_float2((float)cos(2.0 * M_PI * jj / 1024.0), (float)(-sin(2.0 * M_PI * jj / 1024.0)));
-  bool ok = cudaMalloc(&t->d_window, win.size() * 4) == cudaSuccess && cudaMalloc(&t->d_twiddle, tw.size() * 8) == cudaSuccess &&
-            cudaMalloc(&t->d_w1024, 16 * 8) == cudaSuccess && cudaMalloc(&t->d_mel_w, mw.size() * 8) == cudaSuccess &&
-            cudaMalloc(&t->d_mel_lo, mlo.size() * 4) == cudaSuccess;
-  ok = ok && cudaMemcpy(t->d_window, win.data(), win.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-       cudaMemcpy(t->d_twiddle, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
-       cudaMemcpy(t->d_w1024, w1024.data(), 16 * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+  for (int tt = 0; tt < 8; ++tt)
+    for (int c = 0; c < 8; ++c) {
+      const int ph = (c * tt) % 16;
+      tw[kTw2Table + tt * kC0Pitch + c] = make_float2((float)(2.0 * cos(2.0 * M_PI * ph / 16.0)), (float)(-2.0 * sin(2.0 * M_PI * ph / 16.0)));
+    }
+  for (int jj = 0; jj <= 16; ++jj) w1024[jj] = make_float2((float)cos(2.0 * M_PI * jj / 1024.0), (float)(-sin(2.0 * M_PI * jj / 1024.0)));
+  bool ok = cudaMalloc(&t->d_twiddle, tw.size() * 8) == cudaSuccess && cudaMalloc(&t->d_w1024, w1024.size() * 8) == cudaSuccess &&
+            cudaMalloc(&t->d_mel_w, mw.size() * 8) == cudaSuccess && cudaMalloc(&t->d_mel_lo, mlo.size() * 4) == cudaSuccess;
+  ok = ok && cudaMemcpy(t->d_twiddle, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(t->d_w1024, w1024.data(), w1024.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
        cudaMemcpy(t->d_mel_w, mw.data(), mw.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
        cudaMemcpy(t->d_mel_lo, mlo.data(), mlo.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { b200fe_tts_destroy(t); return failc(B200FE_E_CUDA, "device allocation failed"); }
@@ -94,7 +96,7 @@ int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_m
 
 void b200fe_tts_destroy(b200fe_tts* t) {
   if (!t) return;
-  cudaFree(t->d_window); cudaFree(t->d_twiddle); cudaFree(t->d_w1024); cudaFree(t->d_mel_w); cudaFree(t->d_mel_lo);
+  cudaFree(t->d_twiddle); cudaFree(t->d_w1024); cudaFree(t->d_mel_w); cudaFree(t->d_mel_lo);
   delete t;
 }
 
@@ -109,10 +111,10 @@ int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total,
   p.wave = wave_dev; p.wave_total = wave_total; p.offsets = (const long long*)offsets_dev; p.lengths = (const long long*)lengths_dev;
   p.batch = batch; p.hop = t->hop; p.n_mels = t->n_mels; p.mel = mel_dev; p.frames_cap = frames_cap;
   p.mel_lens = (long long*)mel_lens_dev; p.mag_eps = 1e-9f; p.log_floor = 1e-5f;
-  p.window = t->d_window; p.twiddle = t->d_twiddle; p.w1024 = t->d_w1024;
+  p.twiddle = t->d_twiddle; p.w1024 = t->d_w1024;
   p.mel_tab.w = t->d_mel_w; p.mel_tab.lo = t->d_mel_lo; p.mel_tab.rounds = t->mel_rounds;
   for (int r = 0; r < kMelRounds; ++r) { p.mel_tab.cnt[r] = t->mel_cnt[r]; p.mel_tab.base[r] = t->mel_base[r]; }
-  if (cudaFuncSetAttribute(tts_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem) != cudaSuccess) return B200FE_E_CUDA;
+  if (allow_dynamic_smem((const void*)tts_mel_kernel, t->smem) != cudaSuccess) return B200FE_E_CUDA;
   tts_pad_kernel<<<dim3(8, batch), 256, 0, st>>>((const long long*)lengths_dev, t->hop, t->n_mels, mel_dev, frames_cap);
   const int tiles = (int)((max_frames + kTtsFrames - 1) / kTtsFrames);
   if (tiles > 0) tts_mel_kernel<<<dim3(tiles, batch), kCtaThreads, t->smem, st>>>(p);

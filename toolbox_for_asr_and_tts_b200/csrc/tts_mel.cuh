@@ -3,23 +3,25 @@
 // log(clamp(., 1e-5)), output [B, n_mels, frames] (mel-major).  Definition frozen in oracle/tts_mel_np.py (the
 // reference has no audio->mel code: parity unpinned).
 //
-// One 16-thread group transforms ONE frame: the 1024 real samples are packed as 512 complex points
-// z[m] = x[2m] + i x[2m+1], sent through the same 512-point FFT core as the ASR front-end (fft512_columns), and the
-// even/odd spectra are recombined with the W1024 twiddles; because Z[k] and Z[512-k] sit in the same thread that step
-// is thread-local and yields bins k and 512-k at once.
+// Round 2: on the packed f32x2 real-FFT core of the ASR front-end.  A 1024-point real FFT is two 512-point real FFTs,
+// of the even and of the odd samples: X[k] = E[k] + W1024^k O[k].  That is exactly what the ASR core transforms at once
+// - two real 512-point sequences, one per lane of the packed registers - so a 16-thread group runs ONE TTS frame with
+// lane .x = even samples, lane .y = odd samples (one 64-bit shared load fetches both), through the same real 32-point
+// stage, transpose, twiddle and 16-point stage (quad_stage2's data flow), and the recombination is thread-local because
+// E[k] and O[k] sit in the two lanes of one register:  2 X[k] = 2E + W (2O),  2 X[512-k] = conj(2E - W (2O)).
+// The periodic Hann window needs no table: w[32 i + 2 j (+1)] follows from cos(a_i + b) with a_i a compile-time constant.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "fbank_tile.cuh"
-#include "fft512_complex.cuh"
 
 namespace b200fe {
 
 constexpr int kTtsNfft = 1024;
 constexpr int kTtsFrames = 16;          // frames per tile
 constexpr int kTtsBins = 513;
-constexpr int kTtsPRow = 516;           // floats per frame in the magnitude buffer
+constexpr int kTtsMagF2 = 520;          // float2 (frame of group 0, frame of group 1) per bin, padded
 
 struct TtsParams {
   const float* wave;
@@ -34,32 +36,96 @@ struct TtsParams {
   long long* mel_lens;         // [batch] or nullptr
   float mag_eps;               // 1e-9
   float log_floor;             // 1e-5
-  const float* window;         // [1024] periodic Hann
-  const float2* twiddle;       // [kTwTable] table 0 of the ASR front-end
-  const float2* w1024;         // [16] W1024^j
-  MelTab mel_tab;              // interval table over 512 bins (bin 512 carries no weight)
+  const float2* twiddle;       // [kTw2Total]: the ASR front-end's stage-2 twiddles + column-0 table (TileParams::twiddle)
+  const float2* w1024;         // [17] W1024^col, col = 0..16
+  MelTab mel_tab;              // interval table over 512 bins (bin 512 carries no weight), bank-matched lanes
 };
 
 __host__ __device__ inline size_t tts_smem_bytes(int hop, int n_mels) {
   size_t b = 0;
   b += (size_t)((kTtsFrames - 1) * hop + kTtsNfft) * 4;     // staged samples (reflection resolved)
-  b += kTtsNfft * 4;                                        // window
-  b += (size_t)kWarps * 2 * kXGroupFloat2 * 8;              // transpose buffers / magnitude spectra
+  b += (size_t)kWarps * kYWarpF4 * 16;                      // transpose buffers (aliased by the magnitude spectra)
   b += (size_t)kTtsFrames * n_mels * 4;                     // log-mel tile
-  b += kTwTable * 8;
+  b += kTw2Total * 8;
   return b;
 }
 
-// 154 registers and 68 KB of shared memory per CTA: three CTAs (12 warps) per SM
+// Stage 2 of one group's (even, odd) pair, quad_stage2's data flow with complex outputs kept: on return ar/ai[k2] hold
+// 2 x the 512-point spectra (lane .x: even samples, lane .y: odd samples) at bin col + 32 k2, and (c0r, c0i) the same at
+// bin 32 t0 for the lane's own group; u_alt = sum_c (-1)^c Y_c[0] = bin 256 of both sequences (unscaled, real).
+__device__ __forceinline__ void tts_stage2(const f2 (&zr)[16], const f2 (&zi)[16], f2 y0, f2 y16, float4* yg,
+                                           const float2* tw_row, const float2* c0_row, int j, int grp_in_warp,
+                                           f2 (&ar)[16], f2 (&ai)[16], f2& c0r, f2& c0i, f2& u_alt) {
+  {
+    float2* yg2 = reinterpret_cast<float2*>(yg) + 2 * j;
+    const int hr = j >> 3, hi = hr ^ 1;
+    static_for<1, 16>([&](auto ic) {
+      constexpr int k1 = decltype(ic)::value;
+      yg2[(k1 - 1) * 2 * kYPitch + hr] = zr[k1];
+      yg2[(k1 - 1) * 2 * kYPitch + hi] = zi[k1];
+    });
+    yg2[15 * 2 * kYPitch + hr] = y16;
+    yg2[15 * 2 * kYPitch + hi] = make_float2(0.f, 0.f);
+  }
+  reinterpret_cast<float2*>(yg + 16 * kYPitch)[j] = y0;
+  __syncwarp();
+  const int lane = (grp_in_warp << 4) | j;
+  const int c = lane >> 1, g2 = lane & 1;
+  const int col = c == 0 ? 16 : c;
+  float4* const ywarp = yg - grp_in_warp * kYGroupF4;
+  {
+    const float4* rowp = ywarp + g2 * kYGroupF4 + (col - 1) * kYPitch;
+    static_for<0, 8>([&](auto ic) {
+      constexpr int h = decltype(ic)::value;
+      const float2 ta = tw_row[2 * h], tb = tw_row[2 * h + 1];
+      const float4 v0 = rowp[2 * h], v1 = rowp[2 * h + 1];
+      constexpr bool sw = 2 * h >= 8;   // slots 8..15 are stored (im, re)
+      {
+        const f2 yr = sw ? make_float2(v0.z, v0.w) : make_float2(v0.x, v0.y);
+        const f2 yi = sw ? make_float2(v0.x, v0.y) : make_float2(v0.z, v0.w);
+        ar[bitrev<16>(2 * h)] = fma2s(yr, ta.x, neg2(mul2s(yi, ta.y)));
+        ai[bitrev<16>(2 * h)] = fma2s(yr, ta.y, mul2s(yi, ta.x));
+      }
+      {
+        const f2 yr = sw ? make_float2(v1.z, v1.w) : make_float2(v1.x, v1.y);
+        const f2 yi = sw ? make_float2(v1.x, v1.y) : make_float2(v1.z, v1.w);
+        ar[bitrev<16>(2 * h + 1)] = fma2s(yr, tb.x, neg2(mul2s(yi, tb.y)));
+        ai[bitrev<16>(2 * h + 1)] = fma2s(yr, tb.y, mul2s(yi, tb.x));
+      }
+    });
+  }
+  // column 0 of the lane's OWN group: bin 32 t0 (table entries carry the factor 2) and the alternating sum (bin 256)
+  {
+    const int t0 = (lane >> 1) & 7;
+    const float4* u4 = reinterpret_cast<const float4*>(yg + 16 * kYPitch);   // 16 x (even, odd)
+    const float4* w4 = reinterpret_cast<const float4*>(c0_row);
+    const float sgn = (t0 & 1) ? -1.f : 1.f;
+    f2 cr = make_float2(0.f, 0.f), ci = make_float2(0.f, 0.f), alt = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float4 ua = u4[h], ub = u4[h + 4], w = w4[h];
+      const f2 v0 = fma2s(make_float2(ub.x, ub.y), sgn, make_float2(ua.x, ua.y));
+      const f2 v1 = fma2s(make_float2(ub.z, ub.w), sgn, make_float2(ua.z, ua.w));
+      cr = fma2s(v0, w.x, cr);
+      ci = fma2s(v0, w.y, ci);
+      cr = fma2s(v1, w.z, cr);
+      ci = fma2s(v1, w.w, ci);
+      alt = add2(alt, sub2(add2(make_float2(ua.x, ua.y), make_float2(ub.x, ub.y)), add2(make_float2(ua.z, ua.w), make_float2(ub.z, ub.w))));
+    }
+    c0r = cr; c0i = ci; u_alt = alt;
+  }
+  fft_dit2<16>(ar, ai);
+  __syncwarp();   // every lane has consumed the transpose buffers: the magnitudes may overwrite them
+}
+
 __global__ void __launch_bounds__(kCtaThreads, 3)
 tts_mel_kernel(const TtsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int hop = p.hop, M = p.n_mels;
   const int ncap = (kTtsFrames - 1) * hop + kTtsNfft;
   float* xs = reinterpret_cast<float*>(smem_raw);
-  float* win_s = xs + ncap;
-  float2* xbuf = reinterpret_cast<float2*>(win_s + kTtsNfft);
-  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * 2 * kXGroupFloat2);
+  float4* xbuf = reinterpret_cast<float4*>(xs + ncap);
+  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * kYWarpF4);
   float2* tw_s = reinterpret_cast<float2*>(logmel_s + kTtsFrames * M);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -74,8 +140,7 @@ tts_mel_kernel(const TtsParams p) {
   const float* x = p.wave + p.offsets[u];
   const int pad = (kTtsNfft - hop) / 2;
 
-  for (int i = tid; i < kTtsNfft; i += kCtaThreads) win_s[i] = p.window[i];
-  for (int i = tid; i < kTwTable; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   // stage with reflect padding: padded[s] = x[reflect(s - pad)]
   {
     const int n_s = (F - 1) * hop + kTtsNfft;
@@ -88,74 +153,84 @@ tts_mel_kernel(const TtsParams p) {
       xs[i] = x[s];
     }
   }
+  // periodic Hann of this thread's samples n = 32 i + 2 j (+ 1): cos(2 pi n / 1024) = cos(a_i) cos(b) - sin(a_i) sin(b)
+  f2 cb, sb;
+  {
+    float s0, c0, s1, c1;
+    sincospif(2.0f * (float)(2 * j) / 1024.0f, &s0, &c0);
+    sincospif(2.0f * (float)(2 * j + 1) / 1024.0f, &s1, &c1);
+    cb = make_float2(c0, c1);
+    sb = make_float2(s0, s1);
+  }
   __syncthreads();
 
-  float2* xg = xbuf + (warp * 2 + g) * kXGroupFloat2;
-  float* pbuf = reinterpret_cast<float*>(xbuf + warp * 2 * kXGroupFloat2);   // this warp's [2 frames][kTtsPRow] magnitudes
-  const float2 cj = p.w1024[j];          // W1024^j
+  float4* yg = xbuf + warp * kYWarpF4 + g * kYGroupF4;
+  float2* mag = reinterpret_cast<float2*>(xbuf + warp * kYWarpF4);   // this warp's magnitudes (frame of group 0, of group 1)
+  const float2* tw_row = fft_twiddle_row<32>(tw_s, j, g);
+  const float2* c0_row = fft_c0_row(tw_s, j);
+  const int c = lane >> 1, g2 = lane & 1, col = c == 0 ? 16 : c, t0 = (lane >> 1) & 7;
+  const float2 wcol = __ldg(p.w1024 + col);                 // W1024^col = (cos, -sin)
+  float w32r, w32i;                                          // W32^t0 for the column-0 bins
+  {
+    float sn, cs;
+    sincospif(2.0f * (float)t0 / 32.0f, &sn, &cs);
+    w32r = cs; w32i = -sn;
+  }
 
   for (int pair = warp; 2 * pair < F; pair += kWarps) {
     const int f = 2 * pair + g;          // tile-local frame of this group
     const bool valid = f < F;
-    float re[32], im[32];
+    f2 ar[16], ai[16], c0r, c0i, u_alt;
     {
-      const float2* xf = reinterpret_cast<const float2*>(xs + f * hop);   // hop is even: 8-byte aligned
-      const float2* wf = reinterpret_cast<const float2*>(win_s);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int m = 16 * i + j;
-        float2 v = make_float2(0.f, 0.f);
-        if (valid) v = xf[m];
-        const float2 w = wf[m];
-        re[i] = v.x * w.x;
-        im[i] = v.y * w.y;
+      f2 zr[16], zi[16], y0, y16;
+      {
+        f2 y[32];
+        const float2* xf = reinterpret_cast<const float2*>(xs + (valid ? f : 0) * hop) + j;   // hop is even: 8-byte aligned
+        static_for<0, 32>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          constexpr float ca = (float)(0.5 * ct_cos2pi(i, 32)), sa = (float)(0.5 * ct_sin2pi(i, 32));
+          const f2 w = fma2s(sb, sa, fma2s(cb, -ca, make_float2(0.5f, 0.5f)));
+          y[i] = mul2(xf[16 * i], w);
+        });
+        static_for<0, 16>([&](auto ic) {
+          constexpr int m = decltype(ic)::value;
+          zr[bitrev<16>(m)] = y[2 * m];
+          zi[bitrev<16>(m)] = y[2 * m + 1];
+        });
       }
+      fft_dit2<16>(zr, zi);
+      real32_split2(zr, zi, y0, y16);
+      __syncwarp();   // the previous pair's magnitudes (aliased buffer) have been consumed by the mel stage
+      tts_stage2(zr, zi, y0, y16, yg, tw_row, c0_row, j, g, ar, ai, c0r, c0i, u_alt);
     }
-    float ar[16], ai[16], br[16], bi[16];
-    fft512_columns<32>(re, im, xg, tw_s, j, ar, ai, br, bi);
-
-    // even/odd recombination: with s = Z[k] + conj Z[512-k] = 2E and d = Z[k] - conj Z[512-k] = 2iO,
-    // 2X[k] = s + W1024^k (d/i),  2X[512-k] = conj(s - W1024^k (d/i))
+    // ---- recombination: lane .x = 2E[k], lane .y = 2O[k] at k = col + 32 k2;  2X[k] = 2E + W^k 2O,
+    //      2X[512-k] = conj(2E - W^k 2O);  magnitudes into component g2 of the warp's buffer
     {
-      const bool t0 = (j == 0);
-      float* pf = pbuf + g * kTtsPRow;
-#define A_RE(k) ar[bitrev<16>(k)]
-#define A_IM(k) ai[bitrev<16>(k)]
-#define B_RE(k) br[bitrev<16>(((k) + 1) & 15)]
-#define B_IM(k) bi[bitrev<16>(((k) + 1) & 15)]
-      // thread 0, slot 0 holds (Z[0], Z[256]): bin 256 pairs with itself, |X[256]| = |Z[256]|; bins 0 and 512 come from
-      // the generic formula with Z[512-0] := Z[0]
-      const float nyq = sqrtf(fmaf(B_RE(15), B_RE(15), B_IM(15) * B_IM(15)) + p.mag_eps);
+      float* mg = reinterpret_cast<float*>(mag) + g2;
       static_for<0, 16>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        const float ur = A_RE(i), ui = A_IM(i);
-        float vr = B_RE(15 - i), vi = B_IM(15 - i);
-        if (i == 0) { vr = t0 ? ur : vr; vi = t0 ? ui : vi; }
-        const float sr = ur + vr, si = ui - vi;          // 2E
-        const float or_ = ui + vi, oi = vr - ur;         // 2O = d / i
-        // k = cA + 32 i (thread 0, i >= 8: k = 16 + 32 i);  W1024^k = W1024^c * W32^i
-        constexpr float wr32 = (float)ct_cos2pi(i, 32), wi32 = (float)(-ct_sin2pi(i, 32));
-        float cr = cj.x, ci = cj.y;
-        if (i >= 8 && t0) { cr = (float)ct_cos2pi(16, 1024); ci = (float)(-ct_sin2pi(16, 1024)); }
-        const float wr = cr * wr32 - ci * wi32, wi = cr * wi32 + ci * wr32;
-        const float tr = fmaf(or_, wr, -(oi * wi)), ti = fmaf(or_, wi, oi * wr);
-        const float ar2 = sr + tr, ai2 = si + ti;        // 2 X[k]
-        const float br2 = sr - tr, bi2 = si - ti;        // 2 conj X[512-k]
-        const float mk = sqrtf(fmaf(0.25f, fmaf(ar2, ar2, ai2 * ai2), p.mag_eps));
-        const float mm = sqrtf(fmaf(0.25f, fmaf(br2, br2, bi2 * bi2), p.mag_eps));
-        const int k = (i >= 8 && t0) ? 16 + 32 * i : j + 32 * i;
-        pf[k] = mk;
-        pf[512 - k] = mm;
+        constexpr int k2 = decltype(ic)::value;
+        constexpr float c32 = (float)ct_cos2pi(k2, 32), s32 = (float)(-ct_sin2pi(k2, 32));   // W32^k2
+        const float wr = wcol.x * c32 - wcol.y * s32, wi = wcol.x * s32 + wcol.y * c32;      // W1024^(col + 32 k2)
+        const float er = ar[k2].x, ei = ai[k2].x, orr = ar[k2].y, oi = ai[k2].y;
+        const float tr = fmaf(orr, wr, -(oi * wi)), ti = fmaf(orr, wi, oi * wr);
+        const float pr = er + tr, pi = ei + ti, qr = er - tr, qi = ei - ti;
+        const int k = col + 32 * k2;
+        mg[2 * k] = sqrtf(fmaf(0.25f, fmaf(pr, pr, pi * pi), p.mag_eps));
+        if (c != 0) mg[2 * (512 - k)] = sqrtf(fmaf(0.25f, fmaf(qr, qr, qi * qi), p.mag_eps));
       });
-      if (t0) pf[256] = nyq;
-#undef A_RE
-#undef A_IM
-#undef B_RE
-#undef B_IM
+      if ((lane & 1) == 0) {   // column 0 of the lane's own group: bins 32 t0 and 512 - 32 t0, and bin 256
+        float* mo = reinterpret_cast<float*>(mag) + g;
+        const float er = c0r.x, ei = c0i.x, orr = c0r.y, oi = c0i.y;
+        const float tr = fmaf(orr, w32r, -(oi * w32i)), ti = fmaf(orr, w32i, oi * w32r);
+        const float pr = er + tr, pi = ei + ti, qr = er - tr, qi = ei - ti;
+        mo[2 * (32 * t0)] = sqrtf(fmaf(0.25f, fmaf(pr, pr, pi * pi), p.mag_eps));
+        mo[2 * (512 - 32 * t0)] = sqrtf(fmaf(0.25f, fmaf(qr, qr, qi * qi), p.mag_eps));
+        if (t0 == 0) mo[2 * 256] = sqrtf(fmaf(u_alt.x, u_alt.x, u_alt.y * u_alt.y) + p.mag_eps);   // E[256] - i O[256]
+      }
     }
     __syncwarp();
 
-    // mel over magnitudes: lane <-> interval, both frames of the warp at once
+    // ---- mel over magnitudes: lane <-> interval (bank-matched lanes, as in the ASR mel stage), both frames at once
     {
       const MelTab& mel = p.mel_tab;
 #pragma unroll 1
@@ -164,27 +239,27 @@ tts_mel_kernel(const TtsParams p) {
 #pragma unroll
         for (int t = 1; t < kMelRounds; ++t)
           if (r == t) { cnt = mel.cnt[t]; base = mel.base[t]; }
-        const int iv = lane + 31 * r;
-        const int lo = __ldg(mel.lo + 32 * r + lane) & 0xfff;   // identity lane layout (build_interval_table, bank_mod 0)
+        const unsigned word = (unsigned)__ldg(mel.lo + 32 * r + lane);
+        const int lo = (int)(word & 0xfffu), partner = (int)((word >> 12) & 31u), iv = (int)((word >> 17) & 0xffu);
         const float2* wt = mel.w + (base * 32 + lane);
-        float up0 = 0.f, up1 = 0.f, dn0 = 0.f, dn1 = 0.f;
+        const float2* p0 = mag + lo;
+        f2 up = make_float2(0.f, 0.f), dn = make_float2(0.f, 0.f);
 #pragma unroll 4
         for (int q = 0; q < cnt; ++q) {
           const float2 w = __ldg(wt + 32 * q);
-          const float s0 = pbuf[lo + q], s1 = pbuf[kTtsPRow + lo + q];
-          up0 = fmaf(w.x, s0, up0); up1 = fmaf(w.x, s1, up1);
-          dn0 = fmaf(w.y, s0, dn0); dn1 = fmaf(w.y, s1, dn1);
+          const float2 sv = p0[q];
+          up = fma2s(sv, w.x, up);
+          dn = fma2s(sv, w.y, dn);
         }
-        const float e0 = up0 + __shfl_down_sync(0xffffffffu, dn0, 1);
-        const float e1 = up1 + __shfl_down_sync(0xffffffffu, dn1, 1);
-        if (lane < 31 && iv < M) {
+        const float e0 = up.x + __shfl_sync(0xffffffffu, dn.x, partner);
+        const float e1 = up.y + __shfl_sync(0xffffffffu, dn.y, partner);
+        if (word >> 31) {
           const int fr = 2 * pair;
           if (fr < F) logmel_s[fr * M + iv] = logf(fmaxf(e0, p.log_floor));
           if (fr + 1 < F) logmel_s[(fr + 1) * M + iv] = logf(fmaxf(e1, p.log_floor));
         }
       }
     }
-    __syncwarp();
   }
   __syncthreads();
 
