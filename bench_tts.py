@@ -35,7 +35,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lens = synth.utterance_lengths(5 + rank, a.batch, lo=72000, hi=240000)
-    nmax = int(lens.max())
+    nmax = (int(lens.max()) + 3) // 4 * 4          # rows of the dense batch start on 16-byte boundaries
     wave = torch.zeros(a.batch, nmax, device=dev)
     offs = torch.arange(a.batch, dtype=torch.int64) * nmax
     _native.ops().synth_uniform(wave, offs, torch.from_numpy(lens), 5 + rank, 0.3)

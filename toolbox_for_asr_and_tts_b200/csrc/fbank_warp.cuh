@@ -32,6 +32,12 @@
 #ifndef B200FE_CLAIM2        // 1: quads claimed two ahead (atomic read at the end of the iteration); 0: one ahead
 #define B200FE_CLAIM2 0
 #endif
+#ifndef B200FE_HEAD_PRED     // 1: round-2a behaviour, the next quad's head is loaded under a predicate (experiment baseline)
+#define B200FE_HEAD_PRED 0
+#endif
+#ifndef B200FE_CLAIM_STATIC  // 1: no work counter, warp w takes quads w, w + W, w + 2 W, ... (W = warps of the grid)
+#define B200FE_CLAIM_STATIC 0
+#endif
 #ifndef B200FE_WARP_CTAS     // resident CTAs per SM the warp kernel is compiled and launched for
 #define B200FE_WARP_CTAS 4
 #endif
@@ -331,6 +337,7 @@ fbank_warp_kernel(const QuadParams p) {
   // quad k+1 (for its bulk copy), so neither the atomic's nor the descriptor's L2 round trip is ever waited for.
   // The rest of the 64-byte descriptor ({f0, T, rows}, the LFR targets) is read by the quad itself, just before use.
   const int first_wave = gridDim.x * kWarps;
+  const int last_quad = p.n_quads - 1;
   const int n_pad_items = p.batch << kPadPieceShift;
   int q = blockIdx.x * kWarps + warp;
   if (q >= p.n_quads) return;
@@ -347,8 +354,7 @@ fbank_warp_kernel(const QuadParams p) {
   if (lane == 0) qn = first_wave + atomicAdd(p.next_quad, 1);
   qn = __shfl_sync(0xffffffffu, qn, 0);
   bool have_next = qn < p.n_quads;
-  int4 hdn = make_int4(0, 0, 0, 0);
-  if (have_next) hdn = __ldg(reinterpret_cast<const int4*>(p.quads + qn));
+  int4 hdn = __ldg(reinterpret_cast<const int4*>(p.quads + min(qn, last_quad)));
 #endif
   // the first quad's samples: bulk copy if possible (in_flight), else filled at the top of the loop
   unsigned phase = 0;
@@ -363,13 +369,23 @@ fbank_warp_kernel(const QuadParams p) {
 #if B200FE_CLAIM2
     int claim = 0;
     if (lane == 0) claim = atomicAdd(p.next_quad, 1);      // quad k+2; read at the end of this iteration
+#elif B200FE_CLAIM_STATIC
+    const int qn = q + first_wave;
+    const bool have_next = qn < p.n_quads;
+    const int4 hdn = __ldg(reinterpret_cast<const int4*>(p.quads + min(qn, last_quad)));
 #else
     int qn = 0;
     if (lane == 0) qn = first_wave + atomicAdd(p.next_quad, 1);
     qn = __shfl_sync(0xffffffffu, qn, 0);
     const bool have_next = qn < p.n_quads;
+    // unconditional (clamped) load: a predicated one makes the compiler copy the fields right behind the load, which
+    // exposes its whole L2 latency at the top of the quad
+#if B200FE_HEAD_PRED
     int4 hdn = make_int4(0, 0, 0, 0);
     if (have_next) hdn = __ldg(reinterpret_cast<const int4*>(p.quads + qn));
+#else
+    const int4 hdn = __ldg(reinterpret_cast<const int4*>(p.quads + min(qn, last_quad)));
+#endif
 #endif
     const int4 hd1 = __ldg(reinterpret_cast<const int4*>(p.quads + q) + 1);   // f0, T, rows, pad: used by the output stage
     int pad_rows = 0;                                                          // padding piece q: read now, stored mid-quad
@@ -611,7 +627,7 @@ fbank_warp_kernel(const QuadParams p) {
 #if B200FE_CLAIM2
     qn = first_wave + __shfl_sync(0xffffffffu, claim, 0);
     have_next = qn < p.n_quads;
-    if (have_next) hdn = __ldg(reinterpret_cast<const int4*>(p.quads + qn));
+    hdn = __ldg(reinterpret_cast<const int4*>(p.quads + min(qn, last_quad)));
 #endif
   }
   // the zero block must outlive the bulk stores that read it

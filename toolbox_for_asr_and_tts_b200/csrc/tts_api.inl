@@ -7,6 +7,11 @@ struct b200fe_tts {
   int* d_mel_lo = nullptr;
   int mel_rounds = 0, mel_cnt[kMelRounds] = {0}, mel_base[kMelRounds] = {0};
   size_t smem = 0;
+  int n_sms = 0;
+  TtsUtt* d_utts = nullptr;     // launch workspace, grown on demand: [cap] clip descriptors, [cap + 1] pair prefix sums
+  int* d_pair_begin = nullptr;
+  int cap = 0;
+  std::mutex mu;                // one forward at a time per handle: the workspace is shared
   std::string err;
 };
 
@@ -56,8 +61,14 @@ int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_m
   if (!(f_min >= 0 && f_max > f_min && f_max <= sample_rate / 2.0f)) return failc(B200FE_E_INVALID, "bad f_min / f_max");
   b200fe_tts* t = new b200fe_tts();
   t->sample_rate = sample_rate; t->n_fft = n_fft; t->hop = hop; t->n_mels = n_mels;
-  t->smem = tts_smem_bytes(hop, n_mels);
-  if (t->smem > 227 * 1024) { delete t; return failc(B200FE_E_UNSUPPORTED, "hop too large for the shared-memory tile"); }
+  t->smem = tts_smem_bytes(hop);
+  if (t->smem * B200FE_TTS_CTAS > 227 * 1024) { delete t; return failc(B200FE_E_UNSUPPORTED, "hop too large for the per-warp sample buffers"); }
+  {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { delete t; return failc(B200FE_E_CUDA, "cudaGetDeviceProperties failed"); }
+    t->n_sms = prop.multiProcessorCount;
+  }
   std::vector<float> bank;
   build_slaney_bank(n_fft / 2 + 1, f_min, f_max, n_mels, sample_rate, bank);
   std::vector<float2> mw;
@@ -97,6 +108,7 @@ int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_m
 void b200fe_tts_destroy(b200fe_tts* t) {
   if (!t) return;
   cudaFree(t->d_twiddle); cudaFree(t->d_w1024); cudaFree(t->d_mel_w); cudaFree(t->d_mel_lo);
+  cudaFree(t->d_utts); cudaFree(t->d_pair_begin);
   delete t;
 }
 
@@ -107,17 +119,34 @@ int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total,
   if (batch == 0) return B200FE_OK;
   if (!wave_dev || !offsets_dev || !lengths_dev || !mel_dev || batch < 0 || max_frames > frames_cap) return B200FE_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(t->mu);
+  if (batch > t->cap) {   // grow the workspace (synchronises: earlier launches may still read the old one)
+    if (cudaDeviceSynchronize() != cudaSuccess) return B200FE_E_CUDA;
+    cudaFree(t->d_utts); cudaFree(t->d_pair_begin);
+    t->d_utts = nullptr; t->d_pair_begin = nullptr; t->cap = 0;
+    const int cap = batch + batch / 2 + 16;
+    if (cudaMalloc(&t->d_utts, (size_t)cap * sizeof(TtsUtt)) != cudaSuccess || cudaMalloc(&t->d_pair_begin, ((size_t)cap + 1) * 4) != cudaSuccess)
+      return B200FE_E_CUDA;
+    t->cap = cap;
+  }
   TtsParams p;
-  p.wave = wave_dev; p.wave_total = wave_total; p.offsets = (const long long*)offsets_dev; p.lengths = (const long long*)lengths_dev;
+  p.wave = wave_dev; p.wave_total = wave_total;
   p.batch = batch; p.hop = t->hop; p.n_mels = t->n_mels; p.mel = mel_dev; p.frames_cap = frames_cap;
-  p.mel_lens = (long long*)mel_lens_dev; p.mag_eps = 1e-9f; p.log_floor = 1e-5f;
+  p.mag_eps = 1e-9f; p.log_floor = 1e-5f;
   p.twiddle = t->d_twiddle; p.w1024 = t->d_w1024;
   p.mel_tab.w = t->d_mel_w; p.mel_tab.lo = t->d_mel_lo; p.mel_tab.rounds = t->mel_rounds;
   for (int r = 0; r < kMelRounds; ++r) { p.mel_tab.cnt[r] = t->mel_cnt[r]; p.mel_tab.base[r] = t->mel_base[r]; }
+  p.utts = t->d_utts; p.pair_begin = t->d_pair_begin;
   if (allow_dynamic_smem((const void*)tts_mel_kernel, t->smem) != cudaSuccess) return B200FE_E_CUDA;
+  tts_prep_kernel<<<1, 1024, 0, st>>>((const long long*)offsets_dev, (const long long*)lengths_dev, batch, t->hop, t->d_utts,
+                                      t->d_pair_begin, (long long*)mel_lens_dev);
   tts_pad_kernel<<<dim3(8, batch), 256, 0, st>>>((const long long*)lengths_dev, t->hop, t->n_mels, mel_dev, frames_cap);
-  const int tiles = (int)((max_frames + kTtsFrames - 1) / kTtsFrames);
-  if (tiles > 0) tts_mel_kernel<<<dim3(tiles, batch), kCtaThreads, t->smem, st>>>(p);
+  if (max_frames > 0) {
+    // persistent warps: as many CTAs as stay resident, but not more warps than an upper bound of the pair count
+    const long long pairs_ub = (long long)batch * ((max_frames + 1) / 2);
+    const long long ctas = std::min<long long>((long long)t->n_sms * B200FE_TTS_CTAS, (pairs_ub + kWarps - 1) / kWarps);
+    tts_mel_kernel<<<(unsigned)std::max<long long>(ctas, 1), kCtaThreads, t->smem, st>>>(p);
+  }
   return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
 }
 

@@ -3,51 +3,117 @@
 // log(clamp(., 1e-5)), output [B, n_mels, frames] (mel-major).  Definition frozen in oracle/tts_mel_np.py (the
 // reference has no audio->mel code: parity unpinned).
 //
-// Round 2: on the packed f32x2 real-FFT core of the ASR front-end.  A 1024-point real FFT is two 512-point real FFTs,
-// of the even and of the odd samples: X[k] = E[k] + W1024^k O[k].  That is exactly what the ASR core transforms at once
-// - two real 512-point sequences, one per lane of the packed registers - so a 16-thread group runs ONE TTS frame with
-// lane .x = even samples, lane .y = odd samples (one 64-bit shared load fetches both), through the same real 32-point
-// stage, transpose, twiddle and 16-point stage (quad_stage2's data flow), and the recombination is thread-local because
-// E[k] and O[k] sit in the two lanes of one register:  2 X[k] = 2E + W (2O),  2 X[512-k] = conj(2E - W (2O)).
-// The periodic Hann window needs no table: w[32 i + 2 j (+1)] follows from cos(a_i + b) with a_i a compile-time constant.
+// Round 2: on the packed f32x2 real-FFT core of the ASR front-end, and warp-autonomous like fbank_warp_kernel.
+//   * FFT: a 1024-point real FFT is two 512-point real FFTs, of the even and of the odd samples:
+//     X[k] = E[k] + W1024^k O[k].  That is exactly what the ASR core transforms at once - two real 512-point sequences,
+//     one per lane of the packed registers - so a 16-thread group runs ONE TTS frame with lane .x = even samples,
+//     lane .y = odd samples (one 64-bit shared load fetches both), through the same real 32-point stage, transpose,
+//     twiddle and 16-point stage (quad_stage2's data flow), and the recombination is thread-local because E[k] and
+//     O[k] sit in the two lanes of one register:  2 X[k] = 2E + W (2O),  2 X[512-k] = conj(2E - W (2O)).
+//     The periodic Hann window needs no table: w[32 i + 2 j (+1)] follows from cos(a_i + b), a_i a compile-time constant.
+//   * work: one PAIR of consecutive frames (n_fft + hop samples) per warp and iteration; persistent warps stride over
+//     the launch-wide pair list (tts_prep_kernel: prefix sums of ceil(T/2)), so neighbouring warps work on neighbouring
+//     pairs and share their 768 overlapping samples through L2.  The pair's samples arrive by ONE bulk copy
+//     (cp.async.bulk, SASS UBLKCP) into the warp's buffer, issued a whole pair ahead and completed on the warp's own
+//     mbarrier; pairs that touch the reflected ends of a clip (or a clip that does not start on an 8-byte boundary)
+//     are filled by the lanes.  No CTA-wide barrier in the loop.
+//   * output: the lane that holds filter m of the pair's two frames stores them as one 8-byte word of row m.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "fbank_tile.cuh"
+#include "fbank_warp.cuh"
+
+#ifndef B200FE_TTS_CTAS      // resident CTAs per SM the TTS kernel is compiled and launched for
+#define B200FE_TTS_CTAS 3
+#endif
 
 namespace b200fe {
 
 constexpr int kTtsNfft = 1024;
-constexpr int kTtsFrames = 16;          // frames per tile
 constexpr int kTtsBins = 513;
 constexpr int kTtsMagF2 = 520;          // float2 (frame of group 0, frame of group 1) per bin, padded
+
+struct __align__(16) TtsUtt {   // built by tts_prep_kernel
+  long long off;      // first sample of the clip inside the wave buffer
+  long long N;        // samples
+  int T;              // frames = N / hop
+  int pair_begin;     // index of the clip's first pair in the launch-wide pair list
+  int r0, r1;
+};
 
 struct TtsParams {
   const float* wave;
   long long wave_total;
-  const long long* offsets;    // [batch] device
-  const long long* lengths;    // [batch] device
   int batch;
   int hop;                     // 256
   int n_mels;
   float* mel;                  // [batch, n_mels, frames_cap]
   long long frames_cap;
-  long long* mel_lens;         // [batch] or nullptr
   float mag_eps;               // 1e-9
   float log_floor;             // 1e-5
   const float2* twiddle;       // [kTw2Total]: the ASR front-end's stage-2 twiddles + column-0 table (TileParams::twiddle)
   const float2* w1024;         // [17] W1024^col, col = 0..16
   MelTab mel_tab;              // interval table over 512 bins (bin 512 carries no weight), bank-matched lanes
+  const TtsUtt* utts;          // [batch]
+  const int* pair_begin;       // [batch + 1]: exclusive prefix sums of ceil(T / 2); the last entry is the pair count
 };
 
-__host__ __device__ inline size_t tts_smem_bytes(int hop, int n_mels) {
-  size_t b = 0;
-  b += (size_t)((kTtsFrames - 1) * hop + kTtsNfft) * 4;     // staged samples (reflection resolved)
-  b += (size_t)kWarps * kYWarpF4 * 16;                      // transpose buffers (aliased by the magnitude spectra)
-  b += (size_t)kTtsFrames * n_mels * 4;                     // log-mel tile
-  b += kTw2Total * 8;
-  return b;
+// floats of a warp's sample buffer: a pair's n_fft + hop samples, placed up to 2 floats behind a 16-byte boundary
+__host__ __device__ inline int tts_buf_floats(int hop) { return ((hop + kTtsNfft + 3) & ~3) + 4; }
+__host__ __device__ inline size_t tts_smem_bytes(int hop) {
+  return (size_t)kWarps * tts_buf_floats(hop) * 4 + (size_t)kWarps * kYWarpF4 * 16 + (size_t)kTw2Total * 8 + (size_t)kWarps * 8;
+}
+
+// One block: frames, pair prefix sums and clip descriptors of the batch; also the frame counts handed to the caller.
+__global__ void __launch_bounds__(1024)
+tts_prep_kernel(const long long* offsets, const long long* lengths, int batch, int hop, TtsUtt* utts, int* pair_begin,
+                long long* mel_lens) {
+  __shared__ int warp_sums[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int carry = 0;
+  for (int base = 0; base < batch; base += 1024) {
+    const int u = base + threadIdx.x;
+    const long long N = u < batch ? lengths[u] : 0;
+    const int T = (int)(N / hop);
+    const int v = (T + 1) >> 1;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int s = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += y;
+      }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int excl = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;
+    if (u < batch) {
+      pair_begin[u] = excl;
+      TtsUtt d;
+      d.off = offsets[u]; d.N = N; d.T = T; d.pair_begin = excl; d.r0 = d.r1 = 0;
+      utts[u] = d;
+      if (mel_lens) mel_lens[u] = T;
+    }
+    carry += warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) pair_begin[batch] = carry;
+}
+
+__device__ __forceinline__ float fast_sqrt(float x) {   // x >= mag_eps > 0
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // Stage 2 of one group's (even, odd) pair, quad_stage2's data flow with complex outputs kept: on return ar/ai[k2] hold
@@ -118,40 +184,53 @@ __device__ __forceinline__ void tts_stage2(const f2 (&zr)[16], const f2 (&zi)[16
   __syncwarp();   // every lane has consumed the transpose buffers: the magnitudes may overwrite them
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 3)
+// Lanes of a warp: the samples of pair `pair` of a clip into buf (buf[i] = padded[2 pair hop + i], reflection resolved)
+__device__ __forceinline__ void tts_fill_generic(const float* x, long long N, long long s0, int n, int lane, float* buf) {
+  for (int i = lane; i < n; i += 32) {
+    long long s = s0 + i;
+    if (s < 0) s = -s;
+    if (s >= N) s = 2 * (N - 1) - s;
+    s = s < 0 ? 0 : (s >= N ? N - 1 : s);
+    buf[i] = __ldg(x + s);
+  }
+}
+
+// Where the bulk copy of a pair's samples starts (absolute index in the wave buffer) when the pair lies inside the clip
+// and starts on an 8-byte boundary; -1 when the lanes have to fill the buffer (reflected ends, odd offsets).
+__device__ __forceinline__ long long tts_tma_source(const TtsParams& p, const TtsUtt& ut, int pair) {
+  const int pad = (kTtsNfft - p.hop) / 2, n = p.hop + kTtsNfft;
+  const long long s0 = 2ll * pair * p.hop - pad;
+  if (s0 < 0 || s0 + n > ut.N) return -1;
+  const long long g0 = ut.off + s0;
+  return (quad_a_off<float>(p.wave, g0) & 1) ? -1 : g0;
+}
+// The whole warp: issue the copy (lane 0).  Returns 1 + the buffer offset (0 or 2 floats) of the pair's first sample,
+// or 0 when there is no copy in flight.
+__device__ __forceinline__ int tts_issue_copy(const TtsParams& p, long long g0, int lane, float* buf, unsigned long long* bar) {
+  if (g0 < 0) return 0;
+  int ok = 0;
+  if (lane == 0) ok = quad_fill_tma(p.wave, p.wave_total, g0, p.hop + kTtsNfft, buf, bar) ? 1 : 0;
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  return ok ? 1 + quad_a_off<float>(p.wave, g0) : 0;
+}
+
+__global__ void __launch_bounds__(kCtaThreads, B200FE_TTS_CTAS)
 tts_mel_kernel(const TtsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int hop = p.hop, M = p.n_mels;
-  const int ncap = (kTtsFrames - 1) * hop + kTtsNfft;
-  float* xs = reinterpret_cast<float*>(smem_raw);
-  float4* xbuf = reinterpret_cast<float4*>(xs + ncap);
-  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * kYWarpF4);
-  float2* tw_s = reinterpret_cast<float2*>(logmel_s + kTtsFrames * M);
+  const int hop = p.hop;
+  const int nbuf = tts_buf_floats(hop);
+  float* bufs = reinterpret_cast<float*>(smem_raw);
+  float4* xbuf = reinterpret_cast<float4*>(bufs + kWarps * nbuf);
+  float2* tw_s = reinterpret_cast<float2*>(xbuf + kWarps * kYWarpF4);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw_s + kTw2Total);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = tid & (kGroup - 1), g = lane >> 4;
-  const int u = blockIdx.y;
-  const long long N = p.lengths[u];
-  const int T = (int)(N / hop);
-  if (blockIdx.x == 0 && tid == 0 && p.mel_lens) p.mel_lens[u] = T;
-  const int f0 = blockIdx.x * kTtsFrames;
-  if (f0 >= T) return;
-  const int F = min(kTtsFrames, T - f0);
-  const float* x = p.wave + p.offsets[u];
-  const int pad = (kTtsNfft - hop) / 2;
 
   for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
-  // stage with reflect padding: padded[s] = x[reflect(s - pad)]
-  {
-    const int n_s = (F - 1) * hop + kTtsNfft;
-    const long long s0 = (long long)f0 * hop - pad;
-    for (int i = tid; i < n_s; i += kCtaThreads) {
-      long long s = s0 + i;
-      if (s < 0) s = -s;
-      if (s >= N) s = 2 * (N - 1) - s;
-      s = s < 0 ? 0 : s;
-      xs[i] = x[s];
-    }
+  if (lane == 0) {
+    mbar_init(bars + warp, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // periodic Hann of this thread's samples n = 32 i + 2 j (+ 1): cos(2 pi n / 1024) = cos(a_i) cos(b) - sin(a_i) sin(b)
   f2 cb, sb;
@@ -162,8 +241,10 @@ tts_mel_kernel(const TtsParams p) {
     cb = make_float2(c0, c1);
     sb = make_float2(s0, s1);
   }
-  __syncthreads();
+  __syncthreads();   // the only CTA-wide barrier: the twiddle tables and the mbarriers
 
+  float* buf = bufs + warp * nbuf;
+  unsigned long long* bar = bars + warp;
   float4* yg = xbuf + warp * kYWarpF4 + g * kYGroupF4;
   float2* mag = reinterpret_cast<float2*>(xbuf + warp * kYWarpF4);   // this warp's magnitudes (frame of group 0, of group 1)
   const float2* tw_row = fft_twiddle_row<32>(tw_s, j, g);
@@ -177,20 +258,68 @@ tts_mel_kernel(const TtsParams p) {
     w32r = cs; w32i = -sn;
   }
 
-  for (int pair = warp; 2 * pair < F; pair += kWarps) {
-    const int f = 2 * pair + g;          // tile-local frame of this group
-    const bool valid = f < F;
+  // Work distribution: warp w of the grid takes pairs w, w + W, w + 2 W, ...  The clip of a pair is found by walking
+  // the prefix sums forward, 32 entries per step (one load per lane and a ballot).
+  const int W = gridDim.x * kWarps;
+  const int total = __ldg(p.pair_begin + p.batch);
+  int w = blockIdx.x * kWarps + warp;
+  if (w >= total) return;
+  int u = 0, pb_u = 0;
+  auto seek = [&](int wq, int& uu, int& pb) {   // uu, pb: clip with pair_begin <= wq < next pair_begin
+    while (true) {
+      const int idx = uu + 1 + lane;
+      const int v = __ldg(p.pair_begin + min(idx, p.batch));
+      const unsigned m = __ballot_sync(0xffffffffu, idx <= p.batch && wq >= v);
+      const int n = __popc(m);
+      if (n) pb = __shfl_sync(0xffffffffu, v, n - 1);
+      uu += n;
+      if (n < 32) break;
+    }
+  };
+  seek(w, u, pb_u);
+  int in_flight;
+  {
+    const TtsUtt ut = p.utts[u];
+    in_flight = tts_issue_copy(p, tts_tma_source(p, ut, w - pb_u), lane, buf, bar);
+  }
+  unsigned phase = 0;
+  const int pad = (kTtsNfft - hop) / 2;
+  const bool cap_even = (p.frames_cap & 1) == 0;
+
+  while (true) {
+    const TtsUtt ut = p.utts[u];
+    const int pair = w - pb_u;
+    // the next pair of this warp
+    const int wn = w + W;
+    const bool have_next = wn < total;
+    int un = u, pbn = pb_u;
+    long long g0n = -1;
+    if (have_next) {
+      seek(wn, un, pbn);
+      const TtsUtt utn = p.utts[un];
+      g0n = tts_tma_source(p, utn, wn - pbn);
+    }
+
+    int a_off = 0;
+    if (in_flight) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      a_off = in_flight - 1;
+    } else {
+      tts_fill_generic(p.wave + ut.off, ut.N, 2ll * pair * hop - pad, hop + kTtsNfft, lane, buf);
+      __syncwarp();
+    }
     f2 ar[16], ai[16], c0r, c0i, u_alt;
     {
       f2 zr[16], zi[16], y0, y16;
       {
         f2 y[32];
-        const float2* xf = reinterpret_cast<const float2*>(xs + (valid ? f : 0) * hop) + j;   // hop is even: 8-byte aligned
+        const float2* xf = reinterpret_cast<const float2*>(buf + a_off + g * hop) + j;   // hop, a_off even: 8-byte aligned
         static_for<0, 32>([&](auto ic) {
           constexpr int i = decltype(ic)::value;
           constexpr float ca = (float)(0.5 * ct_cos2pi(i, 32)), sa = (float)(0.5 * ct_sin2pi(i, 32));
-          const f2 w = fma2s(sb, sa, fma2s(cb, -ca, make_float2(0.5f, 0.5f)));
-          y[i] = mul2(xf[16 * i], w);
+          const f2 wv = fma2s(sb, sa, fma2s(cb, -ca, make_float2(0.5f, 0.5f)));
+          y[i] = mul2(xf[16 * i], wv);
         });
         static_for<0, 16>([&](auto ic) {
           constexpr int m = decltype(ic)::value;
@@ -198,9 +327,11 @@ tts_mel_kernel(const TtsParams p) {
           zi[bitrev<16>(m)] = y[2 * m + 1];
         });
       }
+      __syncwarp();   // every lane holds its samples (the buffer is free for the next pair's copy) and is done with the
+                      // previous pair's magnitudes, which alias the transpose buffers
+      in_flight = tts_issue_copy(p, g0n, lane, buf, bar);
       fft_dit2<16>(zr, zi);
       real32_split2(zr, zi, y0, y16);
-      __syncwarp();   // the previous pair's magnitudes (aliased buffer) have been consumed by the mel stage
       tts_stage2(zr, zi, y0, y16, yg, tw_row, c0_row, j, g, ar, ai, c0r, c0i, u_alt);
     }
     // ---- recombination: lane .x = 2E[k], lane .y = 2O[k] at k = col + 32 k2;  2X[k] = 2E + W^k 2O,
@@ -215,24 +346,27 @@ tts_mel_kernel(const TtsParams p) {
         const float tr = fmaf(orr, wr, -(oi * wi)), ti = fmaf(orr, wi, oi * wr);
         const float pr = er + tr, pi = ei + ti, qr = er - tr, qi = ei - ti;
         const int k = col + 32 * k2;
-        mg[2 * k] = sqrtf(fmaf(0.25f, fmaf(pr, pr, pi * pi), p.mag_eps));
-        if (c != 0) mg[2 * (512 - k)] = sqrtf(fmaf(0.25f, fmaf(qr, qr, qi * qi), p.mag_eps));
+        mg[2 * k] = fast_sqrt(fmaf(0.25f, fmaf(pr, pr, pi * pi), p.mag_eps));
+        if (c != 0) mg[2 * (512 - k)] = fast_sqrt(fmaf(0.25f, fmaf(qr, qr, qi * qi), p.mag_eps));
       });
       if ((lane & 1) == 0) {   // column 0 of the lane's own group: bins 32 t0 and 512 - 32 t0, and bin 256
         float* mo = reinterpret_cast<float*>(mag) + g;
         const float er = c0r.x, ei = c0i.x, orr = c0r.y, oi = c0i.y;
         const float tr = fmaf(orr, w32r, -(oi * w32i)), ti = fmaf(orr, w32i, oi * w32r);
         const float pr = er + tr, pi = ei + ti, qr = er - tr, qi = ei - ti;
-        mo[2 * (32 * t0)] = sqrtf(fmaf(0.25f, fmaf(pr, pr, pi * pi), p.mag_eps));
-        mo[2 * (512 - 32 * t0)] = sqrtf(fmaf(0.25f, fmaf(qr, qr, qi * qi), p.mag_eps));
-        if (t0 == 0) mo[2 * 256] = sqrtf(fmaf(u_alt.x, u_alt.x, u_alt.y * u_alt.y) + p.mag_eps);   // E[256] - i O[256]
+        mo[2 * (32 * t0)] = fast_sqrt(fmaf(0.25f, fmaf(pr, pr, pi * pi), p.mag_eps));
+        mo[2 * (512 - 32 * t0)] = fast_sqrt(fmaf(0.25f, fmaf(qr, qr, qi * qi), p.mag_eps));
+        if (t0 == 0) mo[2 * 256] = fast_sqrt(fmaf(u_alt.x, u_alt.x, u_alt.y * u_alt.y) + p.mag_eps);   // E[256] - i O[256]
       }
     }
     __syncwarp();
 
-    // ---- mel over magnitudes: lane <-> interval (bank-matched lanes, as in the ASR mel stage), both frames at once
+    // ---- mel over magnitudes: lane <-> interval (bank-matched lanes, as in the ASR mel stage), both frames at once;
+    //      the lane that holds filter iv stores (frame 2 pair, frame 2 pair + 1) of row iv
     {
       const MelTab& mel = p.mel_tab;
+      float* out_u = p.mel + (long long)u * p.n_mels * p.frames_cap + 2 * pair;
+      const bool both = cap_even && 2 * pair + 1 < ut.T;
 #pragma unroll 1
       for (int r = 0; r < mel.rounds; ++r) {
         int cnt = mel.cnt[0], base = mel.base[0];
@@ -246,28 +380,27 @@ tts_mel_kernel(const TtsParams p) {
         f2 up = make_float2(0.f, 0.f), dn = make_float2(0.f, 0.f);
 #pragma unroll 4
         for (int q = 0; q < cnt; ++q) {
-          const float2 w = __ldg(wt + 32 * q);
+          const float2 wq = __ldg(wt + 32 * q);
           const float2 sv = p0[q];
-          up = fma2s(sv, w.x, up);
-          dn = fma2s(sv, w.y, dn);
+          up = fma2s(sv, wq.x, up);
+          dn = fma2s(sv, wq.y, dn);
         }
         const float e0 = up.x + __shfl_sync(0xffffffffu, dn.x, partner);
         const float e1 = up.y + __shfl_sync(0xffffffffu, dn.y, partner);
         if (word >> 31) {
-          const int fr = 2 * pair;
-          if (fr < F) logmel_s[fr * M + iv] = logf(fmaxf(e0, p.log_floor));
-          if (fr + 1 < F) logmel_s[(fr + 1) * M + iv] = logf(fmaxf(e1, p.log_floor));
+          const float l0 = fast_ln(fmaxf(e0, p.log_floor)), l1 = fast_ln(fmaxf(e1, p.log_floor));
+          float* o = out_u + (long long)iv * p.frames_cap;
+          if (both) {
+            *reinterpret_cast<float2*>(o) = make_float2(l0, l1);
+          } else {
+            o[0] = l0;
+            if (2 * pair + 1 < ut.T) o[1] = l1;
+          }
         }
       }
     }
-  }
-  __syncthreads();
-
-  // mel-major output: out[u][m][f0 + f]
-  float* out = p.mel + (long long)u * M * p.frames_cap + f0;
-  for (int idx = tid; idx < M * kTtsFrames; idx += kCtaThreads) {
-    const int m = idx / kTtsFrames, f = idx - m * kTtsFrames;
-    if (f < F) out[(long long)m * p.frames_cap + f] = logmel_s[f * M + m];
+    if (!have_next) break;
+    w = wn; u = un; pb_u = pbn;
   }
 }
 
