@@ -10,50 +10,27 @@ int stream_layout(const b200fe_handle* h, int n_streams, int max_chunk, StreamLa
   lay.cache_cap = h->cfg.lfr_m - 1 > 1 ? h->cfg.lfr_m - 1 : 1;
   lay.n_mels = h->cfg.n_mels;
   nf_max = (max_chunk - 1) / h->S + 1;
+  lay.frames_cap = lay.cache_cap + nf_max;
   e_cap = ((h->L - 1 + max_chunk + 8) + 3) & ~3;
-  smem = stream_smem_bytes(e_cap, nf_max, lay.cache_cap, h->cfg.n_mels, warp_kernel_fits(h->L, h->S));
+  smem = stream_smem_bytes(e_cap, warp_kernel_fits(h->L, h->S));
   return 0;
-}
-
-// Warps per stream-CTA for a tick over n streams: the narrower CTA (2 warps, half the shared memory, 4 CTAs per SM) when
-// it saves a wave - e.g. 512 streams on 148 SMs: 4-warp CTAs need 1.15 waves of 444, 2-warp CTAs one wave of 592.  A
-// 2-warp CTA takes about 1.6x as long as a 4-warp one (measured, bench_streaming.py).  B200FE_STREAM_WARPS=2|4 overrides.
-int stream_cta_warps(const b200fe_handle* h, int n, size_t smem4, size_t smem2) {
-  if (const char* e = getenv("B200FE_STREAM_WARPS")) {
-    if (e[0] == '2') return 2;
-    if (e[0] == '4') return 4;
-  }
-  const size_t per_sm = 227 * 1024;
-  const long long c4 = std::min<long long>(3, (long long)(per_sm / (smem4 + 1024))), c2 = std::min<long long>(4, (long long)(per_sm / (smem2 + 1024)));
-  if (c4 < 1 || c2 < 1) return 4;
-  const long long w4 = (n + h->n_sms * c4 - 1) / (h->n_sms * c4), w2 = (n + h->n_sms * c2 - 1) / (h->n_sms * c2);
-  return (double)w2 * 1.6 < (double)w4 * 1.0 ? 2 : 4;
 }
 
 template <int NROWS, bool EXACT, class MELS>
 int launch_stream(b200fe_handle* h, const StreamParams& p, size_t smem, bool dither, cudaStream_t st) {
-#define LAUNCHS(DI, PQ, W)                                                                            \
+#define LAUNCHS(DI, PQ)                                                                               \
   do {                                                                                                \
-    auto k = stream_push_kernel<NROWS, EXACT, DI, MELS, PQ, W>;                                       \
-    CUDA_TRY(h, allow_dynamic_smem((const void*)k, smem_w));                                          \
-    k<<<p.n, 32 * W, smem_w, st>>>(p);                                                                \
+    auto k = stream_push_kernel<NROWS, EXACT, DI, MELS, PQ>;                                          \
+    CUDA_TRY(h, allow_dynamic_smem((const void*)k, smem));                                            \
+    k<<<p.n, kCtaThreads, smem, st>>>(p);                                                             \
   } while (0)
-  const bool per_quad = warp_kernel_fits(h->L, h->S);   // every warp fetches its own quads (3 CTAs per SM)
-  size_t smem_w = smem;
-  int warps = 4;
-  if (per_quad) {
-    const size_t smem2 = stream_smem_bytes(p.e_cap, p.nf_max, p.lay.cache_cap, p.n_mels, true, 2);
-    warps = stream_cta_warps(h, p.n, smem, smem2);
-    if (warps == 2) smem_w = smem2;
-  }
+  const bool per_quad = warp_kernel_fits(h->L, h->S);   // every warp fetches its own quads (4 CTAs per SM)
 #ifdef B200FE_BENCH_ONLY
   if (!per_quad || dither) return fail(h, B200FE_E_UNSUPPORTED, "bench-only build");
-  if (warps == 2) LAUNCHS(false, true, 2); else LAUNCHS(false, true, 4);
+  LAUNCHS(false, true);
 #else
-  if (per_quad) {
-    if (warps == 2) { if (dither) LAUNCHS(true, true, 2); else LAUNCHS(false, true, 2); }
-    else            { if (dither) LAUNCHS(true, true, 4); else LAUNCHS(false, true, 4); }
-  } else          { if (dither) LAUNCHS(true, false, 4); else LAUNCHS(false, false, 4); }
+  if (per_quad) { if (dither) LAUNCHS(true, true); else LAUNCHS(false, true); }
+  else          { if (dither) LAUNCHS(true, false); else LAUNCHS(false, false); }
 #endif
 #undef LAUNCHS
   CUDA_TRY(h, cudaGetLastError());

@@ -18,11 +18,12 @@ namespace b200fe {
 struct StreamLayout {
   int n_streams;
   int carry_cap;    // floats per stream (>= frame_len - 1, multiple of 4)
-  int cache_cap;    // frames per stream: max(lfr_m - 1, 1)
+  int cache_cap;    // frames a stream carries from tick to tick: max(lfr_m - 1, 1)
+  int frames_cap;   // frames of a stream's log-mel buffer: cache_cap + the frames one push can create
   int n_mels;
   __host__ __device__ size_t counters_bytes() const { return ((size_t)4 * n_streams * sizeof(int) + 255) & ~(size_t)255; }
   __host__ __device__ size_t carry_bytes() const { return ((size_t)n_streams * carry_cap * sizeof(float) + 255) & ~(size_t)255; }
-  __host__ __device__ size_t cache_bytes() const { return ((size_t)n_streams * cache_cap * n_mels * sizeof(float) + 255) & ~(size_t)255; }
+  __host__ __device__ size_t cache_bytes() const { return ((size_t)n_streams * frames_cap * n_mels * sizeof(float) + 255) & ~(size_t)255; }
   __host__ __device__ size_t total_bytes() const { return counters_bytes() + carry_bytes() + cache_bytes(); }
   __host__ __device__ int* counters(void* base) const { return reinterpret_cast<int*>(base); }
   __host__ __device__ float* carry(void* base) const { return reinterpret_cast<float*>((char*)base + counters_bytes()); }
@@ -62,17 +63,16 @@ struct StreamParams {
 };
 
 // per_quad: every warp fetches the samples of its quads itself (3.5 KB per warp) instead of the CTA staging the whole
-// [carry | chunk] buffer: 74 KB instead of 100 KB for a 600 ms chunk, i.e. 3 stream-CTAs per SM instead of 2.
-__host__ __device__ inline size_t stream_smem_bytes(int e_cap, int nf_max, int cache_cap, int n_mels, bool per_quad,
-                                                    int warps = kWarps) {
+// [carry | chunk] buffer.  The log-mel frames of the tick go to the stream's buffer in the state slab (L2-resident), not
+// to shared memory: 53 KB per 4-warp CTA, i.e. 4 stream-CTAs (16 warps) per SM and 592 streams per wave.
+__host__ __device__ inline size_t stream_smem_bytes(int e_cap, bool per_quad) {
   size_t b = 0;
   if (per_quad) {
-    b += (size_t)warps * kQuadBuf * 4;
+    b += (size_t)kWarps * kQuadBuf * 4;
   } else {
     b += (size_t)e_cap * 4;
   }
-  b += (size_t)warps * kYWarpF4 * 16;
-  b += (size_t)(cache_cap + nf_max) * n_mels * 4;
+  b += (size_t)kWarps * kYWarpF4 * 16;
   b += kTw2Total * 8;
   return b;
 }
@@ -116,18 +116,14 @@ __global__ void stream_reset_kernel(void* state, StreamLayout lay, const int* id
   c[3 * lay.n_streams + s] = 0;
 }
 
-// WARPS: warps per stream-CTA.  4 is the default; 2 halves the CTA's shared memory (49 KB for 600 ms chunks: 4 CTAs per SM)
-// so that 445..592 streams still run as ONE wave on 148 SMs instead of a full wave plus a mostly empty one.
-template <int NROWS, bool EXACT, bool DITHER, class MELS, bool PERQUAD, int WARPS = kWarps>
-__global__ void __launch_bounds__(32 * WARPS, PERQUAD ? (WARPS == 2 ? 4 : 3) : 2)
+template <int NROWS, bool EXACT, bool DITHER, class MELS, bool PERQUAD>
+__global__ void __launch_bounds__(kCtaThreads, PERQUAD ? 4 : 2)
 stream_push_kernel(const StreamParams p) {
-  constexpr int kWarps = WARPS;                 // shadows the namespace constants inside this kernel
-  constexpr int kCtaThreads = 32 * WARPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* e_s = reinterpret_cast<float*>(smem_raw);                       // PERQUAD: [kWarps][kQuadBuf] sample buffers
   float4* xbuf = reinterpret_cast<float4*>(e_s + (PERQUAD ? kWarps * kQuadBuf : p.e_cap));
-  float* logmel_s = reinterpret_cast<float*>(xbuf + kWarps * kYWarpF4);
-  float2* tw_s = reinterpret_cast<float2*>(logmel_s + (p.lay.cache_cap + p.nf_max) * p.n_mels);
+  float2* tw_s = reinterpret_cast<float2*>(xbuf + kWarps * kYWarpF4);
+  __shared__ float red_s[2 * kWarps];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = tid & (kGroup - 1), grp_in_warp = lane >> 4;
@@ -146,10 +142,13 @@ stream_push_kernel(const StreamParams p) {
   const int NS = p.lay.n_streams;
   const int carry_len = cnt[sid], t_seen = cnt[NS + sid], rows_done = cnt[2 * NS + sid], cache_len = cnt[3 * NS + sid];
   float* carry = p.lay.carry(p.state) + (size_t)sid * p.lay.carry_cap;
-  float* cache = p.lay.cache(p.state) + (size_t)sid * p.lay.cache_cap * M;
+  // the stream's log-mel buffer: rows 0 .. cache_len-1 are the splice frames of earlier ticks, this tick's frames follow
+  float* logmel_s = p.lay.cache(p.state) + (size_t)sid * p.lay.frames_cap * M;
   const float* chunk = p.chunks + (long long)b * p.chunk_stride;
   const int n_new = min(max(p.chunk_lens[b], 0), p.max_chunk);
   const bool fin = p.is_final && p.is_final[b];
+  // the whole chunk is on its way into L2 while the CTA sets up: the quads' sample fetches then see L2 latency only
+  for (int i = 32 * tid; i < n_new; i += 32 * kCtaThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(chunk + i));
 
   for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   MelTab mel;
@@ -158,9 +157,6 @@ stream_push_kernel(const StreamParams p) {
   for (int r = 0; r < kMelRounds; ++r) { mel.cnt[r] = p.mel_cnt[r]; mel.base[r] = p.mel_base[r]; }
   float win[NROWS + 1];
   load_window_taps<NROWS>(win, p.window, j, grp_in_warp);
-
-  // splice frames of earlier ticks come first in the tile's log-mel buffer
-  for (int i = tid; i < cache_len * M; i += kCtaThreads) logmel_s[i] = cache[i];
 
   const int n = carry_len + n_new;
   const int nf = n >= L ? (n - L) / S + 1 : 0;
@@ -244,26 +240,44 @@ stream_push_kernel(const StreamParams p) {
     rows_total = rows_done + n_emit;
   }
   {
+    // (row, 128-bit piece) pairs dealt to the threads, four at a time: all loads of a batch are issued before its
+    // arithmetic and stores (the log-mel buffer is in L2, not in shared memory)
     float* out = p.feats + (long long)b * p.rows_cap * D;
     const int D4 = D >> 2, M4 = M >> 2;
-    for (int c4 = tid; c4 < D4; c4 += kCtaThreads) {
-      const int cj = c4 / M4, cd = c4 - cj * M4;
-      float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (p.cmvn) {
-        sh = *reinterpret_cast<const float4*>(p.cmvn + 4 * c4);
-        sc = *reinterpret_cast<const float4*>(p.cmvn + D + 4 * c4);
+    const int total4 = n_emit * D4;
+    constexpr int kBatch = 4;
+    for (int i0 = tid; i0 < total4; i0 += kBatch * kCtaThreads) {
+      float4 v[kBatch], sh[kBatch], sc[kBatch];
+      int dst[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int idx = i0 + k * kCtaThreads;
+        dst[k] = -1;
+        if (idx < total4) {
+          const int r = idx / D4, c4 = idx - r * D4;
+          const int cj = c4 / M4, cd = c4 - cj * M4;
+          int f = p.lfr_n * (rows_done + r) + cj - lfr_left;
+          f = min(max(f, 0), T - 1) - base_abs;
+          v[k] = __ldcg(reinterpret_cast<const float4*>(logmel_s + f * M + 4 * cd));
+          sh[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          sc[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.cmvn) {
+            sh[k] = __ldg(reinterpret_cast<const float4*>(p.cmvn + 4 * c4));
+            sc[k] = __ldg(reinterpret_cast<const float4*>(p.cmvn + D + 4 * c4));
+          }
+          dst[k] = r * D + 4 * c4;
+        }
       }
-      for (int r = 0; r < n_emit; ++r) {
-        int f = p.lfr_n * (rows_done + r) + cj - lfr_left;
-        f = min(max(f, 0), T - 1) - base_abs;
-        const float4 v = *reinterpret_cast<const float4*>(logmel_s + f * M + 4 * cd);
-        float4 o;
-        o.x = (v.x + sh.x) * sc.x;
-        o.y = (v.y + sh.y) * sc.y;
-        o.z = (v.z + sh.z) * sc.z;
-        o.w = (v.w + sh.w) * sc.w;
-        *reinterpret_cast<float4*>(out + (long long)r * D + 4 * c4) = o;
-      }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k)
+        if (dst[k] >= 0) {
+          float4 o;
+          o.x = (v[k].x + sh[k].x) * sc[k].x;
+          o.y = (v[k].y + sh[k].y) * sc[k].y;
+          o.z = (v[k].z + sh[k].z) * sc[k].z;
+          o.w = (v[k].w + sh[k].w) * sc[k].w;
+          *reinterpret_cast<float4*>(out + dst[k]) = o;
+        }
     }
   }
   // frames the next rows still need (always at least the newest frame, for right replication on the final flush)
@@ -272,30 +286,50 @@ stream_push_kernel(const StreamParams p) {
   keep_from = max(keep_from, base_abs);
   keep_from = max(keep_from, T - p.lay.cache_cap);
   const int new_cache = T > 0 ? T - keep_from : 0;
-  for (int i = tid; i < new_cache * M; i += kCtaThreads) cache[i] = logmel_s[(keep_from - base_abs) * M + i];
+  // ... move to the front of the buffer, one CTA-wide slice at a time (the slices a step writes were read before its
+  // barrier, the ones later steps read lie behind it; the first barrier also orders the row reads above before any write)
+  if (keep_from > base_abs)
+    for (int i0 = 0; i0 < new_cache * M; i0 += kCtaThreads) {
+      const int i = i0 + tid;
+      float v = 0.f;
+      if (i < new_cache * M) v = __ldcg(logmel_s + (keep_from - base_abs) * M + i);
+      __syncthreads();
+      if (i < new_cache * M) logmel_s[i] = v;
+    }
 
   // The reference's per-chunk energy gate (R:voice-service/app/services/voice_interface.py:1569-1578: mean |x| and
   // max |x| of the chunk against two thresholds) as a by-product of the tick: the chunk was just read by the framing
   // pass (L2-resident), the CTA reduces it once more and returns both numbers next to the rows.
   if (p.chunk_stats) {
     float sa = 0.f, mx = 0.f;
-    for (int i = tid; i < n_new; i += kCtaThreads) {
-      const float a = fabsf(chunk[i]);
-      sa += a;
-      mx = fmaxf(mx, a);
+    const int head = min(n_new, (int)((4 - ((reinterpret_cast<uintptr_t>(chunk) >> 2) & 3)) & 3));   // up to the 16-byte grid
+    const int n4 = (n_new - head) >> 2;
+    auto acc = [&](float x) { const float a = fabsf(x); sa += a; mx = fmaxf(mx, a); };
+    if (tid < head) acc(chunk[tid]);
+    if (tid < n_new - head - 4 * n4) acc(chunk[head + 4 * n4 + tid]);
+    const float4* c4p = reinterpret_cast<const float4*>(chunk + head);
+    constexpr int kU = 8;
+    for (int i0 = tid; i0 < n4; i0 += kU * kCtaThreads) {
+      float4 x[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const int i = i0 + k * kCtaThreads;
+        x[k] = i < n4 ? __ldg(c4p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < kU; ++k) { acc(x[k].x); acc(x[k].y); acc(x[k].z); acc(x[k].w); }
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       sa += __shfl_xor_sync(0xffffffffu, sa, o);
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    __syncthreads();                       // logmel_s is free: every thread is past the row / splice copies above
-    if (lane == 0) { logmel_s[warp] = sa; logmel_s[kWarps + warp] = mx; }
+    if (lane == 0) { red_s[warp] = sa; red_s[kWarps + warp] = mx; }
     __syncthreads();
     if (tid == 0) {
       double tot = 0.0;
       float m = 0.f;
-      for (int w = 0; w < kWarps; ++w) { tot += (double)logmel_s[w]; m = fmaxf(m, logmel_s[kWarps + w]); }
+      for (int w = 0; w < kWarps; ++w) { tot += (double)red_s[w]; m = fmaxf(m, red_s[kWarps + w]); }
       p.chunk_stats[2 * b] = n_new > 0 ? (float)(tot / (double)n_new) : 0.f;
       p.chunk_stats[2 * b + 1] = m;
     }

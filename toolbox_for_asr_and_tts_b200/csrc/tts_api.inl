@@ -7,6 +7,7 @@ struct b200fe_tts {
   int* d_mel_lo = nullptr;
   int mel_rounds = 0, mel_cnt[kMelRounds] = {0}, mel_base[kMelRounds] = {0};
   size_t smem = 0;
+  bool mel_fixed = false;       // the interval table has the shape the kernel is specialised for (MelShapeTts)
   int n_sms = 0;
   TtsUtt* d_utts = nullptr;     // launch workspace, grown on demand: [cap] clip descriptors, [cap + 1] pair prefix sums
   int* d_pair_begin = nullptr;
@@ -78,6 +79,8 @@ int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_m
     delete t;
     return failc(B200FE_E_UNSUPPORTED, why);
   }
+  t->mel_fixed = t->mel_rounds == MelShapeTts::kRounds;
+  for (int r = 0; r < MelShapeTts::kRounds; ++r) t->mel_fixed = t->mel_fixed && t->mel_cnt[r] == MelShapeTts::cnt(r) && t->mel_base[r] == MelShapeTts::base(r);
   for (int m = 0; m < n_mels; ++m)
     if (bank[(size_t)m * (n_fft / 2 + 1) + n_fft / 2] != 0.f) { delete t; return failc(B200FE_E_UNSUPPORTED, "the Nyquist bin must not carry mel weight"); }
   // stage-2 twiddles + column-0 table of the packed 512-point real FFT (same tables as b200fe_create), W1024^col
@@ -137,7 +140,8 @@ int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total,
   p.mel_tab.w = t->d_mel_w; p.mel_tab.lo = t->d_mel_lo; p.mel_tab.rounds = t->mel_rounds;
   for (int r = 0; r < kMelRounds; ++r) { p.mel_tab.cnt[r] = t->mel_cnt[r]; p.mel_tab.base[r] = t->mel_base[r]; }
   p.utts = t->d_utts; p.pair_begin = t->d_pair_begin;
-  if (allow_dynamic_smem((const void*)tts_mel_kernel, t->smem) != cudaSuccess) return B200FE_E_CUDA;
+  if (allow_dynamic_smem((const void*)tts_mel_kernel<MelShapeTts>, t->smem) != cudaSuccess ||
+      allow_dynamic_smem((const void*)tts_mel_kernel<MelShapeRuntime>, t->smem) != cudaSuccess) return B200FE_E_CUDA;
   tts_prep_kernel<<<1, 1024, 0, st>>>((const long long*)offsets_dev, (const long long*)lengths_dev, batch, t->hop, t->d_utts,
                                       t->d_pair_begin, (long long*)mel_lens_dev);
   tts_pad_kernel<<<dim3(8, batch), 256, 0, st>>>((const long long*)lengths_dev, t->hop, t->n_mels, mel_dev, frames_cap);
@@ -145,7 +149,9 @@ int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total,
     // persistent warps: as many CTAs as stay resident, but not more warps than an upper bound of the pair count
     const long long pairs_ub = (long long)batch * ((max_frames + 1) / 2);
     const long long ctas = std::min<long long>((long long)t->n_sms * B200FE_TTS_CTAS, (pairs_ub + kWarps - 1) / kWarps);
-    tts_mel_kernel<<<(unsigned)std::max<long long>(ctas, 1), kCtaThreads, t->smem, st>>>(p);
+    const unsigned grid = (unsigned)std::max<long long>(ctas, 1);
+    if (t->mel_fixed) tts_mel_kernel<MelShapeTts><<<grid, kCtaThreads, t->smem, st>>>(p);
+    else tts_mel_kernel<MelShapeRuntime><<<grid, kCtaThreads, t->smem, st>>>(p);
   }
   return cudaGetLastError() == cudaSuccess ? B200FE_OK : B200FE_E_CUDA;
 }

@@ -62,9 +62,12 @@ struct TtsParams {
 
 // floats of a warp's sample buffer: a pair's n_fft + hop samples, placed up to 2 floats behind a 16-byte boundary
 __host__ __device__ inline int tts_buf_floats(int hop) { return ((hop + kTtsNfft + 3) & ~3) + 4; }
+constexpr int kTtsThreadConsts = 4;   // float2 per thread: Hann angle-addition pair (cos b, sin b), W1024^col, W32^t0
 __host__ __device__ inline size_t tts_smem_bytes(int hop) {
-  return (size_t)kWarps * tts_buf_floats(hop) * 4 + (size_t)kWarps * kYWarpF4 * 16 + (size_t)kTw2Total * 8 + (size_t)kWarps * 8;
+  return (size_t)kWarps * tts_buf_floats(hop) * 4 + (size_t)kWarps * kYWarpF4 * 16 + (size_t)kTw2Total * 8 + (size_t)kWarps * 8 +
+         (size_t)kCtaThreads * kTtsThreadConsts * 8;
 }
+using MelShapeTts = MelShapeFixed<3, 3, 10, 21>;   // 80 Slaney filters 0..12 kHz over the 513 bins of a 1024-point FFT at 24 kHz
 
 // One block: frames, pair prefix sums and clip descriptors of the batch; also the frame counts handed to the caller.
 __global__ void __launch_bounds__(1024)
@@ -184,6 +187,44 @@ __device__ __forceinline__ void tts_stage2(const f2 (&zr)[16], const f2 (&zi)[16
   __syncwarp();   // every lane has consumed the transpose buffers: the magnitudes may overwrite them
 }
 
+// One round of the interval mel over the pair's magnitudes (float2: frame of group 0, frame of group 1); the lane that
+// holds filter iv stores (frame 2 pair, frame 2 pair + 1) of row iv.  CNT >= 0: compile-time trip count, fully unrolled.
+template <int CNT>
+__device__ __forceinline__ void tts_mel_round(const MelTab& mel, int r, int cnt_rt, int base, const float2* mag, int lane,
+                                              float log_floor, float* out_u, long long frames_cap, bool both, bool second) {
+  const int cnt = CNT >= 0 ? CNT : cnt_rt;
+  const unsigned word = (unsigned)__ldg(mel.lo + 32 * r + lane);
+  const int lo = (int)(word & 0xfffu), partner = (int)((word >> 12) & 31u), iv = (int)((word >> 17) & 0xffu);
+  const float2* wt = mel.w + (base * 32 + lane);
+  const float2* p0 = mag + lo;
+  f2 up = make_float2(0.f, 0.f), dn = make_float2(0.f, 0.f);
+  auto body = [&](int q) {
+    const float2 wq = __ldg(wt + 32 * q);
+    const float2 sv = p0[q];
+    up = fma2s(sv, wq.x, up);
+    dn = fma2s(sv, wq.y, dn);
+  };
+  if constexpr (CNT >= 0) {
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) body(q);
+  } else {
+#pragma unroll 4
+    for (int q = 0; q < cnt; ++q) body(q);
+  }
+  const float e0 = up.x + __shfl_sync(0xffffffffu, dn.x, partner);
+  const float e1 = up.y + __shfl_sync(0xffffffffu, dn.y, partner);
+  if (word >> 31) {
+    const float l0 = fast_ln(fmaxf(e0, log_floor)), l1 = fast_ln(fmaxf(e1, log_floor));
+    float* o = out_u + (long long)iv * frames_cap;
+    if (both) {
+      *reinterpret_cast<float2*>(o) = make_float2(l0, l1);
+    } else {
+      o[0] = l0;
+      if (second) o[1] = l1;
+    }
+  }
+}
+
 // Lanes of a warp: the samples of pair `pair` of a clip into buf (buf[i] = padded[2 pair hop + i], reflection resolved)
 __device__ __forceinline__ void tts_fill_generic(const float* x, long long N, long long s0, int n, int lane, float* buf) {
   for (int i = lane; i < n; i += 32) {
@@ -214,6 +255,7 @@ __device__ __forceinline__ int tts_issue_copy(const TtsParams& p, long long g0, 
   return ok ? 1 + quad_a_off<float>(p.wave, g0) : 0;
 }
 
+template <class MELS>
 __global__ void __launch_bounds__(kCtaThreads, B200FE_TTS_CTAS)
 tts_mel_kernel(const TtsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -223,9 +265,13 @@ tts_mel_kernel(const TtsParams p) {
   float4* xbuf = reinterpret_cast<float4*>(bufs + kWarps * nbuf);
   float2* tw_s = reinterpret_cast<float2*>(xbuf + kWarps * kYWarpF4);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw_s + kTw2Total);
+  // per-thread constants live in shared memory and are re-read where they are used (volatile): kept in registers across
+  // the loop they are spilled, and the local-memory footprint of an SM does not stay in L1
+  volatile float2* tc = reinterpret_cast<volatile float2*>(bars + kWarps) + threadIdx.x;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = tid & (kGroup - 1), g = lane >> 4;
+  const int c = lane >> 1, g2 = lane & 1, col = c == 0 ? 16 : c, t0 = (lane >> 1) & 7;
 
   for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   if (lane == 0) {
@@ -233,13 +279,16 @@ tts_mel_kernel(const TtsParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // periodic Hann of this thread's samples n = 32 i + 2 j (+ 1): cos(2 pi n / 1024) = cos(a_i) cos(b) - sin(a_i) sin(b)
-  f2 cb, sb;
   {
-    float s0, c0, s1, c1;
+    float s0, c0, s1, c1, sn, cs;
     sincospif(2.0f * (float)(2 * j) / 1024.0f, &s0, &c0);
     sincospif(2.0f * (float)(2 * j + 1) / 1024.0f, &s1, &c1);
-    cb = make_float2(c0, c1);
-    sb = make_float2(s0, s1);
+    sincospif(2.0f * (float)t0 / 32.0f, &sn, &cs);
+    const float2 wc = __ldg(p.w1024 + col);                  // W1024^col = (cos, -sin)
+    tc[0 * kCtaThreads].x = c0; tc[0 * kCtaThreads].y = c1;   // cos b (even sample, odd sample)
+    tc[1 * kCtaThreads].x = s0; tc[1 * kCtaThreads].y = s1;   // sin b
+    tc[2 * kCtaThreads].x = wc.x; tc[2 * kCtaThreads].y = wc.y;
+    tc[3 * kCtaThreads].x = cs; tc[3 * kCtaThreads].y = -sn;  // W32^t0 for the column-0 bins
   }
   __syncthreads();   // the only CTA-wide barrier: the twiddle tables and the mbarriers
 
@@ -249,14 +298,6 @@ tts_mel_kernel(const TtsParams p) {
   float2* mag = reinterpret_cast<float2*>(xbuf + warp * kYWarpF4);   // this warp's magnitudes (frame of group 0, of group 1)
   const float2* tw_row = fft_twiddle_row<32>(tw_s, j, g);
   const float2* c0_row = fft_c0_row(tw_s, j);
-  const int c = lane >> 1, g2 = lane & 1, col = c == 0 ? 16 : c, t0 = (lane >> 1) & 7;
-  const float2 wcol = __ldg(p.w1024 + col);                 // W1024^col = (cos, -sin)
-  float w32r, w32i;                                          // W32^t0 for the column-0 bins
-  {
-    float sn, cs;
-    sincospif(2.0f * (float)t0 / 32.0f, &sn, &cs);
-    w32r = cs; w32i = -sn;
-  }
 
   // Work distribution: warp w of the grid takes pairs w, w + W, w + 2 W, ...  The clip of a pair is found by walking
   // the prefix sums forward, 32 entries per step (one load per lane and a ballot).
@@ -315,6 +356,7 @@ tts_mel_kernel(const TtsParams p) {
       {
         f2 y[32];
         const float2* xf = reinterpret_cast<const float2*>(buf + a_off + g * hop) + j;   // hop, a_off even: 8-byte aligned
+        const f2 cb = make_float2(tc[0].x, tc[0].y), sb = make_float2(tc[kCtaThreads].x, tc[kCtaThreads].y);
         static_for<0, 32>([&](auto ic) {
           constexpr int i = decltype(ic)::value;
           constexpr float ca = (float)(0.5 * ct_cos2pi(i, 32)), sa = (float)(0.5 * ct_sin2pi(i, 32));
@@ -338,6 +380,7 @@ tts_mel_kernel(const TtsParams p) {
     //      2X[512-k] = conj(2E - W^k 2O);  magnitudes into component g2 of the warp's buffer
     {
       float* mg = reinterpret_cast<float*>(mag) + g2;
+      const float2 wcol = make_float2(tc[2 * kCtaThreads].x, tc[2 * kCtaThreads].y);
       static_for<0, 16>([&](auto ic) {
         constexpr int k2 = decltype(ic)::value;
         constexpr float c32 = (float)ct_cos2pi(k2, 32), s32 = (float)(-ct_sin2pi(k2, 32));   // W32^k2
@@ -351,6 +394,7 @@ tts_mel_kernel(const TtsParams p) {
       });
       if ((lane & 1) == 0) {   // column 0 of the lane's own group: bins 32 t0 and 512 - 32 t0, and bin 256
         float* mo = reinterpret_cast<float*>(mag) + g;
+        const float w32r = tc[3 * kCtaThreads].x, w32i = tc[3 * kCtaThreads].y;
         const float er = c0r.x, ei = c0i.x, orr = c0r.y, oi = c0i.y;
         const float tr = fmaf(orr, w32r, -(oi * w32i)), ti = fmaf(orr, w32i, oi * w32r);
         const float pr = er + tr, pi = ei + ti, qr = er - tr, qi = ei - ti;
@@ -366,36 +410,20 @@ tts_mel_kernel(const TtsParams p) {
     {
       const MelTab& mel = p.mel_tab;
       float* out_u = p.mel + (long long)u * p.n_mels * p.frames_cap + 2 * pair;
-      const bool both = cap_even && 2 * pair + 1 < ut.T;
+      const bool second = 2 * pair + 1 < ut.T, both = cap_even && second;
+      if constexpr (MELS::kFixed) {
+        static_for<0, MELS::kRounds>([&](auto ic) {
+          constexpr int r = decltype(ic)::value;
+          tts_mel_round<MELS::cnt(r)>(mel, r, 0, MELS::base(r), mag, lane, p.log_floor, out_u, p.frames_cap, both, second);
+        });
+      } else {
 #pragma unroll 1
-      for (int r = 0; r < mel.rounds; ++r) {
-        int cnt = mel.cnt[0], base = mel.base[0];
+        for (int r = 0; r < mel.rounds; ++r) {
+          int cnt = mel.cnt[0], base = mel.base[0];
 #pragma unroll
-        for (int t = 1; t < kMelRounds; ++t)
-          if (r == t) { cnt = mel.cnt[t]; base = mel.base[t]; }
-        const unsigned word = (unsigned)__ldg(mel.lo + 32 * r + lane);
-        const int lo = (int)(word & 0xfffu), partner = (int)((word >> 12) & 31u), iv = (int)((word >> 17) & 0xffu);
-        const float2* wt = mel.w + (base * 32 + lane);
-        const float2* p0 = mag + lo;
-        f2 up = make_float2(0.f, 0.f), dn = make_float2(0.f, 0.f);
-#pragma unroll 4
-        for (int q = 0; q < cnt; ++q) {
-          const float2 wq = __ldg(wt + 32 * q);
-          const float2 sv = p0[q];
-          up = fma2s(sv, wq.x, up);
-          dn = fma2s(sv, wq.y, dn);
-        }
-        const float e0 = up.x + __shfl_sync(0xffffffffu, dn.x, partner);
-        const float e1 = up.y + __shfl_sync(0xffffffffu, dn.y, partner);
-        if (word >> 31) {
-          const float l0 = fast_ln(fmaxf(e0, p.log_floor)), l1 = fast_ln(fmaxf(e1, p.log_floor));
-          float* o = out_u + (long long)iv * p.frames_cap;
-          if (both) {
-            *reinterpret_cast<float2*>(o) = make_float2(l0, l1);
-          } else {
-            o[0] = l0;
-            if (2 * pair + 1 < ut.T) o[1] = l1;
-          }
+          for (int t = 1; t < kMelRounds; ++t)
+            if (r == t) { cnt = mel.cnt[t]; base = mel.base[t]; }
+          tts_mel_round<-1>(mel, r, cnt, base, mag, lane, p.log_floor, out_u, p.frames_cap, both, second);
         }
       }
     }
