@@ -7,6 +7,7 @@ struct b200fe_tts {
   int* d_mel_lo = nullptr;
   int mel_rounds = 0, mel_cnt[kMelRounds] = {0}, mel_base[kMelRounds] = {0};
   size_t smem = 0;
+  int mel_slots = 0;            // rows of 32 weights in d_mel_w
   bool mel_fixed = false;       // the interval table has the shape the kernel is specialised for (MelShapeTts)
   int n_sms = 0;
   TtsUtt* d_utts = nullptr;     // launch workspace, grown on demand: [cap] clip descriptors, [cap + 1] pair prefix sums
@@ -62,8 +63,6 @@ int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_m
   if (!(f_min >= 0 && f_max > f_min && f_max <= sample_rate / 2.0f)) return failc(B200FE_E_INVALID, "bad f_min / f_max");
   b200fe_tts* t = new b200fe_tts();
   t->sample_rate = sample_rate; t->n_fft = n_fft; t->hop = hop; t->n_mels = n_mels;
-  t->smem = tts_smem_bytes(hop);
-  if (t->smem * B200FE_TTS_CTAS > 227 * 1024) { delete t; return failc(B200FE_E_UNSUPPORTED, "hop too large for the per-warp sample buffers"); }
   {
     int dev = 0;
     cudaDeviceProp prop;
@@ -79,6 +78,9 @@ int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_m
     delete t;
     return failc(B200FE_E_UNSUPPORTED, why);
   }
+  t->mel_slots = t->mel_base[t->mel_rounds - 1] + t->mel_cnt[t->mel_rounds - 1];
+  t->smem = tts_smem_bytes(hop, t->mel_slots);
+  if ((t->smem + 1024) * B200FE_TTS_CTAS > 227 * 1024) { delete t; return failc(B200FE_E_UNSUPPORTED, "hop too large for the per-warp sample buffers"); }
   t->mel_fixed = t->mel_rounds == MelShapeTts::kRounds;
   for (int r = 0; r < MelShapeTts::kRounds; ++r) t->mel_fixed = t->mel_fixed && t->mel_cnt[r] == MelShapeTts::cnt(r) && t->mel_base[r] == MelShapeTts::base(r);
   for (int m = 0; m < n_mels; ++m)
@@ -121,6 +123,7 @@ int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total,
   if (!t) return B200FE_E_INVALID;
   if (batch == 0) return B200FE_OK;
   if (!wave_dev || !offsets_dev || !lengths_dev || !mel_dev || batch < 0 || max_frames > frames_cap) return B200FE_E_INVALID;
+  if (batch > 65535) { g_tts_error = "at most 65535 clips per b200fe_tts_forward call"; return B200FE_E_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lock(t->mu);
   if (batch > t->cap) {   // grow the workspace (synchronises: earlier launches may still read the old one)
@@ -139,12 +142,12 @@ int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total,
   p.twiddle = t->d_twiddle; p.w1024 = t->d_w1024;
   p.mel_tab.w = t->d_mel_w; p.mel_tab.lo = t->d_mel_lo; p.mel_tab.rounds = t->mel_rounds;
   for (int r = 0; r < kMelRounds; ++r) { p.mel_tab.cnt[r] = t->mel_cnt[r]; p.mel_tab.base[r] = t->mel_base[r]; }
-  p.utts = t->d_utts; p.pair_begin = t->d_pair_begin;
+  p.utts = t->d_utts; p.pair_begin = t->d_pair_begin; p.mel_slots = t->mel_slots;
   if (allow_dynamic_smem((const void*)tts_mel_kernel<MelShapeTts>, t->smem) != cudaSuccess ||
       allow_dynamic_smem((const void*)tts_mel_kernel<MelShapeRuntime>, t->smem) != cudaSuccess) return B200FE_E_CUDA;
   tts_prep_kernel<<<1, 1024, 0, st>>>((const long long*)offsets_dev, (const long long*)lengths_dev, batch, t->hop, t->d_utts,
                                       t->d_pair_begin, (long long*)mel_lens_dev);
-  tts_pad_kernel<<<dim3(8, batch), 256, 0, st>>>((const long long*)lengths_dev, t->hop, t->n_mels, mel_dev, frames_cap);
+  tts_pad_kernel<<<dim3((t->n_mels + 7) / 8, batch), 256, 0, st>>>((const long long*)lengths_dev, t->hop, t->n_mels, mel_dev, frames_cap);
   if (max_frames > 0) {
     // persistent warps: as many CTAs as stay resident, but not more warps than an upper bound of the pair count
     const long long pairs_ub = (long long)batch * ((max_frames + 1) / 2);

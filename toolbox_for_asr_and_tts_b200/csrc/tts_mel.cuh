@@ -56,6 +56,7 @@ struct TtsParams {
   const float2* twiddle;       // [kTw2Total]: the ASR front-end's stage-2 twiddles + column-0 table (TileParams::twiddle)
   const float2* w1024;         // [17] W1024^col, col = 0..16
   MelTab mel_tab;              // interval table over 512 bins (bin 512 carries no weight), bank-matched lanes
+  int mel_slots;               // rows of 32 (up, down) weights in mel_tab.w: copied into shared memory by every CTA
   const TtsUtt* utts;          // [batch]
   const int* pair_begin;       // [batch + 1]: exclusive prefix sums of ceil(T / 2); the last entry is the pair count
 };
@@ -63,9 +64,9 @@ struct TtsParams {
 // floats of a warp's sample buffer: a pair's n_fft + hop samples, placed up to 2 floats behind a 16-byte boundary
 __host__ __device__ inline int tts_buf_floats(int hop) { return ((hop + kTtsNfft + 3) & ~3) + 4; }
 constexpr int kTtsThreadConsts = 4;   // float2 per thread: Hann angle-addition pair (cos b, sin b), W1024^col, W32^t0
-__host__ __device__ inline size_t tts_smem_bytes(int hop) {
+__host__ __device__ inline size_t tts_smem_bytes(int hop, int mel_slots) {
   return (size_t)kWarps * tts_buf_floats(hop) * 4 + (size_t)kWarps * kYWarpF4 * 16 + (size_t)kTw2Total * 8 + (size_t)kWarps * 8 +
-         (size_t)kCtaThreads * kTtsThreadConsts * 8;
+         (size_t)kCtaThreads * kTtsThreadConsts * 8 + (size_t)mel_slots * 32 * 8;
 }
 using MelShapeTts = MelShapeFixed<3, 3, 10, 21>;   // 80 Slaney filters 0..12 kHz over the 513 bins of a 1024-point FFT at 24 kHz
 
@@ -199,7 +200,7 @@ __device__ __forceinline__ void tts_mel_round(const MelTab& mel, int r, int cnt_
   const float2* p0 = mag + lo;
   f2 up = make_float2(0.f, 0.f), dn = make_float2(0.f, 0.f);
   auto body = [&](int q) {
-    const float2 wq = __ldg(wt + 32 * q);
+    const float2 wq = wt[32 * q];     // shared memory (tts_mel_kernel copies the table)
     const float2 sv = p0[q];
     up = fma2s(sv, wq.x, up);
     dn = fma2s(sv, wq.y, dn);
@@ -268,12 +269,14 @@ tts_mel_kernel(const TtsParams p) {
   // per-thread constants live in shared memory and are re-read where they are used (volatile): kept in registers across
   // the loop they are spilled, and the local-memory footprint of an SM does not stay in L1
   volatile float2* tc = reinterpret_cast<volatile float2*>(bars + kWarps) + threadIdx.x;
+  float2* melw_s = reinterpret_cast<float2*>(bars + kWarps) + kCtaThreads * kTtsThreadConsts;   // the mel weights
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = tid & (kGroup - 1), g = lane >> 4;
   const int c = lane >> 1, g2 = lane & 1, col = c == 0 ? 16 : c, t0 = (lane >> 1) & 7;
 
   for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
+  for (int i = tid; i < p.mel_slots * 32; i += kCtaThreads) melw_s[i] = p.mel_tab.w[i];
   if (lane == 0) {
     mbar_init(bars + warp, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -330,17 +333,13 @@ tts_mel_kernel(const TtsParams p) {
   while (true) {
     const TtsUtt ut = p.utts[u];
     const int pair = w - pb_u;
-    // the next pair of this warp
+    // the next pair of this warp: the first window of prefix sums is loaded now and looked at after stage 1
     const int wn = w + W;
     const bool have_next = wn < total;
-    int un = u, pbn = pb_u;
-    long long g0n = -1;
-    if (have_next) {
-      seek(wn, un, pbn);
-      const TtsUtt utn = p.utts[un];
-      g0n = tts_tma_source(p, utn, wn - pbn);
-    }
+    const int v_next = __ldg(p.pair_begin + min(u + 1 + lane, p.batch));
 
+    int un = u, pbn = pb_u;
+    TtsUtt utn = ut;
     int a_off = 0;
     if (in_flight) {
       mbar_wait(bar, phase);
@@ -371,10 +370,20 @@ tts_mel_kernel(const TtsParams p) {
       }
       __syncwarp();   // every lane holds its samples (the buffer is free for the next pair's copy) and is done with the
                       // previous pair's magnitudes, which alias the transpose buffers
-      in_flight = tts_issue_copy(p, g0n, lane, buf, bar);
       fft_dit2<16>(zr, zi);
       real32_split2(zr, zi, y0, y16);
+      // clip of the next pair (its descriptor load overlaps stage 2)
+      if (have_next) {
+        const unsigned mm = __ballot_sync(0xffffffffu, u + 1 + lane <= p.batch && wn >= v_next);
+        const int n = __popc(mm);
+        if (n) pbn = __shfl_sync(0xffffffffu, v_next, n - 1);
+        un = u + n;
+        if (n == 32) seek(wn, un, pbn);
+        utn = p.utts[un];
+      }
       tts_stage2(zr, zi, y0, y16, yg, tw_row, c0_row, j, g, ar, ai, c0r, c0i, u_alt);
+      // the next pair's samples start their way from HBM: the buffer has been free since the barrier above
+      in_flight = tts_issue_copy(p, have_next ? tts_tma_source(p, utn, wn - pbn) : -1, lane, buf, bar);
     }
     // ---- recombination: lane .x = 2E[k], lane .y = 2O[k] at k = col + 32 k2;  2X[k] = 2E + W^k 2O,
     //      2X[512-k] = conj(2E - W^k 2O);  magnitudes into component g2 of the warp's buffer
@@ -408,7 +417,8 @@ tts_mel_kernel(const TtsParams p) {
     // ---- mel over magnitudes: lane <-> interval (bank-matched lanes, as in the ASR mel stage), both frames at once;
     //      the lane that holds filter iv stores (frame 2 pair, frame 2 pair + 1) of row iv
     {
-      const MelTab& mel = p.mel_tab;
+      MelTab mel = p.mel_tab;
+      mel.w = melw_s;
       float* out_u = p.mel + (long long)u * p.n_mels * p.frames_cap + 2 * pair;
       const bool second = 2 * pair + 1 < ut.T, both = cap_even && second;
       if constexpr (MELS::kFixed) {
@@ -432,16 +442,22 @@ tts_mel_kernel(const TtsParams p) {
   }
 }
 
-// frames beyond an utterance's length are zeroed (padded batch)
-__global__ void tts_pad_kernel(const long long* lengths, int hop, int M, float* mel, long long frames_cap) {
-  const int u = blockIdx.y;
+// frames beyond a clip's length are zeroed (padded batch): one warp per (clip, mel row), 128-bit stores on the 16-byte grid
+__global__ void __launch_bounds__(256)
+tts_pad_kernel(const long long* lengths, int hop, int M, float* mel, long long frames_cap) {
+  const int u = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
   const long long T = lengths[u] / hop;
-  const long long per = frames_cap - T;
-  if (per <= 0) return;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per * M; i += (long long)gridDim.x * blockDim.x) {
-    const long long m = i / per, f = T + (i - m * per);
-    mel[((long long)u * M + m) * frames_cap + f] = 0.f;
-  }
+  const long long n = frames_cap - T;
+  if (n <= 0) return;
+  float* row = mel + ((long long)u * M + m) * frames_cap + T;
+  const long long head = min(n, (long long)((4 - ((reinterpret_cast<uintptr_t>(row) >> 2) & 3)) & 3));
+  const long long n4 = (n - head) >> 2;
+  if (lane < head) row[lane] = 0.f;
+  float4* row4 = reinterpret_cast<float4*>(row + head);
+  for (long long i = lane; i < n4; i += 32) row4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < n - head - 4 * n4) row[head + 4 * n4 + lane] = 0.f;
 }
 
 }  // namespace b200fe
