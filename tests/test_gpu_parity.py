@@ -1189,6 +1189,49 @@ def test_stream_tick_returns_the_reference_energy_gate(cmvn):
     assert or_flags.cpu().tolist() == [True, False, True, True, False, False]
 
 
+@pytest.mark.parametrize("chunk", [9600, 3840, 300])
+def test_quad_level_stream_kernel_matches_the_shipped_tick(cmvn, chunk, monkeypatch):
+    """The quad-level alternative of the streaming tick (B200FE_STREAM_KERNEL=quad: descriptors, work items = (chunk, quad)
+    on persistent warps that scatter their frames straight into the rows, state update) is kept as a measured
+    alternative.  Same rows, counts, energy gate and state as the shipped one-CTA-per-stream tick,
+    push by push, incl. a stream that starts later, a final flush and chunks shorter than one frame."""
+    fe = make_fe(cmvn)
+    n_streams, max_chunk = 5, 9600
+    pools = {}
+    for kind in ("cta", "quad"):
+        monkeypatch.setenv("B200FE_STREAM_KERNEL", kind)
+        pools[kind] = StreamPool(fe, n_streams=n_streams, max_chunk_samples=max_chunk, device=DEV)
+    n = 3 * 9600 + 250
+    waves = [synth.uniform_pcm(97, i, n) for i in range(3)]
+    ids = torch.tensor([4, 0, 2], dtype=torch.int32)
+    pos, tick = 0, 0
+    while pos < n:
+        m = min(chunk, n - pos)
+        fin = pos + m >= n
+        c = np.zeros((3, max_chunk), dtype=np.float32)
+        lens = [m, m if tick >= 1 else 0, max(m - 7, 0)]            # stream 0 starts one tick late, stream 2 runs ragged
+        for i in range(3):
+            c[i, :lens[i]] = waves[i][pos:pos + lens[i]]
+        out = {}
+        for kind in ("cta", "quad"):
+            monkeypatch.setenv("B200FE_STREAM_KERNEL", kind)
+            out[kind] = pools[kind].push_with_speech_flags(torch.from_numpy(c).to(DEV), torch.tensor(lens, dtype=torch.int32), ids,
+                                                           torch.tensor([1 if fin else 0] * 3, dtype=torch.uint8))
+            torch.cuda.synchronize()
+        (fa, ra, ga, sa), (fb, rb, gb, sb) = out["cta"], out["quad"]
+        assert torch.equal(ra, rb), (pos, ra, rb)
+        assert torch.equal(ga, gb) and torch.allclose(sa, sb, rtol=1e-5, atol=0) and torch.equal(sa[:, 1], sb[:, 1])
+        for i in range(3):
+            k = int(ra[i])
+            assert torch.allclose(fa[i, :k], fb[i, :k], rtol=0, atol=2e-4), (pos, i, float((fa[i, :k] - fb[i, :k]).abs().max()))
+        pos += m
+        tick += 1
+    # the state slabs agree where they carry state: counters, sample carry (bit-exact), splice frames (rounding noise)
+    a, b = pools["cta"].state, pools["quad"].state
+    nbytes_counters = 4 * n_streams * 4
+    assert torch.equal(a[:nbytes_counters], b[:nbytes_counters])
+
+
 def test_ingest_with_scipy_fourier_resampling_against_the_scipy_golden():
     """the resampling branch the reference takes when scipy is installed (scipy.signal.resample,
     R:voice_interface.py:1022-1027) on the GPU, against outputs of scipy itself (tests/golden/resample_golden.npz):

@@ -11,6 +11,7 @@ int stream_layout(const b200fe_handle* h, int n_streams, int max_chunk, StreamLa
   lay.n_mels = h->cfg.n_mels;
   nf_max = (max_chunk - 1) / h->S + 1;
   lay.frames_cap = lay.cache_cap + nf_max;
+  lay.q_max = (nf_max + 3) / 4;
   e_cap = ((h->L - 1 + max_chunk + 8) + 3) & ~3;
   smem = stream_smem_bytes(e_cap, warp_kernel_fits(h->L, h->S));
   return 0;
@@ -24,14 +25,32 @@ int launch_stream(b200fe_handle* h, const StreamParams& p, size_t smem, bool dit
     CUDA_TRY(h, allow_dynamic_smem((const void*)k, smem));                                            \
     k<<<p.n, kCtaThreads, smem, st>>>(p);                                                             \
   } while (0)
-  const bool per_quad = warp_kernel_fits(h->L, h->S);   // every warp fetches its own quads (4 CTAs per SM)
+#define LAUNCHQ(DI)                                                                                   \
+  do {                                                                                                \
+    auto k = stream_quad_kernel<NROWS, EXACT, DI, MELS>;                                              \
+    CUDA_TRY(h, allow_dynamic_smem((const void*)k, smem));                                            \
+    stream_tick_prep_kernel<<<(p.n + 127) / 128, 128, 0, st>>>(p);                                    \
+    const long long items = (long long)p.n * p.lay.q_max;                                             \
+    const long long ctas = std::min<long long>(4ll * h->n_sms, (items + kWarps - 1) / kWarps);        \
+    k<<<(unsigned)ctas, kCtaThreads, smem, st>>>(p);                                                  \
+    stream_tick_finish_kernel<<<(p.n + kWarps - 1) / kWarps, kCtaThreads, 0, st>>>(p);                \
+  } while (0)
+  // One CTA per stream is the shipped tick.  B200FE_STREAM_KERNEL=quad selects the quad-level alternative (three
+  // launches: descriptors, work items = (chunk, quad) on persistent warps, state update), which needs a quad to fit the
+  // warp buffer.  Measured on B200: 52 us against 46 us per tick of 512 streams - the tick is too
+  // small (19 us of quads) for the flat work list to pay for its two extra launches.
+  const bool per_quad = warp_kernel_fits(h->L, h->S);
+  const char* force = getenv("B200FE_STREAM_KERNEL");
+  const bool quad_level = per_quad && force && force[0] == 'q';
 #ifdef B200FE_BENCH_ONLY
   if (!per_quad || dither) return fail(h, B200FE_E_UNSUPPORTED, "bench-only build");
-  LAUNCHS(false, true);
+  if (quad_level) LAUNCHQ(false); else LAUNCHS(false, true);
 #else
-  if (per_quad) { if (dither) LAUNCHS(true, true); else LAUNCHS(false, true); }
+  if (quad_level) { if (dither) LAUNCHQ(true); else LAUNCHQ(false); }
+  else if (per_quad) { if (dither) LAUNCHS(true, true); else LAUNCHS(false, true); }
   else          { if (dither) LAUNCHS(true, false); else LAUNCHS(false, false); }
 #endif
+#undef LAUNCHQ
 #undef LAUNCHS
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
