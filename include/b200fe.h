@@ -139,8 +139,11 @@ int b200fe_lfr_cmvn(b200fe_handle* h, const float* fbank_dev, int64_t frames_cap
 /* ---- streaming: replaces WavFrontendOnline.forward(input, lengths, cache=..., is_final=...) (upstream funasr
  * wav_frontend.py, reached through vad_model.generate(cache=...) at R:voice-service/app/services/
  * voice_interface.py:1585-1590) and the per-session np.concatenate accumulation at :1304-1311,1688-1746.
- * The state slab keeps, per stream, the sample carry (input_cache), the LFR splice frames
- * (lfr_splice_cache) and counters, resident in HBM. */
+ * The state slab keeps, per stream, the sample carry (input_cache), a log-mel buffer whose first rows are the LFR splice
+ * frames carried from tick to tick (lfr_splice_cache; the frames of the current tick are appended behind them, which
+ * is why its size depends on max_chunk_samples), counters and the per-tick scratch of the kernels, resident in HBM:
+ * allocate b200fe_stream_state_bytes, zero it or call b200fe_stream_reset, and treat it as opaque (a byte copy is a
+ * valid checkpoint). */
 int b200fe_stream_state_bytes(const b200fe_handle* h, int n_streams, int max_chunk_samples, size_t* bytes);
 int b200fe_stream_reset(b200fe_handle* h, void* state_dev, int n_streams, int max_chunk_samples,
                         const int32_t* stream_ids_dev_or_null, int n, void* stream);
@@ -165,7 +168,9 @@ int b200fe_stream_max_rows(const b200fe_handle* h, int max_chunk_samples);
  * oracle/tts_mel_np.py): n_fft = win = 1024, periodic Hann, reflect padding (n_fft-hop)/2 per side so that
  * frames = n_samples / hop, magnitude sqrt(re^2+im^2+1e-9), Slaney-scale Slaney-normalised filters, log(clamp 1e-5).
  * mel_dev: float32 [batch, n_mels, frames_cap] (mel-major); frames beyond an utterance are zero.
- * offsets_dev / lengths_dev: int64 device arrays; max_frames = max_i lengths[i] / hop sizes the launch. */
+ * offsets_dev / lengths_dev: int64 device arrays; max_frames = max_i lengths[i] / hop sizes the launch.  batch <= 65535.
+ * Clips whose first sample lies on an 8-byte boundary of wave_dev take the fast path (bulk copies of the samples).
+ * One forward at a time per handle (calls are serialised inside: the handle owns the launch's work list). */
 typedef struct b200fe_tts b200fe_tts;
 int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_min, float f_max, b200fe_tts** out);
 void b200fe_tts_destroy(b200fe_tts* t);
