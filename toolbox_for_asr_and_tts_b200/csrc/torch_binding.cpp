@@ -292,8 +292,10 @@ std::tuple<at::Tensor, at::Tensor> tts_forward(int64_t t, const at::Tensor& wave
   auto len_host = lengths.to(at::kCPU, at::kLong).contiguous();
   const int b = (int)len_host.numel();
   at::Tensor off_host;
-  if (offsets.has_value() && offsets->defined()) off_host = offsets->to(at::kCPU, at::kLong).contiguous();
-  else {
+  if (offsets.has_value() && offsets->defined()) {
+    off_host = offsets->to(at::kCPU, at::kLong).contiguous();
+    TORCH_CHECK(off_host.numel() == b, "offsets and lengths differ in size");
+  } else {
     TORCH_CHECK(w.dim() == 2 && w.size(0) == b, "waveform must be [B, Nmax] when no offsets are given");
     off_host = at::arange(b, at::kLong) * w.size(1);
   }
@@ -301,7 +303,7 @@ std::tuple<at::Tensor, at::Tensor> tts_forward(int64_t t, const at::Tensor& wave
   for (int i = 0; i < b; ++i) {
     const int64_t n = len_host.data_ptr<int64_t>()[i];
     TORCH_CHECK(n > (1024 - hop) / 2, "reflect padding needs more than (n_fft-hop)/2 samples");
-    TORCH_CHECK(off_host.data_ptr<int64_t>()[i] + n <= w.numel(), "utterance outside the wave buffer");
+    TORCH_CHECK(off_host.data_ptr<int64_t>()[i] >= 0 && off_host.data_ptr<int64_t>()[i] + n <= w.numel(), "utterance outside the wave buffer");
     max_frames = std::max(max_frames, n / hop);
   }
   auto len_dev = len_host.to(w.device(), true), off_dev = off_host.to(w.device(), true);

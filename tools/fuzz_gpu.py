@@ -83,9 +83,52 @@ def fuzz_streaming(a, rng, dev):
     print(f"streaming fuzz ok: {it} random sessions-sets in {time.time() - t0:.0f} s, worst stream-vs-offline difference {worst:.2e}")
 
 
+def fuzz_tts(a, rng, dev):
+    """Random ragged batches through the TTS log-mel kernel, dense [B, Nmax] (any Nmax: odd rows start off the 8-byte
+    grid and take the lane-filled sample path) and length-packed with random offsets, against the frozen numpy
+    definition on a few clips per batch; frame counts, zero padding and finiteness on all of them."""
+    from oracle import tts_mel_np as tm
+    from toolbox_for_asr_and_tts_b200 import TtsLogMel, _native
+    fe = TtsLogMel()
+    t0, it, worst = time.time(), 0, 0.0
+    while time.time() - t0 < a.seconds:
+        B = int(rng.integers(1, 40))
+        kind = int(rng.integers(3))
+        lens = (rng.integers(385, 3000, B) if kind == 0 else rng.integers(385, 60000, B) if kind == 1
+                else rng.integers(385, 1300, B)).astype(np.int64)
+        waves = [(0.3 * rng.standard_normal(int(k))).astype(np.float32) for k in lens]
+        if rng.random() < 0.5:
+            nmax = int(lens.max()) + int(rng.integers(0, 9))
+            dense = np.zeros((B, nmax), dtype=np.float32)
+            for i, w in enumerate(waves):
+                dense[i, :len(w)] = w
+            mel, frames = fe(torch.from_numpy(dense).to(dev), lens)
+        else:
+            offs, total = synth.packed_offsets(lens, align=int(rng.choice([1, 2, 4])))
+            offs = offs + int(rng.integers(0, 7))
+            flat = np.zeros(int(total) + 16, dtype=np.float32)
+            for o, w in zip(offs, waves):
+                flat[o:o + len(w)] = w
+            mel, frames = _native.ops().tts_forward(fe._handle(dev), torch.from_numpy(flat).to(dev), torch.from_numpy(offs),
+                                                    torch.from_numpy(lens), fe.hop_length, fe.n_mels)
+        assert torch.isfinite(mel).all(), (it, "finiteness")
+        assert frames.cpu().tolist() == (lens // 256).tolist(), (it, "frame counts")
+        assert mel.shape[2] == int(lens.max()) // 256, (it, mel.shape)
+        for i in range(B):
+            assert not mel[i, :, int(lens[i]) // 256:].any(), (it, i, "padding")
+        for i in rng.choice(B, size=min(B, 4), replace=False):
+            ref = tm.tts_log_mel(waves[i])
+            err = float(np.abs(mel[i, :, :ref.shape[1]].cpu().numpy() - ref).max()) if ref.shape[1] else 0.0
+            worst = max(worst, err)
+            assert err <= 1e-3, (it, int(i), int(lens[i]), err)
+        it += 1
+    print(f"tts fuzz: {it} batches OK, worst |log-mel - numpy definition| {worst:.2e}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--streaming", action="store_true", help="fuzz the chunked-streaming path instead")
+    ap.add_argument("--tts", action="store_true", help="fuzz the TTS log-mel kernel instead")
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--only", type=int, default=-1, help="replay the random draws and run just this iteration, with diagnostics")
@@ -94,6 +137,9 @@ def main():
     dev = "cuda:0"
     if a.streaming:
         fuzz_streaming(a, rng, dev)
+        return
+    if a.tts:
+        fuzz_tts(a, rng, dev)
         return
     confs = [(7, 6), (5, 1), (1, 1), (3, 2)]
     fes = {}
