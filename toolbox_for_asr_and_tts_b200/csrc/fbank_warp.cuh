@@ -35,6 +35,9 @@
 #ifndef B200FE_HEAD_PRED     // 1: round-2a behaviour, the next quad's head is loaded under a predicate (experiment baseline)
 #define B200FE_HEAD_PRED 0
 #endif
+#ifndef B200FE_DESC_SMEM     // 1: the quad descriptors travel through shared memory (cp.async) instead of registers:
+#define B200FE_DESC_SMEM 1   //    nothing is held across the FFT, no spills (measured -0.8 %); 0: __ldg into registers
+#endif
 #ifndef B200FE_CLAIM_STATIC  // 1: no work counter, warp w takes quads w, w + W, w + 2 W, ... (W = warps of the grid)
 #define B200FE_CLAIM_STATIC 0
 #endif
@@ -290,6 +293,10 @@ fbank_warp_kernel(const QuadParams p) {
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(tw_s + kTw2Total);
   float4* zero_block = reinterpret_cast<float4*>(bars + kWarps);   // kPadChunk bytes of zeros: source of the padding stores
   constexpr bool kTma = std::is_same<SampleT, float>::value;
+#if B200FE_DESC_SMEM
+  // per warp: [0] head of the next quad, [1..3] the rest of the current quad's descriptor ({f0, T, rows, row_begin}, targets)
+  __shared__ __align__(16) int4 desc_s[kWarps][4];
+#endif
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -332,10 +339,10 @@ fbank_warp_kernel(const QuadParams p) {
   const bool act = lane < M4;      // lanes that move a float4 of a log-mel row (n_mels <= 128)
 
   // Work distribution: the first quad of every warp is static (neighbouring warps start on neighbouring quads), all
-  // later ones are claimed from a global counter TWO quads ahead: the claim for quad k+2 is issued at the top of quad k
-  // and read at its end, the 16-byte head {g0, nF, utt} of quad k+1 is loaded then and first used in the middle of
-  // quad k+1 (for its bulk copy), so neither the atomic's nor the descriptor's L2 round trip is ever waited for.
-  // The rest of the 64-byte descriptor ({f0, T, rows}, the LFR targets) is read by the quad itself, just before use.
+  // later ones are claimed from a global counter one quad ahead.  The 16-byte head {g0, nF, utt} of the claimed quad and
+  // the rest of the current quad's descriptor ({f0, T, rows}, the LFR targets) travel by cp.async into four 16-byte
+  // shared-memory slots of the warp at the top of the quad; the head is read after stage 1 (for the bulk copy of the
+  // next quad's samples), the rest by the output stage - no descriptor register lives across the FFT.
   const int first_wave = gridDim.x * kWarps;
   const int last_quad = p.n_quads - 1;
   const int n_pad_items = p.batch << kPadPieceShift;
@@ -383,11 +390,27 @@ fbank_warp_kernel(const QuadParams p) {
 #if B200FE_HEAD_PRED
     int4 hdn = make_int4(0, 0, 0, 0);
     if (have_next) hdn = __ldg(reinterpret_cast<const int4*>(p.quads + qn));
+#elif B200FE_DESC_SMEM
+    // lanes 1..3: the rest of this quad's descriptor, lane 0: the head of the next quad - all by cp.async into the warp's
+    // shared-memory slots (no registers held across the FFT); waited for after stage 1
+    {
+      const int4* src = lane == 0 ? reinterpret_cast<const int4*>(p.quads + min(qn, last_quad))
+                                  : reinterpret_cast<const int4*>(p.quads + q) + lane;
+      if (lane < 4) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&desc_s[warp][lane])), "l"(src) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    }
 #else
     const int4 hdn = __ldg(reinterpret_cast<const int4*>(p.quads + min(qn, last_quad)));
 #endif
 #endif
+#if B200FE_DESC_SMEM
+    const volatile int4* ds = desc_s[warp];
+#define hd1 (*const_cast<const int4*>(ds + 1))
+#else
     const int4 hd1 = __ldg(reinterpret_cast<const int4*>(p.quads + q) + 1);   // f0, T, rows, pad: used by the output stage
+#endif
     int pad_rows = 0;                                                          // padding piece q: read now, stored mid-quad
     if (B200FE_PAD_MODE && lane == 0 && q < n_pad_items) pad_rows = __ldg(&p.utts[q >> kPadPieceShift].n_rows);
 
@@ -410,6 +433,12 @@ fbank_warp_kernel(const QuadParams p) {
     {
       f2 zr[16], zi[16], y0, y16;
       int f0_dither = 0;
+#if B200FE_DESC_SMEM
+      if constexpr (DITHER) {   // the frame index seeds the dither: the descriptor is needed before stage 1
+        if (lane < 4) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
+#endif
       if constexpr (DITHER) f0_dither = hd1.x;
       quad_stage1<NROWS, EXACT, DITHER, SR>(buf + a_off + fA * S, vA, vB, S, L, win, p.preemph, p.remove_dc, p.dither,
                                             p.seed, (unsigned)utt, (unsigned)(f0_dither + fA), j, g, zr, zi, y0, y16);
@@ -417,6 +446,11 @@ fbank_warp_kernel(const QuadParams p) {
       // ---- the next quad's samples start their way from HBM now: one bulk copy into the (now free) buffer, or one L2
       //      prefetch per 128-byte line for the generic fill
       in_flight = 0;
+#if B200FE_DESC_SMEM
+      if (lane < 4) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      const int4 hdn = *const_cast<const int4*>(ds);
+#endif
       if (have_next) {
         g0_next = ((long long)hdn.y << 32) | (unsigned)hdn.x;
         nF_next = hdn.z & 0xff; slow_next = (hdn.z >> 8) & 0xf; utt_next = hdn.w;
@@ -441,8 +475,13 @@ fbank_warp_kernel(const QuadParams p) {
       }
       quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
     }
+#if B200FE_DESC_SMEM
+#define tg0 (*reinterpret_cast<const uint4*>(const_cast<const int4*>(ds + 2)))
+#define tg1 (*reinterpret_cast<const uint4*>(const_cast<const int4*>(ds + 3)))
+#else
     const uint4 tg0 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 2);   // targets of frames 0, 1
     const uint4 tg1 = __ldg(reinterpret_cast<const uint4*>(p.quads + q) + 3);   // targets of frames 2, 3
+#endif
 
 #if B200FE_OUT_DIRECT
     // ---- mel + log + LFR + CMVN in one go: the lane that holds filter iv of the quad's 4 frames writes it straight to
@@ -621,6 +660,12 @@ fbank_warp_kernel(const QuadParams p) {
 
 #endif
     if (!have_next) break;
+#if B200FE_DESC_SMEM
+    __syncwarp();   // the descriptor slots are read: the next quad's copies may overwrite them
+#undef hd1
+#undef tg0
+#undef tg1
+#endif
     q = qn;
     g0_cur = g0_next;
     nF = nF_next; slow = slow_next; utt = utt_next;
