@@ -433,6 +433,35 @@ def test_tts_log_mel_against_frozen_definition():
         fe(torch.zeros(1, 24000), [24000])                  # CPU tensors are rejected
 
 
+def test_tts_log_mel_large_batch_and_other_geometry():
+    """The TTS kernel's work list is built on the device (prefix sums of frame pairs over the batch, 1 024 clips per
+    scan step): a batch of 1 100 short clips crosses that step.  And a second geometry (16 kHz, hop 320, 64 mels up to
+    7.6 kHz) takes the run-time mel shape and a different per-warp sample buffer.  Both against the frozen numpy definition."""
+    from oracle import tts_mel_np as tm
+    from toolbox_for_asr_and_tts_b200 import TtsLogMel
+    rng = np.random.default_rng(5)
+    lens = rng.integers(385, 1400, 1100)
+    waves = [synth.uniform_pcm(95, i, int(n)) for i, n in enumerate(lens)]
+    fe = TtsLogMel()
+    mel, frames = fe(dense_batch(waves), lens.tolist())
+    assert frames.cpu().tolist() == (lens // 256).tolist()
+    for i in [0, 1, 511, 1023, 1024, 1025, 1099] + rng.integers(0, 1100, 8).tolist():
+        ref = tm.tts_log_mel(waves[i])
+        assert np.abs(mel[i, :, :ref.shape[1]].cpu().numpy() - ref).max() <= 1e-3, i
+        assert not mel[i, :, ref.shape[1]:].any()
+    conf = dict(sample_rate=16000, n_fft=1024, hop_length=320, n_mels=64, f_min=50.0, f_max=7600.0)
+    fe2 = TtsLogMel(**conf)
+    lens2 = [16000, 48001, 353, 5000, 640]
+    waves2 = [synth.uniform_pcm(96, i, n) for i, n in enumerate(lens2)]
+    mel2, frames2 = fe2(dense_batch(waves2), lens2)
+    assert tuple(mel2.shape) == (5, 64, max(lens2) // 320)
+    for i, n in enumerate(lens2):
+        ref = tm.tts_log_mel(waves2[i], sample_rate=16000, n_fft=1024, hop=320, n_mels=64, f_min=50.0, f_max=7600.0)
+        assert int(frames2[i]) == n // 320 == ref.shape[1]
+        assert np.abs(mel2[i, :, :ref.shape[1]].cpu().numpy() - ref).max() <= 1e-3, (n, np.abs(mel2[i, :, :ref.shape[1]].cpu().numpy() - ref).max())
+        assert not mel2[i, :, ref.shape[1]:].any()
+
+
 @pytest.mark.parametrize("m,n", [(7, 6), (5, 1), (1, 1), (3, 2), (9, 4)])
 def test_warp_kernel_equals_tile_kernel(m, n):
     """The warp-autonomous kernel (quad list, scattered LFR rows) and the tile kernel (row-major LFR pass) run the

@@ -9,7 +9,7 @@ struct b200fe_tts {
   size_t smem = 0;
   int mel_slots = 0;            // rows of 32 weights in d_mel_w
   bool mel_fixed = false;       // the interval table has the shape the kernel is specialised for (MelShapeTts)
-  int n_sms = 0;
+  int n_sms = 0, ctas_per_sm = B200FE_TTS_CTAS;
   TtsUtt* d_utts = nullptr;     // launch workspace, grown on demand: [cap] clip descriptors, [cap + 1] pair prefix sums
   int* d_pair_begin = nullptr;
   int cap = 0;
@@ -80,7 +80,10 @@ int b200fe_tts_create(int sample_rate, int n_fft, int hop, int n_mels, float f_m
   }
   t->mel_slots = t->mel_base[t->mel_rounds - 1] + t->mel_cnt[t->mel_rounds - 1];
   t->smem = tts_smem_bytes(hop, t->mel_slots);
-  if ((t->smem + 1024) * B200FE_TTS_CTAS > 227 * 1024) { delete t; return failc(B200FE_E_UNSUPPORTED, "hop too large for the per-warp sample buffers"); }
+  // resident CTAs per SM: what the kernel is compiled for (registers), fewer when the sample buffers of a large hop or a
+  // large mel table need the shared memory
+  t->ctas_per_sm = (int)std::min<size_t>(B200FE_TTS_CTAS, (227 * 1024) / (t->smem + 1024));
+  if (t->ctas_per_sm < 1) { delete t; return failc(B200FE_E_UNSUPPORTED, "hop too large for the per-warp sample buffers"); }
   t->mel_fixed = t->mel_rounds == MelShapeTts::kRounds;
   for (int r = 0; r < MelShapeTts::kRounds; ++r) t->mel_fixed = t->mel_fixed && t->mel_cnt[r] == MelShapeTts::cnt(r) && t->mel_base[r] == MelShapeTts::base(r);
   for (int m = 0; m < n_mels; ++m)
@@ -151,7 +154,7 @@ int b200fe_tts_forward(b200fe_tts* t, const float* wave_dev, int64_t wave_total,
   if (max_frames > 0) {
     // persistent warps: as many CTAs as stay resident, but not more warps than an upper bound of the pair count
     const long long pairs_ub = (long long)batch * ((max_frames + 1) / 2);
-    const long long ctas = std::min<long long>((long long)t->n_sms * B200FE_TTS_CTAS, (pairs_ub + kWarps - 1) / kWarps);
+    const long long ctas = std::min<long long>((long long)t->n_sms * t->ctas_per_sm, (pairs_ub + kWarps - 1) / kWarps);
     const unsigned grid = (unsigned)std::max<long long>(ctas, 1);
     if (t->mel_fixed) tts_mel_kernel<MelShapeTts><<<grid, kCtaThreads, t->smem, st>>>(p);
     else tts_mel_kernel<MelShapeRuntime><<<grid, kCtaThreads, t->smem, st>>>(p);
