@@ -171,7 +171,10 @@ def run_ours(args, rank, world, local_rank):
     ops = _native.ops()
     # host placement of the ingest path (e2e): bind the rank to its GPU's NUMA node before any pinned allocation
     from toolbox_for_asr_and_tts_b200 import hostaffinity
-    placement = hostaffinity.bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    # (also at N = 1: on a two-socket host an unbound process may first-touch its pinned buffers on the far socket).  The
+    # original affinity is restored for every thread before the CPU baseline runs, so that leg keeps all host cores.
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    placement = hostaffinity.bind_to_gpu_numa_node(local_rank)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
     ranks_per_node = max(1, local_world // 2) if (placement and placement.get("bound")) else local_world
     ingest_threads = hostaffinity.ingest_threads(ranks_per_node)
@@ -385,7 +388,9 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- the reference's CPU front-end on this box's cores: the whole batch (same config as `value`), all
     #                  cores and one thread, and BASELINE configs[0] (one 10 s utterance)
     cpu = None
-    if not args.no_cpu_baseline:
+    if affinity0 is not None and placement and placement.get("bound"):
+        hostaffinity.restore_affinity(affinity0)
+    if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import ref_thirdparty as ref
             from toolbox_for_asr_and_tts_b200 import synth
@@ -454,7 +459,7 @@ def run_ours(args, rank, world, local_rank):
                     "fraction_of_h2d_ceiling": copy_only_ms / (pre_ms / e2e_steps),
                     "starts_from": "the step's inputs in pinned host memory (one length-packed float32 buffer), as the contract states",
                     "timed_per_step": ["H2D of the waveforms", "prep + fused kernels", "D2H of the feature lengths"],
-                    "features_stay_in_hbm": True,
+                    "features_stay_in_hbm": True, "host_placement": placement,
                     "note": "double-buffered serving loop (step k+1's H2D overlaps step k's kernels); the features stay in HBM "
                             "for the acoustic model (funasr also moves the CPU front-end's output to cuda:0), only the feature "
                             "lengths return to the host; e2e_api below starts one step earlier, at the caller's numpy arrays"},

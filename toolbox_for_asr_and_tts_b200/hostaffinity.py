@@ -46,6 +46,22 @@ def bind_to_gpu_numa_node(device_index: int) -> Optional[dict]:
     return {"bound": True, "numa_node": info["numa_node"], "cpus": len(use)}
 
 
+def restore_affinity(cpus) -> None:
+    """Give every thread of this process the CPU set `cpus` again (sched_setaffinity acts on one thread; worker pools
+    created while the process was bound have inherited the narrow mask)."""
+    if not hasattr(os, "sched_setaffinity"):
+        return
+    try:
+        tids = [int(t) for t in os.listdir("/proc/self/task")]
+    except OSError:
+        tids = [0]
+    for tid in tids:
+        try:
+            os.sched_setaffinity(tid, cpus)
+        except OSError:
+            pass
+
+
 def ingest_threads(local_world_size: int = 1) -> int:
     """Gather threads per rank: the CPUs this process may use, shared among the ranks of the box, 2..32."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
