@@ -55,6 +55,7 @@ struct b200fe_handle {
   int mel_rounds = 0, mel_cnt[kMelRounds] = {0}, mel_base[kMelRounds] = {0};
   bool mel_paraformer = false;      // table shape == MelShapeParaformer: fully unrolled mel stage
   float* d_cmvn = nullptr;          // [2*D]
+  float4* d_cmvn_il = nullptr;      // warp kernel: [32 slots][n_mels/4][shift4, scale4], identity without CMVN (fbank_warp.cuh)
   // dense mel banks for shrunken frames (VF:147), keyed by fft size
   std::map<int, int> short_mel_off;
   float* d_short_mel = nullptr;
@@ -142,7 +143,7 @@ int build_mel(int n_mels, int nfft, double fs, double low, double high, std::vec
 // this lane's filter), 17..24 filter index, bit 31 = this lane outputs a filter.
 int build_interval_table(const std::vector<float>& bank, int nm, int nb, int ld, float scale, std::vector<float2>& mw,
                          std::vector<int>& mlo, int& rounds, int* cnt_out, int* base_out, std::string& why,
-                         int bank_mod = 0) {
+                         int bank_mod = 0, bool last_peak_down = false) {
   mw.assign((size_t)kMelSlots * 32, make_float2(0.f, 0.f));
   mlo.assign(32 * kMelRounds, 1);
   auto W = [&](int m, int k) { return bank[(size_t)m * ld + k]; };
@@ -165,6 +166,10 @@ int build_interval_table(const std::vector<float>& bank, int nm, int nb, int ld,
       for (int kk = 1; kk < nb; ++kk)
         if (W(first, kk) > W(first, peak)) peak = kk;
       iv = k > peak ? first + 1 : first;
+      // last_peak_down: the peak bin of the LAST filter, when it carries that one weight only, goes to the last interval
+      // as a down-slope weight (same sum); the compact table (build_compact_mel) cannot hold a lone up-slope weight on
+      // a lane whose down-slope sum is read
+      if (last_peak_down && first == nm - 1 && k == peak) iv = first + 1;
       if (iv < prev && prev <= first + 1) iv = prev;
     }
     if (iv < prev) { why = "mel filterbank intervals are not monotone"; return -1; }
@@ -265,6 +270,37 @@ int build_interval_table(const std::vector<float>& bank, int nm, int nb, int ld,
   }
   for (int r = rounds; r < kMelRounds; ++r) { cnt_out[r] = 0; base_out[r] = base; }
   return 0;
+}
+
+// Compact form of the interval table for the fixed-shape mel stage (fbank_tile.cuh, B200FE_MEL_COMPACT): one float per
+// slot, appended behind the kMelSlots * 32 (up, down) pairs.  u = up weight; the kernel derives down = scale - u
+// wherever u > 0.  Encodable: padding (0, 0) -> 0; up + down == scale (to float rounding) -> up; a lone up weight whose
+// lane's down-slope sum nobody reads (interval 0) or that equals the scale -> up; a lone down weight on a lane whose
+// up-slope sum nobody reads (it outputs no filter) -> scale - down, or 2^-90 when down == scale.  Returns false if a
+// slot is not (then the fixed-shape instantiations are not used).
+bool build_compact_mel(std::vector<float2>& mw, const std::vector<int>& mlo, int rounds, const int* cnt, const int* base,
+                       float scale) {
+  std::vector<float> cu((size_t)kMelSlots * 32, 0.f);
+  bool ok = true;
+  for (int r = 0; r < rounds; ++r)
+    for (int l = 0; l < 32; ++l) {
+      const unsigned word = (unsigned)mlo[32 * r + l];
+      const int iv = (int)((word >> 17) & 0xffu);
+      const bool outputs = (word >> 31) != 0;
+      for (int q = 0; q < cnt[r]; ++q) {
+        const float2 w = mw[(size_t)(base[r] + q) * 32 + l];
+        float u = 0.f;
+        if (w.x == 0.f && w.y == 0.f) u = 0.f;
+        else if (w.x > 0.f && w.y > 0.f) { u = w.x; ok = ok && fabsf(w.x + w.y - scale) <= 4e-7f * scale; }
+        else if (w.y == 0.f) { u = w.x; ok = ok && (iv == 0 || w.x == scale); }
+        else { u = w.y < scale ? scale - w.y : 0x1p-90f; ok = ok && !outputs && w.y <= scale; }
+        ok = ok && (u == 0.f || u >= 0x1p-100f);
+        cu[(size_t)(base[r] + q) * 32 + l] = u;
+      }
+    }
+  mw.resize((size_t)kMelSlots * 32 + (size_t)kMelSlots * 16, make_float2(0.f, 0.f));
+  memcpy(mw.data() + (size_t)kMelSlots * 32, cu.data(), cu.size() * sizeof(float));
+  return ok;
 }
 
 int frame_count(long long n, int win, int shift) { return n < win ? 0 : (int)(1 + (n - win) / shift); }
@@ -572,10 +608,11 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
   std::vector<int> mlo;
   {
     std::string why;
-    if (build_interval_table(h->mel_host, cfg->n_mels, nfft / 2, nfft / 2, 0.25f, mw, mlo, h->mel_rounds, h->mel_cnt,
-                             h->mel_base, why, 16) != 0)
+    if (build_interval_table(h->mel_host, cfg->n_mels, nfft / 2, nfft / 2, kMelScale, mw, mlo, h->mel_rounds, h->mel_cnt,
+                             h->mel_base, why, 16, B200FE_MEL_COMPACT != 0) != 0)
       return bail(B200FE_E_UNSUPPORTED, why);
-    h->mel_paraformer = h->mel_rounds == MelShapeParaformer::kRounds;
+    const bool compact = build_compact_mel(mw, mlo, h->mel_rounds, h->mel_cnt, h->mel_base, kMelScale);
+    h->mel_paraformer = h->mel_rounds == MelShapeParaformer::kRounds && (compact || !B200FE_MEL_COMPACT);
     for (int r = 0; r < MelShapeParaformer::kRounds && h->mel_paraformer; ++r)
       h->mel_paraformer = h->mel_cnt[r] == MelShapeParaformer::cnt(r);
   }
@@ -607,6 +644,22 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
     CK(cudaMemcpy(h->d_cmvn, cmvn_host, 2 * h->D * sizeof(float), cudaMemcpyHostToDevice));
     h->has_cmvn = true;
   }
+  if (h->cfg.n_mels % 4 == 0 && h->cfg.lfr_m <= kCmvnSlots) {
+    // the warp kernel's view of the CMVN table: per (slot, float4 piece of the mel row) the shift and the scale side by
+    // side, 32 slots so that the slot field of any target code (kNoTarget included) indexes it; (x + 0) * 1 without CMVN
+    const int M = h->cfg.n_mels, M4 = M / 4;
+    std::vector<float> il((size_t)kCmvnSlots * M4 * 8, 0.f);
+    for (int slot = 0; slot < kCmvnSlots; ++slot)
+      for (int l = 0; l < M4; ++l)
+        for (int k = 0; k < 4; ++k) {
+          const bool in = slot < h->cfg.lfr_m;
+          const int col = slot * M + 4 * l + k;
+          il[((size_t)slot * M4 + l) * 8 + k] = (in && cmvn_host) ? cmvn_host[col] : 0.f;
+          il[((size_t)slot * M4 + l) * 8 + 4 + k] = (in && cmvn_host) ? cmvn_host[h->D + col] : 1.f;
+        }
+    CK(cudaMalloc(&h->d_cmvn_il, il.size() * sizeof(float)));
+    CK(cudaMemcpy(h->d_cmvn_il, il.data(), il.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
 #undef CK
   *out = h;
   return B200FE_OK;
@@ -615,7 +668,7 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
 void b200fe_destroy(b200fe_handle* h) {
   if (!h) return;
   cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo);
-  cudaFree(h->d_cmvn); cudaFree(h->d_short_mel);
+  cudaFree(h->d_cmvn); cudaFree(h->d_cmvn_il); cudaFree(h->d_short_mel);
   for (auto& pr : h->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& e : h->event_pool) cudaEventDestroy(e);
   for (auto& s : h->slots) {
@@ -803,7 +856,7 @@ int forward_impl(b200fe_handle* h, const void* wave_any, bool pcm16, int64_t wav
     p.seed = dither_seed;
     p.window = h->d_window; p.twiddle = h->d_twiddle; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_rounds = h->mel_rounds;
     for (int r = 0; r < kMelRounds; ++r) { p.mel_cnt[r] = h->mel_cnt[r]; p.mel_base[r] = h->mel_base[r]; }
-    p.cmvn = h->d_cmvn;
+    p.cmvn = h->d_cmvn; p.cmvn_il = h->d_cmvn_il;
     p.utts = d_utts; p.batch = batch;
     const int ctas = (pl.n_quads + kWarps - 1) / kWarps;
     const int grid = ctas < B200FE_WARP_CTAS * h->n_sms ? ctas : B200FE_WARP_CTAS * h->n_sms;

@@ -28,6 +28,9 @@
 #ifndef B200FE_S1_UNCOND
 #define B200FE_S1_UNCOND 1
 #endif
+#ifndef B200FE_MEL_COMPACT   // 1: the fixed-shape mel stage reads ONE float per (bin, lane) - the up-slope weight - and derives
+#define B200FE_MEL_COMPACT 1 //    the down-slope weight (they sum to the bank's scale): half the weight bytes through L1
+#endif
 
 namespace b200fe {
 
@@ -55,6 +58,7 @@ constexpr int kMaxInt = kMaxMels + 1;  // intervals between consecutive filter c
 constexpr int kMelRounds = (kMaxMels + 30) / 31;  // rounds of 31 filters: lane <-> interval, lane 31 only feeds lane 30
 constexpr int kMelSlots = 64;       // sum over rounds of the round's widest interval (bins), upper bound
 constexpr int kNfft = 512;
+constexpr float kMelScale = 0.25f;  // the stored powers are 4 |X|^2: the mel weights carry the 0.25
 
 struct UttDesc {          // built on the host by b200fe_plan/forward
   long long wave_off;     // first sample of the utterance inside the wave buffer
@@ -197,7 +201,7 @@ __device__ __forceinline__ float fast_ln(float x) {   // x is a normal positive 
 
 // Compile-time shape of the interval table (rounds and per-round trip counts).  MelShapeRuntime reads them from MelTab;
 // MelShapeFixed lets the compiler unroll the whole mel stage and hoist its loads (the 80-mel / 512-point / 16 kHz bank
-// of the Paraformer front-end is MelShapeFixed<3, 2, 5, 9>).
+// of the Paraformer front-end is MelShapeFixed<3, 2, 5, 8>, <3, 2, 5, 9> without B200FE_MEL_COMPACT).
 struct MelShapeRuntime { static constexpr bool kFixed = false; };
 template <int R, int C0, int C1 = 0, int C2 = 0>
 struct MelShapeFixed {
@@ -206,7 +210,11 @@ struct MelShapeFixed {
   __host__ __device__ static constexpr int cnt(int r) { return r == 0 ? C0 : (r == 1 ? C1 : C2); }
   __host__ __device__ static constexpr int base(int r) { return r == 0 ? 0 : (r == 1 ? C0 : C0 + C1); }
 };
+#if B200FE_MEL_COMPACT   // the last filter's peak bin sits in the last interval there (build_interval_table): 8 trips, not 9
+using MelShapeParaformer = MelShapeFixed<3, 2, 5, 8>;
+#else
 using MelShapeParaformer = MelShapeFixed<3, 2, 5, 9>;
+#endif
 
 // One round of the interval mel: lane <-> interval 31 r + lane.  CNT >= 0: compile-time trip count (fully unrolled).
 // epi(iv, a, b, c, d) receives the natural-log mel energies of filter iv for the warp's 4 frames.
@@ -220,8 +228,24 @@ __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, 
   const float2* p0 = pg + lo;
   // packed accumulators: (frame A, frame B) of group 0 and of group 1, as the spectra are stored
   f2 up0 = make_float2(0.f, 0.f), up1 = up0, dn0 = up0, dn1 = up0;
+#if B200FE_MEL_COMPACT
+  // compact table behind the (up, down) table (build_compact_mel, b200fe.cu): u = up-slope weight, 0 in padding slots;
+  // down = scale - u where u > 0.  min(scale - u, u * 2^100) is that without a predicate (u * 2^100 >= 2^-2 for every
+  // weight a bank can hold, 0 for padding).  Only instantiated for banks the host has checked to be encodable.
+  const float* wu = reinterpret_cast<const float*>(mel.w + kMelSlots * 32) + (base * 32 + lane);
+#endif
   auto body = [&](int q) {
+#if B200FE_MEL_COMPACT
+    float2 w;
+    if constexpr (CNT >= 0) {
+      w.x = __ldg(wu + 32 * q);
+      w.y = fminf(kMelScale - w.x, w.x * 0x1p100f);
+    } else {
+      w = __ldg(wt + 32 * q);
+    }
+#else
     const float2 w = __ldg(wt + 32 * q);
+#endif
     const float2 s0 = p0[q], s1 = p0[kSpecPitch + q];
     up0 = fma2s(s0, w.x, up0);
     up1 = fma2s(s1, w.x, up1);

@@ -29,6 +29,12 @@
 #ifndef B200FE_OUT_DIRECT    // 1: the mel epilogue writes the output rows itself (32-bit stores, no staging tile)
 #define B200FE_OUT_DIRECT 0
 #endif
+#ifndef B200FE_OUT_V2        // 1: output stage on the interleaved CMVN table (QuadParams::cmvn_il): unconditional loads,
+#define B200FE_OUT_V2 1      //    packed arithmetic, one 32-bit offset per store, predicated stores (no branches, no zeroed registers)
+#endif
+#ifndef B200FE_TMA_FENCE_ALWAYS   // 1: proxy fence in front of every bulk copy; 0: only after a generic fill wrote the buffer
+#define B200FE_TMA_FENCE_ALWAYS 0
+#endif
 #ifndef B200FE_CLAIM2        // 1: quads claimed two ahead (atomic read at the end of the iteration); 0: one ahead
 #define B200FE_CLAIM2 0
 #endif
@@ -54,6 +60,7 @@ constexpr int kQuadVecs = 7;                      // float4 per lane and quad
 constexpr int kQuadBuf = kQuadVecs * 32 * 4;      // 896 floats per warp
 constexpr unsigned kNoTarget = 0xFFFFFFFFu;
 constexpr int kTargetOffBits = 27;                // output offsets inside one utterance must stay below 2^27 floats
+constexpr int kCmvnSlots = 1 << (32 - kTargetOffBits);   // slots of the interleaved CMVN table: every slot field indexes it
 
 // One unit of work, fully resolved by build_quads_kernel (64 bytes).  The first 16 bytes are everything the sample
 // fetch of a quad needs and are read one quad ahead; the second 16 bytes and the targets are read by the quad itself.
@@ -90,6 +97,7 @@ struct QuadParams {
   int mel_cnt[kMelRounds];
   int mel_base[kMelRounds];
   const float* cmvn;      // nullptr or [2][out_dim]
+  const float4* cmvn_il;  // [kCmvnSlots][n_mels / 4][2]: (shift4, scale4) of slot jj, piece l; identity when cmvn == nullptr
   const UttDesc* utts;    // [batch] in global memory: the padding fill reads n_rows from it
   int batch;
 };
@@ -170,14 +178,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 // Lane 0 only.  True when the quad's samples can be fetched with one bulk copy; then the copy is in flight.
 __device__ __forceinline__ bool quad_fill_tma(const float* wave, long long wave_total, long long g0, int n_samples,
-                                              float* buf, unsigned long long* bar) {
+                                              float* buf, unsigned long long* bar, bool generic_wrote = true) {
   const int a_off = quad_a_off<float>(wave, g0);
   const long long ga = g0 - a_off;
   const int nv = (a_off + n_samples + 3) >> 2;
   if (ga < 0 || ga + 4ll * nv > wave_total) return false;
   const unsigned bytes = 16u * (unsigned)nv;
   // earlier generic-proxy accesses of the buffer (the generic fill's stores) are ordered before the async-proxy write
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  // (a buffer that was only READ through the generic proxy since the last bulk copy needs no fence: the reads were
+  // consumed by the FFT registers before the __syncwarp in front of this call)
+  if (B200FE_TMA_FENCE_ALWAYS || generic_wrote) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(buf)), "l"(wave + ga), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -337,6 +347,13 @@ fbank_warp_kernel(const QuadParams p) {
   const float2* c0_row = fft_c0_row(tw_s, j);
   const int M4 = M >> 2;
   const bool act = lane < M4;      // lanes that move a float4 of a log-mel row (n_mels <= 128)
+#if B200FE_OUT_V2
+  // lanes beyond the row repeat its last piece (their stores are predicated off), so that every address below is valid
+  // without a predicate
+  const int lane_c = act ? lane : M4 - 1;
+  const float4* const cm_il = p.cmvn_il + 2 * lane_c;
+  const unsigned cm_slot_bytes = 32u * (unsigned)M4;
+#endif
 
   // Work distribution: the first quad of every warp is static (neighbouring warps start on neighbouring quads), all
   // later ones are claimed from a global counter one quad ahead.  The 16-byte head {g0, nF, utt} of the claimed quad and
@@ -366,9 +383,10 @@ fbank_warp_kernel(const QuadParams p) {
   // the first quad's samples: bulk copy if possible (in_flight), else filled at the top of the loop
   unsigned phase = 0;
   int in_flight = 0;
+  bool dirty = false;   // the generic fill has written the sample buffer since the last bulk copy (warp-uniform)
   if constexpr (kTma) {
     if (lane == 0)
-      in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_cur, (nF - 1) * S + L, buf, bar);
+      in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_cur, (nF - 1) * S + L, buf, bar, false);
     in_flight = __shfl_sync(0xffffffffu, in_flight, 0);
   }
 
@@ -421,6 +439,7 @@ fbank_warp_kernel(const QuadParams p) {
       phase ^= 1u;
     } else {
       quad_fill_generic<SampleT>(p.wave, p.wave_total, g0_cur, (nF - 1) * S + L, lane, buf);
+      dirty = true;
       __syncwarp();
     }
     const int a_off = quad_a_off<SampleT>(p.wave, g0_cur);
@@ -456,8 +475,9 @@ fbank_warp_kernel(const QuadParams p) {
         nF_next = hdn.z & 0xff; slow_next = (hdn.z >> 8) & 0xf; utt_next = hdn.w;
         if constexpr (kTma) {
           if (lane == 0)
-            in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_next, (nF_next - 1) * S + L, buf, bar);
+            in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_next, (nF_next - 1) * S + L, buf, bar, dirty);
           in_flight = __shfl_sync(0xffffffffu, in_flight, 0);
+          dirty = false;
         } else {
           const char* base = static_cast<const char*>(p.wave);
           const long long first = (g0_next * (long long)sizeof(SampleT) - 16) & ~127ll;
@@ -543,6 +563,73 @@ fbank_warp_kernel(const QuadParams p) {
 #endif
 
 #if B200FE_OUT_DIRECT
+#elif B200FE_OUT_V2
+    // ---- LFR + CMVN: each frame's row of n_mels goes, as 128-bit pieces, to the (row, slot) pairs of its descriptor.
+    //      The slot field of a target code indexes the interleaved CMVN table directly (kNoTarget reads its last, unused
+    //      slot), so all loads are unconditional and issued first; the arithmetic is packed; a store costs one 32-bit
+    //      offset and a predicate.  Same operation order as the reference, (x + shift) * scale (VF:34-35): bit-identical
+    //      to the scalar form.
+    {
+      char* const out_b = reinterpret_cast<char*>(p.feats + (PACKED ? (long long)hd1.w : (long long)utt * p.rows_cap) * D + 4 * lane_c);
+      const unsigned tgt[8] = {tg0.x, tg0.y, tg0.z, tg0.w, tg1.x, tg1.y, tg1.z, tg1.w};
+      const float4* lm4 = reinterpret_cast<const float4*>(lm_s) + lane_c;
+      constexpr unsigned kOffMask = (1u << kTargetOffBits) - 1;
+      auto cm_at = [&](unsigned code) {
+        return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(cm_il) + (size_t)((code >> kTargetOffBits) * cm_slot_bytes));
+      };
+      auto cmvn4 = [&](const float4& v, const float4& sh, const float4& sc) {
+        const f2 a = mul2(add2(make_float2(v.x, v.y), make_float2(sh.x, sh.y)), make_float2(sc.x, sc.y));
+        const f2 b = mul2(add2(make_float2(v.z, v.w), make_float2(sh.z, sh.w)), make_float2(sc.z, sc.w));
+        return make_float4(a.x, a.y, b.x, b.y);
+      };
+      auto store_if = [&](bool on, unsigned code, const float4& o) {
+        float* dst = reinterpret_cast<float*>(out_b + (size_t)(4u * (code & kOffMask)));
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+                     "@q st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
+                     :: "l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w), "r"((unsigned)on) : "memory");
+      };
+      float4 v[4], sh[4], sc[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4* c = cm_at(tgt[2 * t]);
+        v[t] = lm4[t * M4];
+        sh[t] = __ldg(c);
+        sc[t] = __ldg(c + 1);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) store_if(act && tgt[2 * t] != kNoTarget, tgt[2 * t], cmvn4(v[t], sh[t], sc[t]));
+      // second slot (one frame in lfr_n when lfr_m = lfr_n + 1): warp-uniform branch
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const unsigned code = tgt[2 * t + 1];
+        if (code != kNoTarget) {
+          const float4* c = cm_at(code);
+          store_if(act, code, cmvn4(v[t], __ldg(c), __ldg(c + 1)));
+        }
+      }
+      if (slow) {   // first / last frame of the utterance (replicated by the LFR padding), or lfr_m > 2 lfr_n
+        const int f0 = hd1.x, T = hd1.y, rows = hd1.z;
+#pragma unroll 1
+        for (int t = 0; t < nF; ++t) {
+          if (!((slow >> t) & 1)) continue;
+          const int f = f0 + t;
+          const int num = f + lfr_left - (lfr_m - 1);
+          const int i_lo = (f == 0 || num <= 0) ? 0 : (num + lfr_n - 1) / lfr_n;
+          const int i_top = f == T - 1 ? rows - 1 : min((f + lfr_left) / lfr_n, rows - 1);
+          const float4 vv = lm4[t * M4];
+#pragma unroll 1
+          for (int i = i_lo; i <= i_top; ++i)
+#pragma unroll 1
+            for (int jj = 0; jj < lfr_m; ++jj)
+              if (min(max(lfr_n * i + jj - lfr_left, 0), T - 1) == f) {
+                const float4* c = cm_at((unsigned)jj << kTargetOffBits);
+                const float4 o = cmvn4(vv, __ldg(c), __ldg(c + 1));
+                if (act) stg_stream4(reinterpret_cast<float*>(out_b) + (long long)i * D + jj * M, o);
+              }
+        }
+      }
+    }
+
 #elif B200FE_OUT_LEAN
     // ---- LFR + CMVN: each frame's row of n_mels goes, as 128-bit pieces, to the (row, slot) pairs of its descriptor.
     //      One divergent region for the lanes that carry a piece; inside it every branch is warp-uniform.
