@@ -28,6 +28,12 @@
 #ifndef B200FE_S1_UNCOND
 #define B200FE_S1_UNCOND 1
 #endif
+#ifndef B200FE_S2_TW_EARLY   // 1: stage 2 loads its twiddle row and column-0 weights BEFORE the barrier that follows the transpose
+#define B200FE_S2_TW_EARLY 0 //    stores (they do not depend on them), so only the transposed rows are loaded behind it
+#endif
+#ifndef B200FE_MEL_WORD_REGS // 1: the lane's interval words of a fixed-shape bank live in registers for the whole kernel
+#define B200FE_MEL_WORD_REGS 1
+#endif
 #ifndef B200FE_MEL_COMPACT   // 1: the fixed-shape mel stage reads ONE float per (bin, lane) - the up-slope weight - and derives
 #define B200FE_MEL_COMPACT 1 //    the down-slope weight (they sum to the bank's scale): half the weight bytes through L1
 #endif
@@ -191,7 +197,17 @@ struct MelTab {
   int rounds;
   int cnt[kMelRounds];
   int base[kMelRounds];
+#if B200FE_MEL_WORD_REGS
+  unsigned word[3];   // fixed-shape banks: this lane's interval words, loaded once per kernel (mel_preload)
+#endif
 };
+
+__device__ __forceinline__ void mel_preload(MelTab& mel, int lane) {
+#if B200FE_MEL_WORD_REGS
+#pragma unroll
+  for (int r = 0; r < 3; ++r) mel.word[r] = (unsigned)__ldg(mel.lo + 32 * r + lane);
+#endif
+}
 
 __device__ __forceinline__ float fast_ln(float x) {   // x is a normal positive number (>= the log floor)
   float y;
@@ -222,7 +238,11 @@ template <int CNT, class EPI>
 __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, int base, const float2* pg, int lane, int M,
                                           float log_floor, EPI&& epi) {
   const int cnt = CNT >= 0 ? CNT : cnt_rt;
+#if B200FE_MEL_WORD_REGS
+  const unsigned word = CNT >= 0 ? mel.word[r < 3 ? r : 0] : (unsigned)__ldg(mel.lo + 32 * r + lane);
+#else
   const unsigned word = (unsigned)__ldg(mel.lo + 32 * r + lane);   // run start | partner lane | filter | outputs
+#endif
   const int lo = (int)(word & 0xfffu), partner = (int)((word >> 12) & 31u), iv = (int)((word >> 17) & 0xffu);
   const float2* wt = mel.w + (base * 32 + lane);
   const float2* p0 = pg + lo;
@@ -494,6 +514,14 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
     yg2[15 * 2 * kYPitch + hi] = make_float2(0.f, 0.f);
   }
   reinterpret_cast<float2*>(yg + 16 * kYPitch)[j] = y0;
+#if B200FE_S2_TW_EARLY
+  float2 tw_e[16];
+  float4 c0w_e[4];
+#pragma unroll
+  for (int h = 0; h < 16; ++h) tw_e[h] = tw_row[h];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) c0w_e[h] = reinterpret_cast<const float4*>(c0_row)[h];
+#endif
   __syncwarp();
 
   // Stage 2 is assigned across the warp, not per group: lanes 2c and 2c+1 transform column c (16 for c = 0) of group 0
@@ -508,7 +536,11 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
     const float4* rowp = ywarp + g2 * kYGroupF4 + (col - 1) * kYPitch;
     static_for<0, 8>([&](auto ic) {
       constexpr int h = decltype(ic)::value;
+#if B200FE_S2_TW_EARLY
+      const float2 ta = tw_e[2 * h], tb = tw_e[2 * h + 1];
+#else
       const float2 ta = tw_row[2 * h], tb = tw_row[2 * h + 1];
+#endif
       const float4 t = make_float4(ta.x, ta.y, tb.x, tb.y);
       const float4 v0 = rowp[2 * h], v1 = rowp[2 * h + 1];
       constexpr bool sw = 2 * h >= 8;   // slots 8..15 are stored (im, re)
@@ -537,7 +569,11 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
     f2 cr = make_float2(0.f, 0.f), ci = make_float2(0.f, 0.f);
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
+#if B200FE_S2_TW_EARLY
+      const float4 ua = u4[h], ub = u4[h + 4], w = c0w_e[h];
+#else
       const float4 ua = u4[h], ub = u4[h + 4], w = w4[h];
+#endif
       const f2 v0 = fma2s(make_float2(ub.x, ub.y), sgn, make_float2(ua.x, ua.y));
       const f2 v1 = fma2s(make_float2(ub.z, ub.w), sgn, make_float2(ua.z, ua.w));
       cr = fma2s(v0, w.x, cr);
@@ -618,6 +654,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   MelTab mel;
   mel.w = p.mel_w; mel.lo = p.mel_lo; mel.rounds = p.mel_rounds;
+  mel_preload(mel, threadIdx.x & 31);
 #pragma unroll
   for (int r = 0; r < kMelRounds; ++r) { mel.cnt[r] = p.mel_cnt[r]; mel.base[r] = p.mel_base[r]; }
   float win[NROWS + 1];

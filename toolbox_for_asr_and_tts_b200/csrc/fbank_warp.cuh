@@ -35,6 +35,15 @@
 #ifndef B200FE_TMA_FENCE_ALWAYS   // 1: proxy fence in front of every bulk copy; 0: only after a generic fill wrote the buffer
 #define B200FE_TMA_FENCE_ALWAYS 0
 #endif
+#ifndef B200FE_CLAIM_LATE    // 1 (needs DESC_SMEM): the work counter's atomic is issued at the top of a quad but its result is
+#define B200FE_CLAIM_LATE 1  //    first read after stage 1; the next quad's head is fetched behind stage 2 and its bulk copy
+#endif                       //    issued after stage 2: neither the atomic's nor the head's latency is exposed
+#ifndef B200FE_CMVN_EARLY    // 1 (OUT_V2): the CMVN entries of the quad's primary targets are loaded BEFORE the mel stage, so
+#define B200FE_CMVN_EARLY 0  //    their L1 latency hides behind it instead of sitting in front of the row stores
+#endif
+#ifndef B200FE_TMA_UNIFORM   // 1: every lane evaluates whether the next quad takes the bulk copy (no broadcast from lane 0)
+#define B200FE_TMA_UNIFORM 1
+#endif
 #ifndef B200FE_CLAIM2        // 1: quads claimed two ahead (atomic read at the end of the iteration); 0: one ahead
 #define B200FE_CLAIM2 0
 #endif
@@ -174,6 +183,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Every lane: the quad's samples can be fetched with one bulk copy (16-byte aligned, in-bounds ends).
+__device__ __forceinline__ bool quad_tma_ok(const float* wave, long long wave_total, long long g0, int n_samples) {
+  const int a_off = quad_a_off<float>(wave, g0);
+  const long long ga = g0 - a_off;
+  const int nv = (a_off + n_samples + 3) >> 2;
+  return !(ga < 0 || ga + 4ll * nv > wave_total);
 }
 
 // Lane 0 only.  True when the quad's samples can be fetched with one bulk copy; then the copy is in flight.
@@ -328,6 +345,7 @@ fbank_warp_kernel(const QuadParams p) {
   }
   MelTab mel;
   mel.w = p.mel_w; mel.lo = p.mel_lo; mel.rounds = p.mel_rounds;
+  mel_preload(mel, threadIdx.x & 31);
 #pragma unroll
   for (int r = 0; r < kMelRounds; ++r) { mel.cnt[r] = p.mel_cnt[r]; mel.base[r] = p.mel_base[r]; }
   float win[NROWS + 1];
@@ -398,6 +416,15 @@ fbank_warp_kernel(const QuadParams p) {
     const int qn = q + first_wave;
     const bool have_next = qn < p.n_quads;
     const int4 hdn = __ldg(reinterpret_cast<const int4*>(p.quads + min(qn, last_quad)));
+#elif B200FE_CLAIM_LATE && B200FE_DESC_SMEM
+    int qn = 0;
+    if (lane == 0) qn = first_wave + atomicAdd(p.next_quad, 1);   // consumed after stage 1
+    bool have_next = false;
+    if (lane >= 1 && lane < 4) {   // the rest of this quad's descriptor
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&desc_s[warp][lane])),
+                   "l"(reinterpret_cast<const int4*>(p.quads + q) + lane) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 #else
     int qn = 0;
     if (lane == 0) qn = first_wave + atomicAdd(p.next_quad, 1);
@@ -465,6 +492,17 @@ fbank_warp_kernel(const QuadParams p) {
       // ---- the next quad's samples start their way from HBM now: one bulk copy into the (now free) buffer, or one L2
       //      prefetch per 128-byte line for the generic fill
       in_flight = 0;
+#if B200FE_CLAIM_LATE && B200FE_DESC_SMEM
+      // the claim's result is read here; the claimed quad's head travels while stage 2 runs
+      qn = __shfl_sync(0xffffffffu, qn, 0);
+      have_next = qn < p.n_quads;
+      if (lane == 0) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&desc_s[warp][0])),
+                     "l"(reinterpret_cast<const int4*>(p.quads + min(qn, last_quad))) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
+#endif
 #if B200FE_DESC_SMEM
       if (lane < 4) asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
@@ -474,9 +512,15 @@ fbank_warp_kernel(const QuadParams p) {
         g0_next = ((long long)hdn.y << 32) | (unsigned)hdn.x;
         nF_next = hdn.z & 0xff; slow_next = (hdn.z >> 8) & 0xf; utt_next = hdn.w;
         if constexpr (kTma) {
+#if B200FE_TMA_UNIFORM
+          in_flight = quad_tma_ok(static_cast<const float*>(p.wave), p.wave_total, g0_next, (nF_next - 1) * S + L);
+          if (lane == 0 && in_flight)
+            quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_next, (nF_next - 1) * S + L, buf, bar, dirty);
+#else
           if (lane == 0)
             in_flight = quad_fill_tma(static_cast<const float*>(p.wave), p.wave_total, g0_next, (nF_next - 1) * S + L, buf, bar, dirty);
           in_flight = __shfl_sync(0xffffffffu, in_flight, 0);
+#endif
           dirty = false;
         } else {
           const char* base = static_cast<const char*>(p.wave);
@@ -493,7 +537,9 @@ fbank_warp_kernel(const QuadParams p) {
         for (int it = q + p.n_quads; it < n_pad_items; it += p.n_quads)      // fewer quads than pieces: rare
           pad_piece_store(p.feats, p.rows_cap, D, it, __ldg(&p.utts[it >> kPadPieceShift].n_rows), zero_block);
       }
+#if !(B200FE_CLAIM_LATE && B200FE_DESC_SMEM)
       quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
+#endif
     }
 #if B200FE_DESC_SMEM
 #define tg0 (*reinterpret_cast<const uint4*>(const_cast<const int4*>(ds + 2)))
@@ -552,6 +598,19 @@ fbank_warp_kernel(const QuadParams p) {
       });
     }
 #else
+#if B200FE_OUT_V2 && B200FE_CMVN_EARLY
+    float4 sh_e[4], sc_e[4];
+    {
+      const unsigned t4[4] = {tg0.x, tg0.z, tg1.x, tg1.z};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4* c = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(cm_il) +
+                                                          (size_t)((t4[t] >> kTargetOffBits) * cm_slot_bytes));
+        sh_e[t] = __ldg(c);
+        sc_e[t] = __ldg(c + 1);
+      }
+    }
+#endif
     // ---- log-mel of the 4 frames into the warp's staging tile
     mel_stage<MELS>(mel, pbuf4, lane, M, p.log_floor, [&](int iv, float a, float b, float c, float d) {
       lm_s[iv] = a;
@@ -591,10 +650,15 @@ fbank_warp_kernel(const QuadParams p) {
       float4 v[4], sh[4], sc[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float4* c = cm_at(tgt[2 * t]);
         v[t] = lm4[t * M4];
+#if B200FE_CMVN_EARLY
+        sh[t] = sh_e[t];
+        sc[t] = sc_e[t];
+#else
+        const float4* c = cm_at(tgt[2 * t]);
         sh[t] = __ldg(c);
         sc[t] = __ldg(c + 1);
+#endif
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) store_if(act && tgt[2 * t] != kNoTarget, tgt[2 * t], cmvn4(v[t], sh[t], sc[t]));

@@ -166,6 +166,7 @@ stream_push_kernel(const StreamParams p) {
   for (int i = tid; i < kTw2Total; i += kCtaThreads) tw_s[i] = p.twiddle[i];
   MelTab mel;
   mel.w = p.mel_w; mel.lo = p.mel_lo; mel.rounds = p.mel_rounds;
+  mel_preload(mel, threadIdx.x & 31);
 #pragma unroll
   for (int r = 0; r < kMelRounds; ++r) { mel.cnt[r] = p.mel_cnt[r]; mel.base[r] = p.mel_base[r]; }
   float win[NROWS + 1];
@@ -580,6 +581,7 @@ stream_quad_kernel(const StreamParams p) {
   }
   MelTab mel;
   mel.w = p.mel_w; mel.lo = p.mel_lo; mel.rounds = p.mel_rounds;
+  mel_preload(mel, threadIdx.x & 31);
 #pragma unroll
   for (int r = 0; r < kMelRounds; ++r) { mel.cnt[r] = p.mel_cnt[r]; mel.base[r] = p.mel_base[r]; }
   float win[NROWS + 1];
