@@ -625,7 +625,10 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
       tw[(k1 - 1) * kTwPitch + c] =
           make_float2((float)(sc * cos(2.0 * M_PI * ph / 512.0)), (float)(-sc * sin(2.0 * M_PI * ph / 512.0)));
     }
-  for (int t = 0; t < 8; ++t)
+#if B200FE_C0_SHFL
+  fill_c0_lane_table(tw.data() + kTw2Table);
+#endif
+  for (int t = 0; t < 8 && !B200FE_C0_SHFL; ++t)
     for (int c = 0; c < 8; ++c) {
       const int ph = (c * t) % 16;
       tw[kTw2Table + t * kC0Pitch + c] =

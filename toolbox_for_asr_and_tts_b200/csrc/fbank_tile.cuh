@@ -28,6 +28,12 @@
 #ifndef B200FE_S1_UNCOND
 #define B200FE_S1_UNCOND 1
 #endif
+#ifndef B200FE_DC_LATE       // 1: stage 1 multiplies by the window BEFORE the frame-mean shuffle reduction and adds -(1-p) mean w[n]
+#define B200FE_DC_LATE 0     //    afterwards (one FMA): the 25 multiplies run while the 4 shuffle levels are in flight
+#endif
+#ifndef B200FE_C0_SHFL       // 1: column 0 of the spectrum (bins 32 t) by a 16-point radix-2 FFT ACROSS the 16 lanes of a group (14
+#define B200FE_C0_SHFL 1     //    shuffles, 3 table loads) instead of 8 broadcast row loads + 4 table loads per lane through shared memory
+#endif
 #ifndef B200FE_S2_TW_EARLY   // 1: stage 2 loads its twiddle row and column-0 weights BEFORE the barrier that follows the transpose
 #define B200FE_S2_TW_EARLY 0 //    stores (they do not depend on them), so only the transposed rows are loaded behind it
 #endif
@@ -59,6 +65,9 @@ constexpr int kTwPitch = 17;         // float2 per row: 136 B, so the 16 lanes o
 constexpr int kTw2Table = 16 * kTwPitch;
 constexpr int kC0Pitch = 10;                      // float2; 80 B rows: conflict-free 128-bit reads by 8 threads
 constexpr int kTw2Total = kTw2Table + 8 * kC0Pitch;       // float2
+constexpr int kC0sPitch = 5;                      // B200FE_C0_SHFL: [16 lanes][kC0sPitch] float2 in the same 80 float2: the lane's
+                                                  // twiddles of butterfly stages 0..2; 40 B rows: conflict-free 64-bit reads
+static_assert(16 * kC0sPitch <= 8 * kC0Pitch, "the lane-FFT table must fit the column-0 table");
 constexpr int kMaxMels = 128;
 constexpr int kMaxInt = kMaxMels + 1;  // intervals between consecutive filter centres
 constexpr int kMelRounds = (kMaxMels + 30) / 31;  // rounds of 31 filters: lane <-> interval, lane 31 only feeds lane 30
@@ -337,6 +346,28 @@ __device__ __forceinline__ const float2* fft_twiddle_row(const float2* tw_s, int
 __device__ __forceinline__ const float2* fft_c0_row(const float2* tw_s, int j) {
   return tw_s + kTw2Table + ((j >> 1) & 7) * kC0Pitch;
 }
+// B200FE_C0_SHFL: this lane's twiddles of the 16-point FFT across the lanes of its group (fill_c0_lane_table).
+__device__ __forceinline__ const float2* fft_c0s_row(const float2* tw_s, int j) {
+#if B200FE_C0_SHFL
+  return tw_s + kTw2Table + j * kC0sPitch;
+#else
+  return fft_c0_row(tw_s, j);
+#endif
+}
+// Host: entry [j][s], s = 0..2, of that table.  Decimation in frequency over the lane index with xor distances
+// D = 8, 4, 2, 1: a lane whose bit D is clear keeps a + b, the other one (a - b) W_2D^(j mod D); stage 0 carries the
+// factor 2 every stored spectrum value has.  Stage 3 has no twiddle.  After the four stages lane j holds bin
+// 32 * bitrev4(j).
+inline void fill_c0_lane_table(float2* tab /* [16 * kC0sPitch] */) {
+  for (int j = 0; j < 16; ++j)
+    for (int s = 0; s < 3; ++s) {
+      const int D = 8 >> s;
+      const bool upper = (j & D) != 0;
+      const double ang = -2.0 * 3.14159265358979323846 * (double)(j & (D - 1)) / (double)(2 * D);
+      const double sc = s == 0 ? 2.0 : 1.0;
+      tab[j * kC0sPitch + s] = upper ? make_float2((float)(sc * cos(ang)), (float)(sc * sin(ang))) : make_float2((float)sc, 0.f);
+    }
+}
 
 // ROT: the second 16-thread group of a warp loads its samples one 16-sample row late (register i holds row i-1).
 // Frames start 160 samples = 5*32 banks apart, so without this both groups of a warp would hit the same 16 banks on
@@ -466,6 +497,10 @@ __device__ __forceinline__ void quad_stage1(const float* xA, bool vA, bool vB, i
       }
       s = fma2s(gs, dither, s);
     }
+#if B200FE_DC_LATE
+#pragma unroll
+    for (int i = 0; i < NR; ++i) y[i] = mul2s(y[i], win[i]);
+#endif
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) {
       f2 t;
@@ -477,7 +512,11 @@ __device__ __forceinline__ void quad_stage1(const float* xA, bool vA, bool vB, i
     f2 nmean = make_float2(0.f, 0.f);
     if (remove_dc) nmean = mul2s(s, -(1.0f - preemph) / (float)L);
 #pragma unroll
+#if B200FE_DC_LATE
+    for (int i = 0; i < NR; ++i) y[i] = fma2s(nmean, win[i], y[i]);
+#else
     for (int i = 0; i < NR; ++i) y[i] = fma2s(y[i], win[i], mul2s(nmean, win[i]));
+#endif
     // z[m] = y[2m] + i y[2m+1] at bit-reversed positions (decimation in time)
     static_for<0, 16>([&](auto ic) {
       constexpr int m = decltype(ic)::value;
@@ -513,14 +552,18 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
     yg2[15 * 2 * kYPitch + hr] = y16;
     yg2[15 * 2 * kYPitch + hi] = make_float2(0.f, 0.f);
   }
+#if !B200FE_C0_SHFL
   reinterpret_cast<float2*>(yg + 16 * kYPitch)[j] = y0;
+#endif
 #if B200FE_S2_TW_EARLY
   float2 tw_e[16];
   float4 c0w_e[4];
 #pragma unroll
   for (int h = 0; h < 16; ++h) tw_e[h] = tw_row[h];
+#if !B200FE_C0_SHFL
 #pragma unroll
   for (int h = 0; h < 4; ++h) c0w_e[h] = reinterpret_cast<const float4*>(c0_row)[h];
+#endif
 #endif
   __syncwarp();
 
@@ -560,6 +603,37 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
   }
   // ---- column 0 of the lane's OWN group (half-warp): lanes 2t and 2t+1 both sum the 16 real bins Y_c[0] against
   //      W16^(c t), folded to 8 terms (the pair's identical loads merge; the even lane stores)
+#if B200FE_C0_SHFL
+  // ---- column 0 of the lane's OWN group: X[32 t] = 2 sum_j Y_j[0] W16^(j t) is a 16-point DFT of the REAL values the
+  //      16 lanes hold in y0: four butterfly stages over xor-shuffles (2 + 4 + 4 + 4 shuffles for the packed pair of
+  //      frames), the lane's three twiddles from the table, signs from the lane's bits.  Lane j ends up with bin
+  //      32 * bitrev4(j); bins 0..224 sit on the even lanes.
+  const int t0 = (int)(__brev((unsigned)j) >> 28);      // bitrev4(j): below 8 on the even lanes, the ones that store
+  f2 p0;
+  {
+    const unsigned jb = (unsigned)j << 28;               // bit 3 of j in the sign position
+    auto sgn = [&](int s) { return __uint_as_float(0x3f800000u | ((jb << s) & 0x80000000u)); };
+    auto xchg = [&](const f2& v, int d) {
+      return make_float2(__shfl_xor_sync(0xffffffffu, v.x, d), __shfl_xor_sync(0xffffffffu, v.y, d));
+    };
+    const float2 w0 = c0_row[0], w1 = c0_row[1], w2 = c0_row[2];
+    f2 d = fma2s(y0, sgn(0), xchg(y0, 8));
+    f2 cr = mul2s(d, w0.x), ci = mul2s(d, w0.y);
+    {
+      const f2 dr = fma2s(cr, sgn(1), xchg(cr, 4)), di = fma2s(ci, sgn(1), xchg(ci, 4));
+      cr = fma2s(dr, w1.x, neg2(mul2s(di, w1.y)));
+      ci = fma2s(dr, w1.y, mul2s(di, w1.x));
+    }
+    {
+      const f2 dr = fma2s(cr, sgn(2), xchg(cr, 2)), di = fma2s(ci, sgn(2), xchg(ci, 2));
+      cr = fma2s(dr, w2.x, neg2(mul2s(di, w2.y)));
+      ci = fma2s(dr, w2.y, mul2s(di, w2.x));
+    }
+    cr = fma2s(cr, sgn(3), xchg(cr, 1));
+    ci = fma2s(ci, sgn(3), xchg(ci, 1));
+    p0 = fma2(cr, cr, mul2(ci, ci));
+  }
+#else
   const int t0 = (lane >> 1) & 7;
   f2 p0;
   {
@@ -583,6 +657,7 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
     }
     p0 = fma2(cr, cr, mul2(ci, ci));
   }
+#endif
   fft_dit2<16>(ar, ai);
   __syncwarp();   // every lane has consumed the transpose buffers: the spectra may overwrite them
   {
@@ -693,7 +768,7 @@ fbank_lfr_cmvn_tile_kernel(const TileParams p) {
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;   // this group's transpose buffer
   float4* pbuf4 = xbuf + warp * kYWarpF4;                          // this warp's power spectra (aliases both groups)
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = fft_c0_row(tw_s, j);
+  const float2* c0_row = fft_c0s_row(tw_s, j);
 
     // Work distribution: the first tile of every CTA is static, later ones are claimed from a global counter (thread 0,
   // published through shared memory across the barrier that follows the staging).

@@ -362,7 +362,7 @@ fbank_warp_kernel(const QuadParams p) {
   float4* pbuf4 = xbuf + warp * kYWarpF4;
   float* lm_s = reinterpret_cast<float*>(pbuf4 + kSpecF4);   // log-mel staging tile, behind the warp's spectra
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = fft_c0_row(tw_s, j);
+  const float2* c0_row = fft_c0s_row(tw_s, j);
   const int M4 = M >> 2;
   const bool act = lane < M4;      // lanes that move a float4 of a log-mel row (n_mels <= 128)
 #if B200FE_OUT_V2

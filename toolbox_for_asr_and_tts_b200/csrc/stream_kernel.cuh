@@ -196,7 +196,7 @@ stream_push_kernel(const StreamParams p) {
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;
   float4* pbuf4 = xbuf + warp * kYWarpF4;
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = fft_c0_row(tw_s, j);
+  const float2* c0_row = fft_c0s_row(tw_s, j);
   if constexpr (PERQUAD) {
     // every warp fetches, transforms and mel-projects its own quads: no CTA-wide staging
     float* buf = e_s + warp * kQuadBuf;
@@ -594,7 +594,7 @@ stream_quad_kernel(const StreamParams p) {
   float4* pbuf4 = xbuf + warp * kYWarpF4;
   float* lm_s = reinterpret_cast<float*>(pbuf4 + kSpecF4);   // log-mel staging tile, behind the warp's spectra
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = fft_c0_row(tw_s, j);
+  const float2* c0_row = fft_c0s_row(tw_s, j);
   const int4* ticks = p.lay.tick(p.state);
 
   const int q_max = p.lay.q_max;

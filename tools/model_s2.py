@@ -45,13 +45,23 @@ def group_power(x, g):
                 P[col + 32 * k2] = abs(X[k2]) ** 2
             elif j != 0:
                 P[(32 - col) + 32 * (15 - k2)] = abs(X[k2]) ** 2
-    # column 0, direct: thread t -> bin 32 t
-    u = xg[0, :].real
-    for t in range(8):
-        s = 1.0 if t % 2 == 0 else -1.0
-        v = u[:8] + s * u[8:]
-        U = sum(v[c] * 2.0 * W(16, c * t) for c in range(8))
-        P[32 * t] = abs(U) ** 2
+    # column 0: a 16-point FFT of the real values Y_j[0] ACROSS the 16 lanes of the group (B200FE_C0_SHFL, quad_stage2):
+    # decimation in frequency over the lane index with xor distances 8, 4, 2, 1 - a lane whose bit D is clear keeps
+    # a + b, its partner (a - b) * W_2D^(j mod D); stage 0 carries the factor 2, stage 3 has no twiddle.  Lane j ends up
+    # with bin 32 * bitrev4(j); the even lanes hold bins 0 .. 224.
+    z = xg[0, :].real.astype(complex)
+    for s, D in enumerate((8, 4, 2, 1)):
+        nz = np.empty(16, complex)
+        for j in range(16):
+            p = z[j ^ D]
+            upper = (j & D) != 0
+            d = p - z[j] if upper else p + z[j]
+            w = W(2 * D, j & (D - 1)) if (upper and D > 1) else 1.0
+            nz[j] = d * w * (2.0 if s == 0 else 1.0)
+        z = nz
+    for j in range(0, 16, 2):
+        t = int(format(j, "04b")[::-1], 2)
+        P[32 * t] = abs(z[j]) ** 2
     return P[:256]
 
 
