@@ -44,6 +44,9 @@
 #ifndef B200FE_TMA_UNIFORM   // 1: every lane evaluates whether the next quad takes the bulk copy (no broadcast from lane 0)
 #define B200FE_TMA_UNIFORM 1
 #endif
+#ifndef B200FE_CLAIM_ASM     // 1 (CLAIM_LATE): the counter's atomic as plain PTX, not atomicAdd() (see the call site)
+#define B200FE_CLAIM_ASM 1
+#endif
 #ifndef B200FE_CLAIM2        // 1: quads claimed two ahead (atomic read at the end of the iteration); 0: one ahead
 #define B200FE_CLAIM2 0
 #endif
@@ -324,6 +327,10 @@ fbank_warp_kernel(const QuadParams p) {
   // per warp: [0] head of the next quad, [1..3] the rest of the current quad's descriptor ({f0, T, rows, row_begin}, targets)
   __shared__ __align__(16) int4 desc_s[kWarps][4];
 #endif
+#if B200FE_CLAIM_ASM
+  __shared__ int claim_zero[kWarps];   // zeros, see the work claim
+  if (threadIdx.x < kWarps) claim_zero[threadIdx.x] = 0;
+#endif
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -418,7 +425,18 @@ fbank_warp_kernel(const QuadParams p) {
     const int4 hdn = __ldg(reinterpret_cast<const int4*>(p.quads + min(qn, last_quad)));
 #elif B200FE_CLAIM_LATE && B200FE_DESC_SMEM
     int qn = 0;
-    if (lane == 0) qn = first_wave + atomicAdd(p.next_quad, 1);   // consumed after stage 1
+#if B200FE_CLAIM_ASM
+    // atom.inc, not atom.add / atomicAdd(): ptxas turns an add under a divergent branch into a warp-aggregated sequence (vote, leader atomic,
+    // SHFL of the result) whose shuffle waits for the atomic on the spot - the round trip this variant is about
+    if (lane == 0) {
+      // the address goes through a value ptxas cannot prove warp-uniform (a zero read back from shared memory): an
+      // atomic on a provably uniform address is aggregated whatever its width or spelling (add, inc, inline PTX)
+      const int* ctr = p.next_quad + *const_cast<const volatile int*>(&claim_zero[warp]);
+      asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(qn) : "l"(ctr) : "memory");
+    }
+#else
+    if (lane == 0) qn = atomicAdd(p.next_quad, 1);   // consumed after stage 1
+#endif
     bool have_next = false;
     if (lane >= 1 && lane < 4) {   // the rest of this quad's descriptor
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&desc_s[warp][lane])),
@@ -494,7 +512,7 @@ fbank_warp_kernel(const QuadParams p) {
       in_flight = 0;
 #if B200FE_CLAIM_LATE && B200FE_DESC_SMEM
       // the claim's result is read here; the claimed quad's head travels while stage 2 runs
-      qn = __shfl_sync(0xffffffffu, qn, 0);
+      qn = first_wave + __shfl_sync(0xffffffffu, qn, 0);
       have_next = qn < p.n_quads;
       if (lane == 0) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&desc_s[warp][0])),
