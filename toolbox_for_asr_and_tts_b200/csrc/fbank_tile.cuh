@@ -28,6 +28,9 @@
 #ifndef B200FE_S1_UNCOND
 #define B200FE_S1_UNCOND 1
 #endif
+#ifndef B200FE_DC_REDUCE4    // 1: the frame sums are reduced over the 16 lanes in TWO dependent levels of three independent shuffles
+#define B200FE_DC_REDUCE4 0  //    (lanes j^1, j^2, j^3, then j^4, j^8, j^12) instead of four levels of one: 12 shuffles, half the chain
+#endif
 #ifndef B200FE_DC_LATE       // 1: stage 1 multiplies by the window BEFORE the frame-mean shuffle reduction and adds -(1-p) mean w[n]
 #define B200FE_DC_LATE 0     //    afterwards (one FMA): the 25 multiplies run while the 4 shuffle levels are in flight
 #endif
@@ -501,6 +504,17 @@ __device__ __forceinline__ void quad_stage1(const float* xA, bool vA, bool vB, i
 #pragma unroll
     for (int i = 0; i < NR; ++i) y[i] = mul2s(y[i], win[i]);
 #endif
+#if B200FE_DC_REDUCE4
+#pragma unroll
+    for (int lvl = 0; lvl < 2; ++lvl) {
+      const int o = lvl ? 4 : 1;
+      f2 t1, t2, t3;
+      t1.x = __shfl_xor_sync(0xffffffffu, s.x, o);     t1.y = __shfl_xor_sync(0xffffffffu, s.y, o);
+      t2.x = __shfl_xor_sync(0xffffffffu, s.x, 2 * o); t2.y = __shfl_xor_sync(0xffffffffu, s.y, 2 * o);
+      t3.x = __shfl_xor_sync(0xffffffffu, s.x, 3 * o); t3.y = __shfl_xor_sync(0xffffffffu, s.y, 3 * o);
+      s = add2(add2(s, t1), add2(t2, t3));
+    }
+#else
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) {
       f2 t;
@@ -508,6 +522,7 @@ __device__ __forceinline__ void quad_stage1(const float* xA, bool vA, bool vB, i
       t.y = __shfl_xor_sync(0xffffffffu, s.y, o);
       s = add2(s, t);
     }
+#endif
     // -(1-p) * mean(frame), applied inside the window FMA: e*w - ((1-p) mean)*w rounds once, after the subtraction
     f2 nmean = make_float2(0.f, 0.f);
     if (remove_dc) nmean = mul2s(s, -(1.0f - preemph) / (float)L);
