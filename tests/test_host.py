@@ -201,3 +201,43 @@ def test_online_frontend_host_mirror_counts_rows_like_the_oracle():
                 assert fe._rows_after_push(st, m, fin) == want, (lfr_m, lfr_n, n, pos, m)
                 pos += m
             assert st == dict(carry=0, frames=0, rows=0)
+
+
+def test_numpy_model_of_the_packed_fft_data_flow():
+    """tools/model_s2.py restates quad_stage1 / quad_stage2 (fbank_tile.cuh) in numpy - the rotated second group, the
+    17-column transpose, the column-0 FFT across the lanes of a group - and compares it with np.fft.rfft."""
+    import runpy
+    from pathlib import Path
+    runpy.run_path(str(Path(__file__).resolve().parents[1] / "tools" / "model_s2.py"), run_name="__main__")
+
+
+def test_compact_mel_weight_rule_against_the_reference_bank():
+    """The fixed-shape mel stage stores one weight u per (bin, interval) and derives the other slope as
+    min(1/4 - u, u * 2^100) (fbank_tile.cuh, B200FE_MEL_COMPACT).  Check the rule on the reference's own bank
+    (TA:436-511): in float32, for every bin that feeds two filters, up + down == 1 to rounding, so the derived weight
+    is within 2^-24 of the stored one and the mel energies move by less than 1e-6 relative."""
+    import numpy as np
+    import torch
+    from torchaudio.compliance import kaldi
+    bank, _ = kaldi.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)   # [80, 256]
+    bank = bank.numpy().astype(np.float32)
+    scale = np.float32(0.25)
+    derived = np.zeros_like(bank)
+    for k in range(1, bank.shape[1]):
+        nz = np.nonzero(bank[:, k])[0]
+        assert len(nz) <= 2 and (len(nz) < 2 or nz[1] == nz[0] + 1)
+        if len(nz) == 2:                       # interval nz[1]: up-slope of nz[1], down-slope of nz[0]
+            u = scale * bank[nz[1], k]
+            d = np.minimum(scale - u, u * np.float32(2.0 ** 100))
+            derived[nz[1], k] = u
+            derived[nz[0], k] = d
+            assert abs(float(d) - float(scale * bank[nz[0], k])) <= 2.0 ** -24
+        elif len(nz) == 1:
+            derived[nz[0], k] = scale * bank[nz[0], k]
+    rng = np.random.default_rng(0)
+    power = rng.random((64, 256)).astype(np.float64) * 1e6
+    e_ref = power @ (0.25 * bank.astype(np.float64)).T
+    e_new = power @ derived.astype(np.float64).T
+    assert np.max(np.abs(e_new - e_ref) / e_ref) < 1e-6
+    # padding slots: u == 0 -> both weights 0
+    assert np.minimum(scale - np.float32(0), np.float32(0) * np.float32(2.0 ** 100)) == 0
