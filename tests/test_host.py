@@ -241,3 +241,36 @@ def test_compact_mel_weight_rule_against_the_reference_bank():
     assert np.max(np.abs(e_new - e_ref) / e_ref) < 1e-6
     # padding slots: u == 0 -> both weights 0
     assert np.minimum(scale - np.float32(0), np.float32(0) * np.float32(2.0 ** 100)) == 0
+
+
+def test_host_affinity_bind_and_restore_round_trip():
+    """bench.py binds a rank to its GPU's NUMA node before the pinned allocations and gives every thread its original
+    CPU set back before the CPU baseline runs (hostaffinity.restore_affinity walks /proc/self/task)."""
+    import os
+    import threading
+    from toolbox_for_asr_and_tts_b200 import hostaffinity
+    if not hasattr(os, "sched_getaffinity"):
+        pytest.skip("no sched_getaffinity on this platform")
+    before = os.sched_getaffinity(0)
+    one = {min(before)}
+    seen = {}
+    started, release = threading.Event(), threading.Event()
+
+    def worker():
+        seen["tid"] = threading.get_native_id()
+        started.set()
+        release.wait(10)
+
+    os.sched_setaffinity(0, one)
+    try:
+        t = threading.Thread(target=worker)
+        t.start()                       # inherits the narrow mask, like a worker pool created while bound
+        started.wait(10)
+        assert os.sched_getaffinity(seen["tid"]) == one
+        hostaffinity.restore_affinity(before)
+        assert os.sched_getaffinity(0) == before and os.sched_getaffinity(seen["tid"]) == before
+    finally:
+        release.set()
+        t.join()
+        os.sched_setaffinity(0, before)
+    assert hostaffinity.ingest_threads(1) >= 2
