@@ -55,6 +55,7 @@ struct b200fe_handle {
   int mel_rounds = 0, mel_cnt[kMelRounds] = {0}, mel_base[kMelRounds] = {0};
   bool mel_paraformer = false;      // table shape == MelShapeParaformer: fully unrolled mel stage
   float* d_cmvn = nullptr;          // [2*D]
+  float2* d_twiddle_stream = nullptr;   // the same twiddles with the [8][kC0Pitch] column-0 table (stream kernels)
   float4* d_cmvn_il = nullptr;      // warp kernel: [32 slots][n_mels/4][shift4, scale4], identity without CMVN (fbank_warp.cuh)
   // dense mel banks for shrunken frames (VF:147), keyed by fft size
   std::map<int, int> short_mel_off;
@@ -625,10 +626,7 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
       tw[(k1 - 1) * kTwPitch + c] =
           make_float2((float)(sc * cos(2.0 * M_PI * ph / 512.0)), (float)(-sc * sin(2.0 * M_PI * ph / 512.0)));
     }
-#if B200FE_C0_SHFL
-  fill_c0_lane_table(tw.data() + kTw2Table);
-#endif
-  for (int t = 0; t < 8 && !B200FE_C0_SHFL; ++t)
+  for (int t = 0; t < 8; ++t)
     for (int c = 0; c < 8; ++c) {
       const int ph = (c * t) % 16;
       tw[kTw2Table + t * kC0Pitch + c] =
@@ -636,9 +634,17 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
     }
   CK(cudaMalloc(&h->d_window, 512 * sizeof(float)));
   CK(cudaMalloc(&h->d_twiddle, tw.size() * sizeof(float2)));
+  CK(cudaMalloc(&h->d_twiddle_stream, tw.size() * sizeof(float2)));
   CK(cudaMalloc(&h->d_mel_w, mw.size() * sizeof(float2)));
   CK(cudaMalloc(&h->d_mel_lo, mlo.size() * sizeof(int)));
   CK(cudaMemcpy(h->d_window, win512.data(), 512 * sizeof(float), cudaMemcpyHostToDevice));
+  // tw carries the [8][kC0Pitch] column-0 table here: that copy is the stream kernels'; the offline kernels' copy gets
+  // the lane-FFT twiddles in its place (B200FE_C0_SHFL)
+  CK(cudaMemcpy(h->d_twiddle_stream, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+#if B200FE_C0_SHFL
+  for (int i = kTw2Table; i < kTw2Total; ++i) tw[i] = make_float2(0.f, 0.f);
+  fill_c0_lane_table(tw.data() + kTw2Table);
+#endif
   CK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_mel_w, mw.data(), mw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_mel_lo, mlo.data(), mlo.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -670,7 +676,7 @@ int b200fe_create(const b200fe_config* cfg, const float* cmvn_host, b200fe_handl
 
 void b200fe_destroy(b200fe_handle* h) {
   if (!h) return;
-  cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo);
+  cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_twiddle_stream); cudaFree(h->d_mel_w); cudaFree(h->d_mel_lo);
   cudaFree(h->d_cmvn); cudaFree(h->d_cmvn_il); cudaFree(h->d_short_mel);
   for (auto& pr : h->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& e : h->event_pool) cudaEventDestroy(e);

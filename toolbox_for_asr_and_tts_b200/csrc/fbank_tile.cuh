@@ -246,7 +246,7 @@ using MelShapeParaformer = MelShapeFixed<3, 2, 5, 9>;
 
 // One round of the interval mel: lane <-> interval 31 r + lane.  CNT >= 0: compile-time trip count (fully unrolled).
 // epi(iv, a, b, c, d) receives the natural-log mel energies of filter iv for the warp's 4 frames.
-template <int CNT, class EPI>
+template <int CNT, bool COMPACT, class EPI>
 __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, int base, const float2* pg, int lane, int M,
                                           float log_floor, EPI&& epi) {
   const int cnt = CNT >= 0 ? CNT : cnt_rt;
@@ -269,7 +269,7 @@ __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, 
   auto body = [&](int q) {
 #if B200FE_MEL_COMPACT
     float2 w;
-    if constexpr (CNT >= 0) {
+    if constexpr (CNT >= 0 && COMPACT) {
       w.x = __ldg(wu + 32 * q);
       w.y = fminf(kMelScale - w.x, w.x * 0x1p100f);
     } else {
@@ -304,13 +304,16 @@ __device__ __forceinline__ void mel_round(const MelTab& mel, int r, int cnt_rt, 
 // Sparse mel + log for the warp's 4 frames.  lane <-> interval between two filter centres: every FFT bin lies in
 // exactly one interval and feeds the up-slope of filter j and the down-slope of filter j-1, so each bin is read once:
 // energy[m] = up[m] + down[m+1].  Trip counts are warp-uniform (zero-padded weights): no divergence.
-template <class MELS, class EPI>
+// COMPACT = false keeps the (up, down) weight pairs also for a fixed-shape bank: the streaming tick is latency-bound and
+// the three dependent operations that derive the second weight cost it more than the halved weight bytes save
+// (measured: 512 streams 46.65 vs 47.2 us per tick).
+template <class MELS, bool COMPACT = (B200FE_MEL_COMPACT != 0), class EPI>
 __device__ __forceinline__ void mel_stage(const MelTab& mel, const float4* pbuf4, int lane, int M, float log_floor, EPI&& epi) {
   const float2* pg = reinterpret_cast<const float2*>(pbuf4);
   if constexpr (MELS::kFixed) {
     static_for<0, MELS::kRounds>([&](auto ic) {
       constexpr int r = decltype(ic)::value;
-      mel_round<MELS::cnt(r)>(mel, r, 0, MELS::base(r), pg, lane, M, log_floor, epi);
+      mel_round<MELS::cnt(r), COMPACT>(mel, r, 0, MELS::base(r), pg, lane, M, log_floor, epi);
     });
   } else {
 #pragma unroll 1
@@ -319,7 +322,7 @@ __device__ __forceinline__ void mel_stage(const MelTab& mel, const float4* pbuf4
 #pragma unroll
       for (int t = 1; t < kMelRounds; ++t)
         if (r == t) { cnt = mel.cnt[t]; base = mel.base[t]; }
-      mel_round<-1>(mel, r, cnt, base, pg, lane, M, log_floor, epi);
+      mel_round<-1, false>(mel, r, cnt, base, pg, lane, M, log_floor, epi);
     }
   }
 }
@@ -552,6 +555,11 @@ __device__ __forceinline__ void quad_stage1(const float* xA, bool vA, bool vB, i
 // and the power spectra of the group's two frames into pbuf4 = [2 groups][256 bins] x (frame A, frame B), which
 // aliases both groups' transpose buffers.  The caller has passed a __syncwarp since the last reader of that memory;
 // on return every lane has passed a __syncwarp after the last write.
+// C0LANE: column 0 by the FFT across the lanes of a group (c0_row = fft_c0s_row of a table filled by
+// fill_c0_lane_table); false: by broadcast row loads through shared memory (c0_row = fft_c0_row of the [8][kC0Pitch]
+// table).  The streaming tick keeps the latter: its CTAs walk through the quad's phases together, so the four dependent
+// shuffle stages sit on its critical path (measured: 512 streams 46.5 vs 47.2 us per tick).
+template <bool C0LANE = (B200FE_C0_SHFL != 0)>
 __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[16], f2 y0, f2 y16, float4* yg, float4* pbuf4,
                                             const float2* tw_row, const float2* c0_row, int j, int grp_in_warp) {
   // 64-bit stores (the register allocator does not form the aligned quads a 128-bit store needs).  Slots 8..15 hold
@@ -567,18 +575,16 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
     yg2[15 * 2 * kYPitch + hr] = y16;
     yg2[15 * 2 * kYPitch + hi] = make_float2(0.f, 0.f);
   }
-#if !B200FE_C0_SHFL
-  reinterpret_cast<float2*>(yg + 16 * kYPitch)[j] = y0;
-#endif
+  if constexpr (!C0LANE) reinterpret_cast<float2*>(yg + 16 * kYPitch)[j] = y0;
 #if B200FE_S2_TW_EARLY
   float2 tw_e[16];
   float4 c0w_e[4];
 #pragma unroll
   for (int h = 0; h < 16; ++h) tw_e[h] = tw_row[h];
-#if !B200FE_C0_SHFL
+  if constexpr (!C0LANE) {
 #pragma unroll
-  for (int h = 0; h < 4; ++h) c0w_e[h] = reinterpret_cast<const float4*>(c0_row)[h];
-#endif
+    for (int h = 0; h < 4; ++h) c0w_e[h] = reinterpret_cast<const float4*>(c0_row)[h];
+  }
 #endif
   __syncwarp();
 
@@ -618,13 +624,14 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
   }
   // ---- column 0 of the lane's OWN group (half-warp): lanes 2t and 2t+1 both sum the 16 real bins Y_c[0] against
   //      W16^(c t), folded to 8 terms (the pair's identical loads merge; the even lane stores)
-#if B200FE_C0_SHFL
+  int t0;
+  f2 p0;
+  if constexpr (C0LANE) {
   // ---- column 0 of the lane's OWN group: X[32 t] = 2 sum_j Y_j[0] W16^(j t) is a 16-point DFT of the REAL values the
   //      16 lanes hold in y0: four butterfly stages over xor-shuffles (2 + 4 + 4 + 4 shuffles for the packed pair of
   //      frames), the lane's three twiddles from the table, signs from the lane's bits.  Lane j ends up with bin
   //      32 * bitrev4(j); bins 0..224 sit on the even lanes.
-  const int t0 = (int)(__brev((unsigned)j) >> 28);      // bitrev4(j): below 8 on the even lanes, the ones that store
-  f2 p0;
+  t0 = (int)(__brev((unsigned)j) >> 28);      // bitrev4(j): below 8 on the even lanes, the ones that store
   {
     const unsigned jb = (unsigned)j << 28;               // bit 3 of j in the sign position
     auto sgn = [&](int s) { return __uint_as_float(0x3f800000u | ((jb << s) & 0x80000000u)); };
@@ -648,9 +655,8 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
     ci = fma2s(ci, sgn(3), xchg(ci, 1));
     p0 = fma2(cr, cr, mul2(ci, ci));
   }
-#else
-  const int t0 = (lane >> 1) & 7;
-  f2 p0;
+  } else {
+  t0 = (lane >> 1) & 7;
   {
     const float4* u4 = reinterpret_cast<const float4*>(yg + 16 * kYPitch);   // 16 x (A, B)
     const float4* w4 = reinterpret_cast<const float4*>(c0_row);   // fft_c0_row: row t0
@@ -672,7 +678,7 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
     }
     p0 = fma2(cr, cr, mul2(ci, ci));
   }
-#endif
+  }
   fft_dit2<16>(ar, ai);
   __syncwarp();   // every lane has consumed the transpose buffers: the spectra may overwrite them
   {
@@ -690,7 +696,7 @@ __device__ __forceinline__ void quad_stage2(const f2 (&zr)[16], const f2 (&zi)[1
 }
 
 // Log-mel of tile-local frames 4*quad .. 4*quad+3 into logmel[F][M] (shared memory): tile and streaming kernels.
-template <int NROWS, bool EXACT, bool DITHER, class MELS>
+template <int NROWS, bool EXACT, bool DITHER, class MELS, bool LANE_OPT = true>
 __device__ __forceinline__ void fbank_quad(const float* x_base, int F, int quad,
                                            int S, int L, const float (&win)[NROWS + 1], float4* yg, float4* pbuf4,
                                            const float2* tw_row, const float2* c0_row, const MelTab& mel, int M,
@@ -704,9 +710,9 @@ __device__ __forceinline__ void fbank_quad(const float* x_base, int F, int quad,
   quad_stage1<NROWS, EXACT, DITHER>(x_base + fA * S, vA, vB, S, L, win, preemph, remove_dc, dither, seed, utt,
                                     frame_abs0 + (unsigned)fA, j, g, zr, zi, y0, y16);
   __syncwarp();   // earlier readers of the (aliased) buffer are done
-  quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
+  quad_stage2<LANE_OPT && (B200FE_C0_SHFL != 0)>(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
   const int fr = 4 * quad;
-  mel_stage<MELS>(mel, pbuf4, lane, M, log_floor, [&](int iv, float a, float b, float c, float d) {
+  mel_stage<MELS, LANE_OPT && (B200FE_MEL_COMPACT != 0)>(mel, pbuf4, lane, M, log_floor, [&](int iv, float a, float b, float c, float d) {
     float* dst = logmel + fr * M + iv;
     if (fr < F) dst[0] = a;
     if (fr + 1 < F) dst[M] = b;

@@ -119,7 +119,7 @@ int b200fe_stream_push_stats(b200fe_handle* h, void* state_dev, int n_streams, i
   p.frame_len = h->L; p.frame_shift = h->S; p.n_mels = h->cfg.n_mels; p.lfr_m = h->cfg.lfr_m; p.lfr_n = h->cfg.lfr_n;
   p.e_cap = e_cap; p.preemph = h->cfg.preemphasis; p.remove_dc = h->cfg.remove_dc_offset; p.log_floor = h->cfg.log_floor;
   p.dither = h->cfg.dither / (h->cfg.upscale_samples ? 32768.f : 1.f); p.seed = 0;
-  p.window = h->d_window; p.twiddle = h->d_twiddle; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_rounds = h->mel_rounds;
+  p.window = h->d_window; p.twiddle = h->d_twiddle_stream; p.mel_w = h->d_mel_w; p.mel_lo = h->d_mel_lo; p.mel_rounds = h->mel_rounds;
   for (int r = 0; r < kMelRounds; ++r) { p.mel_cnt[r] = h->mel_cnt[r]; p.mel_base[r] = h->mel_base[r]; } p.cmvn = h->d_cmvn;
   const bool dither = h->cfg.dither != 0.f;
   if (h->L == 400 && h->mel_paraformer) return launch_stream<25, true, MelShapeParaformer>(h, p, smem, dither, (cudaStream_t)stream);

@@ -196,7 +196,7 @@ stream_push_kernel(const StreamParams p) {
   float4* yg = xbuf + warp * kYWarpF4 + grp_in_warp * kYGroupF4;
   float4* pbuf4 = xbuf + warp * kYWarpF4;
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = fft_c0s_row(tw_s, j);
+  const float2* c0_row = fft_c0_row(tw_s, j);   // StreamParams::twiddle carries the [8][kC0Pitch] column-0 table
   if constexpr (PERQUAD) {
     // every warp fetches, transforms and mel-projects its own quads: no CTA-wide staging
     float* buf = e_s + warp * kQuadBuf;
@@ -212,10 +212,10 @@ stream_push_kernel(const StreamParams p) {
         quad_stage1<NROWS, EXACT, DITHER>(buf + a_off + fA * S, vA, vB, S, L, win, p.preemph, p.remove_dc, p.dither,
                                           p.seed, (unsigned)sid, (unsigned)(t_seen + 4 * quad + fA), j, g, zr, zi, y0, y16);
         __syncwarp();
-        quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
+        quad_stage2<false>(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
       }
       float* dst = logmel_s + (cache_len + 4 * quad) * M;
-      mel_stage<MELS>(mel, pbuf4, lane, M, p.log_floor, [&](int iv, float a, float b2, float c, float d) {
+      mel_stage<MELS, false>(mel, pbuf4, lane, M, p.log_floor, [&](int iv, float a, float b2, float c, float d) {
         if (nFq > 0) dst[iv] = a;
         if (nFq > 1) dst[M + iv] = b2;
         if (nFq > 2) dst[2 * M + iv] = c;
@@ -225,7 +225,7 @@ stream_push_kernel(const StreamParams p) {
     }
   } else {
     for (int quad = warp; 4 * quad < nf; quad += kWarps)
-      fbank_quad<NROWS, EXACT, DITHER, MELS>(e_s, nf, quad, S, L, win, yg, pbuf4, tw_row, c0_row, mel, M,
+      fbank_quad<NROWS, EXACT, DITHER, MELS, false>(e_s, nf, quad, S, L, win, yg, pbuf4, tw_row, c0_row, mel, M,
                                              p.preemph, p.remove_dc, p.log_floor, p.dither, p.seed, (unsigned)sid,
                                              (unsigned)t_seen, logmel_s + cache_len * M, j, grp_in_warp, lane);
   }
@@ -594,7 +594,7 @@ stream_quad_kernel(const StreamParams p) {
   float4* pbuf4 = xbuf + warp * kYWarpF4;
   float* lm_s = reinterpret_cast<float*>(pbuf4 + kSpecF4);   // log-mel staging tile, behind the warp's spectra
   const float2* tw_row = fft_twiddle_row<NROWS>(tw_s, j, grp_in_warp);
-  const float2* c0_row = fft_c0s_row(tw_s, j);
+  const float2* c0_row = fft_c0_row(tw_s, j);   // StreamParams::twiddle carries the [8][kC0Pitch] column-0 table
   const int4* ticks = p.lay.tick(p.state);
 
   const int q_max = p.lay.q_max;
@@ -697,9 +697,9 @@ stream_quad_kernel(const StreamParams p) {
                                           p.seed, dsid, dframe, j, g, zr, zi, y0, y16);
         __syncwarp();   // every lane is done with the sample buffer and with the previous item's staging tile
         in_flight = next_copy();
-        quad_stage2(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
+        quad_stage2<false>(zr, zi, y0, y16, yg, pbuf4, tw_row, c0_row, j, grp_in_warp);
       }
-      mel_stage<MELS>(mel, pbuf4, lane, M, p.log_floor, [&](int iv, float a, float b2, float c, float dd) {
+      mel_stage<MELS, false>(mel, pbuf4, lane, M, p.log_floor, [&](int iv, float a, float b2, float c, float dd) {
         lm_s[iv] = a;
         lm_s[M + iv] = b2;
         lm_s[2 * M + iv] = c;
