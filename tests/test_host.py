@@ -274,3 +274,38 @@ def test_host_affinity_bind_and_restore_round_trip():
         t.join()
         os.sched_setaffinity(0, before)
     assert hostaffinity.ingest_threads(1) >= 2
+
+
+def test_work_claim_of_the_fused_kernel_is_not_warp_aggregated():
+    """ptxas turns an atomic add on a provably warp-uniform address into a warp-aggregated sequence (vote, leader
+    atomic, SHFL of the result); the shuffle waits for the atomic where it is issued, which costs the fused kernel
+    1.3 % (profiles/r2_kernel_ab.txt).  fbank_warp.cuh routes the counter's address through a value the compiler cannot
+    prove uniform; this guards the shipped SASS: one ATOMG per float32 instantiation, no vote / shuffle behind it, and
+    the bulk copy (UBLKCP) and packed arithmetic (FFMA2) the design rests on are there."""
+    import re
+    import shutil
+    from toolbox_for_asr_and_tts_b200 import _build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not _build.LIB.exists():
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run([cuobjdump, "-sass", str(_build.LIB)], capture_output=True, text=True, check=True).stdout
+    kernels = {}
+    name = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            continue
+        if name and "fbank_warp_kernel" in name and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+            kernels.setdefault(name, []).append(re.sub(r"^\s+/\*[0-9a-f]+\*/\s+", "", line).split(";")[0].strip())
+    shipped = [k for k in kernels if "MelShapeFixedILi3ELi2ELi5ELi8EEELi10EfLb0" in k and "ILi25ELb1ELb0E" in k]
+    assert len(shipped) == 1, sorted(kernels)[:4]
+    ins = kernels[shipped[0]]
+    ops = [re.sub(r"^@!?U?P\w+\s+", "", i).split()[0] for i in ins]
+    atom = [i for i, o in enumerate(ops) if o.startswith("ATOMG")]
+    assert len(atom) == 1
+    behind = ops[atom[0] + 1:atom[0] + 8]
+    assert not any(o.startswith(("SHFL", "VOTE", "POPC")) for o in behind), behind
+    assert not any(o.startswith(("VOTE", "POPC", "FLO")) for o in ops[max(0, atom[0] - 8):atom[0]])
+    assert sum(o.startswith("UBLKCP") for o in ops) >= 1 and sum(o.startswith("FFMA2") for o in ops) > 300
+    assert not any(o.startswith(("LDL", "STL")) for o in ops)      # no spills
